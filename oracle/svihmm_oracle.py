@@ -1,0 +1,334 @@
+"""Float64 CPU oracle for the SVI-HMM local E-step path.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module, and only as the
+checker.  The product package (pysvihmm_b200) never imports it.
+
+It restates, in plain numpy float64 and in the reference's own *log domain*
+(np.logaddexp.reduce, no scaling table), the algorithm of dillonalaird/pysvihmm
+for the path named by BASELINE.json.  Every function cites the reference
+file:line it follows (paths relative to /root/reference).  The recursions loop
+over t in Python exactly like the reference but are vectorised over a leading
+batch axis of windows so that B windows cost one pass.
+
+PINNING: the reference ships no golden vectors, so this
+oracle is pinned against outputs of the reference itself: oracle/build_ref.py
+makes the reference importable on Python 3 (mechanical patches only),
+tests/golden/make_golden.py runs reference classes hmmsgd_metaobs.VBHMM /
+hmmbatchcd.VBHMM on seeded inputs and commits their outputs as fixtures, and
+tests/test_oracle_golden.py checks this file against them (agreement ~1e-13).
+Extensions that have no reference implementation (diagonal Gaussian, GMM
+emissions) are pinned only indirectly through Gaussian(D=1) calls and say
+"parity unpinned" where that is so.
+"""
+import numpy as np
+from scipy.special import digamma
+
+EPS = 1e-9            # hmmbase.py:30, hmmsgd_metaobs.py:26
+WEPS = 1e-12          # pybasicbayes/distributions.py:22
+
+
+# --------------------------------------------------------------------------
+# globals -> per-step constants
+# --------------------------------------------------------------------------
+def stationary_init(var_tran):
+    """hmmsgd_metaobs.py:413-418.  |top eigenvector of A_mean^T|, unit L2 norm
+    (quirk Q3: it is *not* renormalised to a distribution)."""
+    A_mean = var_tran / np.sum(var_tran, axis=1)[:, None]
+    ew, ev = np.linalg.eig(A_mean.T)
+    ew_dec = np.argsort(ew)[::-1]
+    return np.abs(ev[:, ew_dec[0]])
+
+
+def mod_params(var_init, var_tran):
+    """hmmsgd_metaobs.py:502-504 / hmmbase.py:214-216."""
+    mod_init = digamma(var_init + EPS) - digamma(np.sum(var_init) + EPS)
+    tran_sum = np.sum(var_tran, axis=1)
+    mod_tran = digamma(var_tran + EPS) - digamma(tran_sum[:, None] + EPS)
+    return mod_init, mod_tran
+
+
+# --------------------------------------------------------------------------
+# emission expected log-likelihoods
+# --------------------------------------------------------------------------
+def gaussian_loglmbdatilde(sigma_mf, nu_mf):
+    """pybasicbayes/distributions.py:361-366."""
+    D = sigma_mf.shape[0]
+    chol = np.linalg.cholesky(sigma_mf)
+    return digamma((nu_mf - np.arange(D)) / 2.).sum() + D * np.log(2) \
+        - 2 * np.log(chol.diagonal()).sum()
+
+
+def gaussian_ell(x, mu_mf, sigma_mf, kappa_mf, nu_mf):
+    """pybasicbayes/distributions.py:351-359 (Gaussian.expected_log_likelihood).
+    x: (..., D) -> (...)."""
+    D = len(mu_mf)
+    shp = x.shape[:-1]
+    xc = np.reshape(x, (-1, D)) - mu_mf
+    xs = np.linalg.solve(np.linalg.cholesky(sigma_mf), xc.T)
+    out = gaussian_loglmbdatilde(sigma_mf, nu_mf) / 2 - D / (2 * kappa_mf) \
+        - nu_mf / 2 * np.einsum('ij,ij->j', xs, xs) - D / 2 * np.log(2 * np.pi)
+    return out.reshape(shp)
+
+
+def diag_gaussian_ell(x, mu_mf, sig_mf, kappa_mf, nu_mf):
+    """EXTENSION (BASELINE config 2; no mean-field DiagonalGaussian exists in the
+    reference, pybasicbayes/distributions.py:666-797 is Gibbs/ML only).  Defined
+    as a product of D independent one-dimensional NIW factors, i.e.
+    sum_d Gaussian_{1-D}.expected_log_likelihood(x_d) with formula :351-366 at
+    D=1.  mu_mf, sig_mf, kappa_mf, nu_mf: (D,) each.  Pinned only through
+    reference Gaussian(D=1) calls; end-to-end parity unpinned."""
+    out = 0.
+    for d in range(x.shape[-1]):
+        out = out + gaussian_ell(x[..., d:d + 1], mu_mf[d:d + 1],
+                                 np.array([[sig_mf[d]]]), kappa_mf[d], nu_mf[d])
+    return out
+
+
+def categorical_ell(x, alpha_mf):
+    """pybasicbayes/distributions.py:1383-1386."""
+    return digamma(alpha_mf[x]) - digamma(alpha_mf.sum())
+
+
+def lliks_gaussian(xw, emit):
+    """hmmsgd_metaobs.py:508-509: per state expected_log_likelihood, then
+    np.nan_to_num (a NaN row gives ll = 0 = 'missing').
+    xw: (B,T,D); emit: list of K dicts(mu, sigma, kappa, nu) -> (B,T,K)."""
+    B, T, D = xw.shape
+    ll = np.empty((B, T, len(emit)))
+    with np.errstate(invalid='ignore'):
+        for k, e in enumerate(emit):
+            if np.ndim(e['sigma']) == 2:
+                ll[:, :, k] = gaussian_ell(xw, e['mu'], e['sigma'], e['kappa'], e['nu'])
+            else:
+                ll[:, :, k] = diag_gaussian_ell(xw, e['mu'], e['sigma'], e['kappa'], e['nu'])
+    return np.nan_to_num(ll)
+
+
+# --------------------------------------------------------------------------
+# messages (log domain, exactly the reference's recursions)
+# --------------------------------------------------------------------------
+def forward_msgs(ll, mod_init, mod_tran):
+    """hmmsgd_metaobs.py:775-803 / hmmbase.py:266-295.  ll: (B,T,K)."""
+    B, T, K = ll.shape
+    lalpha = np.empty((B, T, K))
+    lalpha[:, 0] = mod_init + ll[:, 0]
+    ltT = mod_tran.T
+    for t in range(1, T):
+        # lalpha[t,j] = logsumexp_i(lalpha[t-1,i] + ltran[i,j]) + ll[t,j]
+        lalpha[:, t] = np.logaddexp.reduce(lalpha[:, t - 1][:, None, :] + ltT[None], axis=2) + ll[:, t]
+    return lalpha
+
+
+def backward_msgs(ll, mod_tran):
+    """hmmsgd_metaobs.py:828-855 / hmmbase.py:297-320."""
+    B, T, K = ll.shape
+    lbeta = np.empty((B, T, K))
+    lbeta[:, T - 1] = 0.
+    for t in range(T - 2, -1, -1):
+        lbeta[:, t] = np.logaddexp.reduce(
+            mod_tran[None] + (lbeta[:, t + 1] + ll[:, t + 1])[:, None, :], axis=2)
+    return lbeta
+
+
+def marginals(lalpha, lbeta):
+    """hmmsgd_metaobs.py:516-519 / hmmbase.py:226-229."""
+    v = lalpha + lbeta
+    v = v - np.max(v, axis=-1, keepdims=True)
+    v = np.exp(v)
+    return v / np.sum(v, axis=-1, keepdims=True)
+
+
+def local_update(xw, var_init, var_tran, emit):
+    """hmmsgd_metaobs.py:487-519 on a batch of windows xw (B,T,D).
+    Returns dict(ll, lalpha, lbeta, var_x)."""
+    mod_init, mod_tran = mod_params(var_init, var_tran)
+    ll = lliks_gaussian(xw, emit)
+    lalpha = forward_msgs(ll, mod_init, mod_tran)
+    lbeta = backward_msgs(ll, mod_tran)
+    return dict(ll=ll, lalpha=lalpha, lbeta=lbeta, var_x=marginals(lalpha, lbeta),
+                mod_init=mod_init, mod_tran=mod_tran)
+
+
+def local_lower_bound(lalpha):
+    """hmmsgd_metaobs.py:257-271 (quirk Q4: sums logsumexp over *all* t)."""
+    return np.sum(np.logaddexp.reduce(lalpha, axis=-1), axis=-1)
+
+
+def log_Z(lalpha):
+    """True log normaliser of one window = logsumexp_k lalpha[T-1,k]."""
+    return np.logaddexp.reduce(lalpha[..., -1, :], axis=-1)
+
+
+def exact_xi_stat(res):
+    """NOT reference behaviour (the reference uses the product of marginals,
+    quirk Q1).  Sum over t=1..T-1 of the true pairwise posterior
+    xi_t[i,j] ~ exp(lalpha[t-1,i] + ltran[i,j] + ll[t,j] + lbeta[t,j])."""
+    la, lb, ll, lt = res['lalpha'], res['lbeta'], res['ll'], res['mod_tran']
+    B, T, K = ll.shape
+    out = np.zeros((B, K, K))
+    for t in range(1, T):
+        lx = la[:, t - 1][:, :, None] + lt[None] + (ll[:, t] + lb[:, t])[:, None, :]
+        lx -= lx.max(axis=(1, 2), keepdims=True)
+        x = np.exp(lx)
+        out += x / x.sum(axis=(1, 2), keepdims=True)
+    return out
+
+
+# --------------------------------------------------------------------------
+# sufficient statistics
+# --------------------------------------------------------------------------
+def tran_stat(var_x, wrap):
+    """hmmsgd_metaobs.py:876-878 (wrap=True: the index t-loff-1 = -1 at t=loff
+    wraps around, quirk Q2) or hmmbatchcd.py:182-184 (wrap=False).
+    var_x: (B,T,K) -> (B,K,K) product-of-marginals statistic (quirk Q1)."""
+    prev = np.roll(var_x, 1, axis=1) if wrap else var_x[:, :-1]
+    cur = var_x if wrap else var_x[:, 1:]
+    return np.einsum('bti,btj->bij', prev, cur)
+
+
+def niw_suffstats(xw, w):
+    """util.py:73-83 for one state.  xw: (n,D), w: (n,) -> [xbar, neff, S, neff]."""
+    tmp = w[:, None] * xw
+    return [np.sum(tmp, axis=0), w.sum(), xw.T.dot(tmp), w.sum()]
+
+
+def intermediate_pars(var_x, xw, maskw, prior_tran, wrap=True):
+    """hmmsgd_metaobs.py:857-904 for ONE window.  var_x (T,K), xw (T,D),
+    maskw (T,) bool.  Returns A_inter (K,K) (prior added per window, quirk Q5)
+    and per-state [sum w x, sum w, sum w x x^T, sum w]."""
+    A_inter = prior_tran + tran_stat(var_x[None], wrap)[0] - 1.
+    inds = np.logical_not(maskw)
+    emit_inter = [niw_suffstats(xw[inds], var_x[inds, k]) for k in range(var_x.shape[1])]
+    return A_inter, emit_inter
+
+
+def diag_suffstats(xw, w):
+    """EXTENSION: per-dimension version of util.py:73-83 (D independent 1-D NIWs)."""
+    tmp = w[:, None] * xw
+    n = w.sum()
+    return [np.sum(tmp, axis=0), n, np.sum(tmp * xw, axis=0), n]
+
+
+# --------------------------------------------------------------------------
+# NIW natural <-> moment parameters and the global steps
+# --------------------------------------------------------------------------
+def niw_natural(mu, sigma, kappa, nu):
+    """util.py:28-37 (follows the code: eta3 = sigma + kappa mu mu^T)."""
+    p = len(mu)
+    return [kappa * mu, kappa, sigma + np.outer(mu, mu) * kappa, nu + 2 + p]
+
+
+def niw_moment(e1, e2, e3, e4):
+    """util.py:40-60 -> dict(mu, sigma, kappa, nu)."""
+    p = len(e1)
+    mu = e1 / e2
+    kappa = e2
+    return dict(mu=mu, sigma=e3 - np.outer(mu, mu) * kappa, kappa=kappa, nu=e4 - 2 - p)
+
+
+def diag_natural(mu, sig, kappa, nu):
+    """EXTENSION: util.py:28-37 applied per dimension with p = 1."""
+    return [kappa * mu, kappa, sig + mu * mu * kappa, nu + 3.]
+
+
+def diag_moment(e1, e2, e3, e4):
+    mu = e1 / e2
+    return dict(mu=mu, sigma=e3 - mu * mu * e2, kappa=e2, nu=e4 - 3.)
+
+
+def svi_global_update(var_tran, emit, prior_emit, A_inter, emit_inter, lrate, T_full, L, S):
+    """hmmsgd_metaobs.py:1010-1069 (non-adagrad branch).
+    emit / prior_emit: lists of dict(mu, sigma, kappa, nu); emit_inter[k] =
+    [e1,e2,e3,e4] summed over the minibatch.  Returns (var_tran_new, emit_new)."""
+    bfact = (T_full - 2 * L - 1) / (2. * L * S)
+    nats_new = (1. - lrate) * (var_tran - 1.) + lrate * bfact * A_inter
+    var_tran_new = nats_new + 1.
+    bfact = (T_full - 2 * L - 1) / ((2. * L + 1.) * S)
+    emit_new = []
+    for k in range(len(emit)):
+        full = np.ndim(emit[k]['sigma']) == 2
+        nat, mom = (niw_natural, niw_moment) if full else (diag_natural, diag_moment)
+        old = nat(emit[k]['mu'], emit[k]['sigma'], emit[k]['kappa'], emit[k]['nu'])
+        pri = nat(prior_emit[k]['mu'], prior_emit[k]['sigma'], prior_emit[k]['kappa'],
+                  prior_emit[k]['nu'])
+        new = [(1. - lrate) * o + lrate * (p + bfact * e)
+               for o, p, e in zip(old, pri, emit_inter[k])]
+        emit_new.append(mom(*new))
+    return var_tran_new, emit_new
+
+
+def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_emit,
+                       lrate, L, S=None, wrap=True, mask_ll=False):
+    """One global step of hmmsgd_metaobs.VBHMM.infer (:396-439) given the window
+    start indices `starts` (window b = obs[starts[b] : starts[b]+T]).
+    Returns dict with var_x (B,T,K), A_inter, emit_inter, lb, var_tran_new, emit_new."""
+    T_full = obs.shape[0]
+    K = var_tran.shape[0]
+    S = len(starts) if S is None else S
+    idx = np.asarray(starts)[:, None] + np.arange(T)[None]
+    xw = obs[idx]
+    mw = mask[idx] if mask is not None else np.zeros(idx.shape, bool)
+    if mask_ll:                      # hmmsgd_metaobs.py:1167-1168 style NaN-masking
+        xw = xw.copy()
+        xw[mw] = np.nan
+    var_init = stationary_init(var_tran)
+    res = local_update(xw, var_init, var_tran, emit)
+    A_inter = np.zeros_like(var_tran)
+    emit_inter = None
+    for b in range(len(starts)):
+        xb = np.nan_to_num(xw[b]) if mask_ll else xw[b]
+        A_i, e_i = intermediate_pars(res['var_x'][b], xb, mw[b], prior_tran, wrap) \
+            if np.ndim(emit[0]['sigma']) == 2 else _intermediate_pars_diag(
+                res['var_x'][b], xb, mw[b], prior_tran, wrap)
+        A_inter += A_i                                           # :430
+        if emit_inter is None:
+            emit_inter = [[np.array(v, dtype=float) for v in e] for e in e_i]
+        else:
+            for k in range(K):                                   # :432-433
+                for j in range(4):
+                    emit_inter[k][j] = emit_inter[k][j] + e_i[k][j]
+    lb = float(np.sum(local_lower_bound(res['lalpha'])))         # :436
+    var_tran_new, emit_new = svi_global_update(var_tran, emit, prior_emit, A_inter,
+                                               emit_inter, lrate, T_full, L, S)
+    res.update(A_inter=A_inter, emit_inter=emit_inter, lb=lb, logZ=log_Z(res['lalpha']),
+               var_tran_new=var_tran_new, emit_new=emit_new, var_init=var_init)
+    return res
+
+
+def _intermediate_pars_diag(var_x, xw, maskw, prior_tran, wrap):
+    A_inter = prior_tran + tran_stat(var_x[None], wrap)[0] - 1.
+    inds = np.logical_not(maskw)
+    return A_inter, [diag_suffstats(xw[inds], var_x[inds, k]) for k in range(var_x.shape[1])]
+
+
+# --------------------------------------------------------------------------
+# batch coordinate ascent (BASELINE config 1)
+# --------------------------------------------------------------------------
+def niw_posterior(prior, xw, w):
+    """pybasicbayes/distributions.py:240-276 (+:324-329): conjugate NIW update from
+    weighted (n, xbar, centred scatter); keeps the prior when n <= weps."""
+    n = w.sum()
+    if not n > WEPS:
+        return dict(mu=prior['mu'], sigma=prior['sigma'], kappa=prior['kappa'], nu=prior['nu'])
+    xbar = np.dot(w, xw) / n
+    c = xw - xbar
+    sumsq = np.dot(c.T, w[:, None] * c)
+    k0, m0 = prior['kappa'], prior['mu']
+    return dict(mu=k0 / (k0 + n) * m0 + n / (k0 + n) * xbar,
+                sigma=prior['sigma'] + sumsq + k0 * n / (k0 + n) * np.outer(xbar - m0, xbar - m0),
+                kappa=k0 + n, nu=prior['nu'] + n)
+
+
+def batch_cavi_step(obs, mask, var_init, var_tran, emit, prior_init, prior_tran, prior_emit):
+    """One iteration of hmmbatchcd.VBHMM.infer (:135-141): base local_update
+    (hmmbase.py:201-229) then global_update (hmmbatchcd.py:172-189)."""
+    res = local_update(obs[None], var_init, var_tran, emit)
+    q = res['var_x'][0]
+    new_init = prior_init + q[0]
+    new_tran = prior_tran + tran_stat(q[None], wrap=False)[0]
+    inds = np.logical_not(mask) if mask is not None else np.ones(len(obs), bool)
+    new_emit = [niw_posterior(prior_emit[k], obs[inds], q[inds, k]) for k in range(q.shape[1])]
+    res.update(var_init_new=new_init, var_tran_new=new_tran, emit_new=new_emit,
+               lZ=float(local_lower_bound(res['lalpha'])[0]))
+    return res

@@ -1,0 +1,219 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by running the REFERENCE ITSELF (patched to Python 3
+by oracle/build_ref.py; arithmetic untouched) on seeded inputs.
+
+Run in the build container only (needs /root/reference):
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+The .npz files written next to this script are committed; nothing at test time
+reads /root/reference or oracle/_ref.
+
+Every fixture stores the inputs (obs, mask, window starts, initial globals,
+priors) and the reference's outputs (lliks, lalpha, lbeta, var_x per window,
+A_inter / emission statistics per window, post-update globals).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref")
+warnings.filterwarnings("ignore")
+sys.path.insert(0, REF)
+
+import hmmsgd_metaobs as HSGD          # noqa: E402
+import hmmbatchcd as HCD               # noqa: E402
+import gen_synthetic as GS             # noqa: E402
+from pybasicbayes.distributions import Gaussian   # noqa: E402
+
+
+def make_problem(seed, K, D, T_full, sep, miss=0.0):
+    """Synthetic series from reference gen_synthetic.generate_data (gen_synthetic.py:8-56)."""
+    rs = np.random.RandomState(seed)
+    tran = 0.9 * np.eye(K) + 0.1 / (K - 1) * (1 - np.eye(K))
+    mus = sep * rs.randn(K, D)
+    emit_true = [Gaussian(mu=mus[k], sigma=np.eye(D), mu_0=np.zeros(D), sigma_0=np.eye(D),
+                          kappa_0=1., nu_0=D + 2.) for k in range(K)]
+    np.random.seed(seed)
+    obs, sts, mask = GS.generate_data(tran, emit_true, T_full, miss=miss)
+    if mask is None:
+        mask = np.zeros(T_full, bool)
+    # initial variational emission parameters: perturbed truth, explicit (no prior sampling)
+    init = []
+    for k in range(K):
+        A = rs.randn(D, D) * 0.3
+        init.append(dict(mu=mus[k] + 0.5 * rs.randn(D),
+                         sigma=(2.0 * np.eye(D) + A.dot(A.T)),
+                         kappa=0.7 + rs.rand(), nu=D + 3. + 2 * rs.rand()))
+    prior = dict(mu=np.zeros(D), sigma=0.75 * np.cov(obs.T).reshape(D, D), kappa=0.01, nu=D + 2.)
+    init_tran = 1. + 5. * rs.rand(K, K)
+    return obs, sts, mask, init, prior, init_tran
+
+
+def emit_objects(init, prior):
+    """Reference objects: mu/sigma explicit, so var_emit = deepcopy has mu_mf=mu,
+    sigma_mf=sigma and (kappa_mf, nu_mf) given (distributions.py:195-212)."""
+    return np.array([Gaussian(mu=e['mu'].copy(), sigma=e['sigma'].copy(), mu_0=prior['mu'],
+                              sigma_0=prior['sigma'], kappa_0=prior['kappa'], nu_0=prior['nu'],
+                              kappa_mf=e['kappa'], nu_mf=e['nu']) for e in init])
+
+
+def pack_emit(prefix, objs, out):
+    out[prefix + "_mu"] = np.array([g.mu_mf for g in objs])
+    out[prefix + "_sigma"] = np.array([g.sigma_mf for g in objs])
+    out[prefix + "_kappa"] = np.array([g.kappa_mf for g in objs], dtype=float)
+    out[prefix + "_nu"] = np.array([g.nu_mf for g in objs], dtype=float)
+
+
+def svi_case(name, seed, K, D, T_full, L, mb_sz, sep, miss=0.0, maxit=2):
+    obs, sts, mask, init, prior, init_tran = make_problem(seed, K, D, T_full, sep, miss)
+    prior_emit = emit_objects(init, prior)
+    hmm = HSGD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7,
+                     metaobs_half=L, mb_sz=mb_sz, mask=mask, init_tran=init_tran.copy(),
+                     maxit=maxit, seed=seed)
+    out = dict(obs=obs, sts=sts, mask=mask, init_tran=init_tran, prior_tran=np.ones((K, K)),
+               prior_mu=prior['mu'], prior_sigma=prior['sigma'], prior_kappa=prior['kappa'],
+               prior_nu=prior['nu'], L=L, mb_sz=mb_sz, tau=1., kappa_lr=0.7, maxit=maxit)
+    pack_emit("init", hmm.var_emit, out)
+    rec = dict(starts=[], ll=[], lalpha=[], lbeta=[], var_x=[], var_init=[], A_i=[],
+               e1=[], e2=[], e3=[], lb=[])
+    glob = dict(var_tran=[], mu=[], sigma=[], kappa=[], nu=[], lrate=[])
+
+    lu, ip, gu, llb = hmm.local_update, hmm.intermediate_pars, hmm.global_update, hmm.local_lower_bound
+
+    def rec_local_update(metaobs=None):
+        lu(metaobs=metaobs)
+        rec['starts'].append(metaobs.i1)
+        rec['ll'].append(hmm.lliks.copy())
+        rec['lalpha'].append(hmm.lalpha.copy())
+        rec['lbeta'].append(hmm.lbeta.copy())
+        rec['var_x'].append(hmm.var_x.copy())
+        rec['var_init'].append(hmm.var_init.copy())
+
+    def rec_ip(metaobs=None):
+        A_i, e_i = ip(metaobs)
+        rec['A_i'].append(A_i.copy())
+        rec['e1'].append(np.array([e[0] for e in e_i]))
+        rec['e2'].append(np.array([e[1] for e in e_i], dtype=float))
+        rec['e3'].append(np.array([e[2] for e in e_i]))
+        return A_i, e_i
+
+    def rec_llb():
+        v = llb()
+        rec['lb'].append(v)
+        return v
+
+    def rec_gu(A_inter, emit_inter):
+        gu(A_inter, emit_inter)
+        glob['var_tran'].append(hmm.var_tran.copy())
+        glob['mu'].append(np.array([g.mu_mf for g in hmm.var_emit]))
+        glob['sigma'].append(np.array([g.sigma_mf for g in hmm.var_emit]))
+        glob['kappa'].append(np.array([g.kappa_mf for g in hmm.var_emit], dtype=float))
+        glob['nu'].append(np.array([g.nu_mf for g in hmm.var_emit], dtype=float))
+        glob['lrate'].append(hmm.lrate)
+
+    hmm.local_update, hmm.intermediate_pars = rec_local_update, rec_ip
+    hmm.global_update, hmm.local_lower_bound = rec_gu, rec_llb
+    # global_lower_bound needs the absent pymattutil (shimmed, unverifiable) -> skip it
+    hmm.global_lower_bound = lambda: 0.0
+    hmm.infer()
+    B = mb_sz
+    for k, v in rec.items():
+        a = np.array(v)
+        out["w_" + k] = a.reshape((maxit, B) + a.shape[1:])
+    for k, v in glob.items():
+        out["g_" + k] = np.array(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    q = out["w_var_x"]
+    print("%-22s K=%d D=%d T=%d B=%d it=%d  frac(max q<0.99)=%.2f  masked=%d" % (
+        name, K, D, 2 * L + 1, B, maxit, float(np.mean(q.max(-1) < 0.99)), int(mask.sum())))
+
+
+def cavi_case(name, seed, T, maxit=3):
+    """hmmbatchcd.VBHMM on test_hmmbatchcd.py:17-49-like data (two clusters, here
+    1.5 apart so the posteriors are not one-hot), explicit emission inits."""
+    K, D = 2, 2
+    rs = np.random.RandomState(seed)
+    sts = (np.arange(T) >= T // 2).astype(int)
+    obs = rs.randn(T, D) + 1.5 * sts[:, None]
+    mask = np.zeros(T, bool)
+    mask[rs.choice(T, T // 10, replace=False)] = True
+    prior = dict(mu=np.zeros(D), sigma=0.75 * np.cov(obs.T), kappa=0.01, nu=4.)
+    init = [dict(mu=np.array([-0.3, 0.2]), sigma=np.eye(D) * 2., kappa=0.01, nu=4.),
+            dict(mu=np.array([1.0, 1.3]), sigma=np.eye(D) * 2., kappa=0.01, nu=4.)]
+    prior_emit = emit_objects(init, prior)
+    hmm = HCD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, mask=mask, maxit=maxit,
+                    epsilon=0.0)
+    out = dict(obs=obs, sts=sts, mask=mask, prior_init=np.ones(K), prior_tran=np.ones((K, K)),
+               prior_mu=prior['mu'], prior_sigma=prior['sigma'], prior_kappa=prior['kappa'],
+               prior_nu=prior['nu'], init_var_init=hmm.var_init.copy(),
+               init_var_tran=hmm.var_tran.copy(), maxit=maxit)
+    pack_emit("init", hmm.var_emit, out)
+    rec = dict(var_x=[], lalpha=[], var_init=[], var_tran=[], mu=[], sigma=[], kappa=[], nu=[], lZ=[])
+    gu = hmm.global_update
+
+    def rec_gu():
+        gu()
+        rec['var_x'].append(hmm.var_x.copy())
+        rec['lalpha'].append(hmm.lalpha.copy())
+        rec['lZ'].append(np.sum(np.logaddexp.reduce(hmm.lalpha, axis=1)))
+        rec['var_init'].append(hmm.var_init.copy())
+        rec['var_tran'].append(hmm.var_tran.copy())
+        rec['mu'].append(np.array([g.mu_mf for g in hmm.var_emit]))
+        rec['sigma'].append(np.array([g.sigma_mf for g in hmm.var_emit]))
+        rec['kappa'].append(np.array([g.kappa_mf for g in hmm.var_emit], dtype=float))
+        rec['nu'].append(np.array([g.nu_mf for g in hmm.var_emit], dtype=float))
+
+    hmm.global_update = rec_gu
+    hmm.lower_bound = lambda: float(len(rec['lZ']))   # get_vlb needs absent pymattutil; never converge
+    hmm.infer()
+    for k, v in rec.items():
+        out["it_" + k] = np.array(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s CAVI T=%d iters=%d frac(max q<0.99)=%.2f" % (
+        name, T, len(rec['lZ']), float(np.mean(out["it_var_x"].max(-1) < 0.99))))
+
+
+def ell_1d_case(name, seed):
+    """Gaussian(D=1).expected_log_likelihood values: pins the diagonal-Gaussian
+    extension (product of 1-D NIW factors) to distributions.py:351-366."""
+    rs = np.random.RandomState(seed)
+    x = rs.randn(50, 1) * 2
+    mu, sig, kap, nu = rs.randn(6), 0.5 + rs.rand(6) * 3, 0.2 + rs.rand(6), 3. + 4 * rs.rand(6)
+    ell = np.empty((6, 50))
+    for i in range(6):
+        g = Gaussian(mu=mu[i:i + 1], sigma=np.array([[sig[i]]]), mu_0=np.zeros(1),
+                     sigma_0=np.eye(1), kappa_0=1., nu_0=3., kappa_mf=kap[i], nu_mf=nu[i])
+        ell[i] = g.expected_log_likelihood(x)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, mu=mu, sigma=sig, kappa=kap,
+                        nu=nu, ell=ell)
+    print("%-22s 1-D ELL table 6x50" % name)
+
+
+def gen_case(name, seed):
+    """gen_synthetic.generate_data (gen_synthetic.py:8-56) under the legacy global RNG."""
+    K, D, T = 4, 3, 400
+    rs = np.random.RandomState(seed)
+    tran = 0.9 * np.eye(K) + 0.1 / (K - 1) * (1 - np.eye(K))
+    mus = rs.randn(K, D)
+    A = rs.randn(K, D, D) * 0.3
+    sig = np.array([np.eye(D) + a.dot(a.T) for a in A])
+    emit = [Gaussian(mu=mus[k], sigma=sig[k], mu_0=np.zeros(D), sigma_0=np.eye(D), kappa_0=1.,
+                     nu_0=D + 2.) for k in range(K)]
+    np.random.seed(seed)
+    obs, sts, mask = GS.generate_data(tran, emit, T, miss=0.1)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), tran=tran, mus=mus, sigmas=sig, T=T,
+                        seed=seed, miss=0.1, obs=obs, sts=sts, mask=mask)
+    print("%-22s gen_synthetic T=%d masked=%d" % (name, T, int(mask.sum())))
+
+
+if __name__ == "__main__":
+    svi_case("svi_k3_d2_l5", seed=11, K=3, D=2, T_full=300, L=5, mb_sz=4, sep=0.6)
+    svi_case("svi_k5_d3_l20_mask", seed=12, K=5, D=3, T_full=600, L=20, mb_sz=6, sep=0.5, miss=0.15)
+    svi_case("svi_k16_d8_l50", seed=13, K=16, D=8, T_full=1500, L=50, mb_sz=3, sep=0.4, maxit=1)
+    svi_case("svi_k2_d2_l1", seed=14, K=2, D=2, T_full=60, L=1, mb_sz=5, sep=0.8, maxit=3)
+    cavi_case("cavi_k2_d2_t200", seed=21, T=200)
+    ell_1d_case("ell_1d", seed=31)
+    gen_case("gen_synthetic_k4", seed=8675309)

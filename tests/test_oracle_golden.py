@@ -1,0 +1,100 @@
+"""The oracle (oracle/svihmm_oracle.py) against outputs of the REFERENCE ITSELF
+(fixtures made by tests/golden/make_golden.py from the patched-to-py3 reference).
+CPU only.  Tolerances: float64 round-off (1e-10 relative)."""
+import numpy as np
+import pytest
+
+from oracle import svihmm_oracle as O
+from tests.helpers import SVI_CASES, emit_list, golden_prior_emit, load_golden
+
+RT, AT = 1e-10, 1e-12
+
+
+@pytest.mark.parametrize("name", SVI_CASES)
+def test_svi_minibatch_matches_reference(name):
+    g = load_golden(name)
+    obs, mask = g["obs"], g["mask"]
+    L, S = int(g["L"]), int(g["mb_sz"])
+    T = 2 * L + 1
+    K = g["init_tran"].shape[0]
+    var_tran = g["init_tran"].copy()
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    prior_emit = golden_prior_emit(g, K)
+    for it in range(int(g["maxit"])):
+        lrate = (it + float(g["tau"])) ** (-float(g["kappa_lr"]))
+        assert np.isclose(lrate, g["g_lrate"][it])
+        starts = g["w_starts"][it]
+        r = O.svi_minibatch_step(obs, mask, starts, T, var_tran, emit, g["prior_tran"],
+                                 prior_emit, lrate, L, S)
+        np.testing.assert_allclose(r["var_init"], g["w_var_init"][it][0], rtol=1e-9, atol=AT)
+        np.testing.assert_allclose(r["ll"], g["w_ll"][it], rtol=RT, atol=AT)
+        np.testing.assert_allclose(r["lalpha"], g["w_lalpha"][it], rtol=RT, atol=1e-9)
+        np.testing.assert_allclose(r["lbeta"], g["w_lbeta"][it], rtol=RT, atol=1e-9)
+        np.testing.assert_allclose(r["var_x"], g["w_var_x"][it], rtol=1e-9, atol=AT)
+        # per-window statistics (Q1 product of marginals, Q2 wrap, Q5 prior per window)
+        for b in range(S):
+            mw = mask[starts[b]:starts[b] + T]
+            A_i, e_i = O.intermediate_pars(r["var_x"][b], obs[starts[b]:starts[b] + T], mw,
+                                           g["prior_tran"], wrap=True)
+            np.testing.assert_allclose(A_i, g["w_A_i"][it][b], rtol=RT, atol=AT)
+            np.testing.assert_allclose(np.array([e[0] for e in e_i]), g["w_e1"][it][b], rtol=RT, atol=AT)
+            np.testing.assert_allclose(np.array([e[1] for e in e_i]), g["w_e2"][it][b], rtol=RT, atol=AT)
+            np.testing.assert_allclose(np.array([e[2] for e in e_i]), g["w_e3"][it][b], rtol=RT, atol=AT)
+        np.testing.assert_allclose(r["lb"], np.sum(g["w_lb"][it]), rtol=RT)
+        # global natural-gradient step
+        np.testing.assert_allclose(r["var_tran_new"], g["g_var_tran"][it], rtol=RT, atol=AT)
+        for k in range(K):
+            np.testing.assert_allclose(r["emit_new"][k]["mu"], g["g_mu"][it][k], rtol=1e-9, atol=AT)
+            np.testing.assert_allclose(r["emit_new"][k]["sigma"], g["g_sigma"][it][k], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(r["emit_new"][k]["kappa"], g["g_kappa"][it][k], rtol=RT)
+            np.testing.assert_allclose(r["emit_new"][k]["nu"], g["g_nu"][it][k], rtol=RT)
+        var_tran, emit = r["var_tran_new"], r["emit_new"]
+
+
+def test_wrap_quirk_is_needed():
+    """Q2: without the wrap-around term the statistic differs by O(1)."""
+    g = load_golden("svi_k3_d2_l5")
+    q = g["w_var_x"][0][0]
+    A_wrap = g["prior_tran"] + O.tran_stat(q[None], True)[0] - 1.
+    A_nowrap = g["prior_tran"] + O.tran_stat(q[None], False)[0] - 1.
+    assert np.allclose(A_wrap, g["w_A_i"][0][0], rtol=1e-12)
+    assert abs(A_wrap.sum() - A_nowrap.sum() - 1.0) < 1e-9
+
+
+def test_batch_cavi_matches_reference():
+    g = load_golden("cavi_k2_d2_t200")
+    K = 2
+    var_init, var_tran = g["init_var_init"], g["init_var_tran"]
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    prior_emit = golden_prior_emit(g, K)
+    for it in range(len(g["it_lZ"])):
+        r = O.batch_cavi_step(g["obs"], g["mask"], var_init, var_tran, emit, g["prior_init"],
+                              g["prior_tran"], prior_emit)
+        np.testing.assert_allclose(r["var_x"][0], g["it_var_x"][it], rtol=1e-9, atol=AT)
+        np.testing.assert_allclose(r["lZ"], g["it_lZ"][it], rtol=RT)
+        np.testing.assert_allclose(r["var_init_new"], g["it_var_init"][it], rtol=RT)
+        np.testing.assert_allclose(r["var_tran_new"], g["it_var_tran"][it], rtol=RT)
+        for k in range(K):
+            np.testing.assert_allclose(r["emit_new"][k]["mu"], g["it_mu"][it][k], rtol=1e-9, atol=AT)
+            np.testing.assert_allclose(r["emit_new"][k]["sigma"], g["it_sigma"][it][k], rtol=1e-9, atol=AT)
+            np.testing.assert_allclose(r["emit_new"][k]["kappa"], g["it_kappa"][it][k], rtol=RT)
+            np.testing.assert_allclose(r["emit_new"][k]["nu"], g["it_nu"][it][k], rtol=RT)
+        var_init, var_tran, emit = r["var_init_new"], r["var_tran_new"], r["emit_new"]
+
+
+def test_diag_extension_pinned_to_1d_reference():
+    g = load_golden("ell_1d")
+    for i in range(6):
+        got = O.diag_gaussian_ell(g["x"], g["mu"][i:i + 1], g["sigma"][i:i + 1],
+                                  g["kappa"][i:i + 1], g["nu"][i:i + 1])
+        np.testing.assert_allclose(got, g["ell"][i], rtol=1e-12, atol=1e-12)
+
+
+def test_logZ_identities():
+    """Property tests the reference implies: rows of var_x sum to 1; the Q4 bound is the
+    prefix sum of per-step normalisers; logZ = logsumexp lalpha[T-1]."""
+    g = load_golden("svi_k5_d3_l20_mask")
+    la = g["w_lalpha"][0]
+    assert np.allclose(g["w_var_x"][0].sum(-1), 1.0, atol=1e-12)
+    assert np.allclose(O.local_lower_bound(la), g["w_lb"][0], rtol=1e-12)
+    assert np.all(O.log_Z(la) < 0)
