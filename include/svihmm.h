@@ -1,0 +1,146 @@
+/*
+ * svihmm.h -- C ABI of the B200-native SVI-HMM local E-step engine (libsvihmm.so).
+ *
+ * This is the drop-in boundary for the hot path of dillonalaird/pysvihmm: everything
+ * hmmsgd_metaobs.VBHMM.infer does per global step between sampling a minibatch of
+ * meta-observations and the natural-gradient update (reference hmmsgd_metaobs.py:405-439),
+ * and the batch variant hmmbatchcd.VBHMM.infer (hmmbatchcd.py:135-141).
+ *
+ * The reference has no FFI for this path: its plugin surface is Python subclassing of
+ * hmmbase.VariationalHMMBase (hmmbase.py:34-50; local_update :201, forward_msgs :266,
+ * backward_msgs :297 are the documented override points).  The entry points below are what
+ * such an override binds with ctypes; each cites the reference code it
+ * replaces.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative SVIHMM_E* code on failure;
+ *     svihmm_last_error() returns a thread-local message for the last failure.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued on it; the *_host entry points synchronise the stream before returning.
+ *   - `loc` says where a pointer argument lives: SVIHMM_LOC_DEVICE or SVIHMM_LOC_HOST.
+ *   - Matrices are row-major (C order), like the reference's numpy arrays.
+ *   - One svihmm_ctx per GPU / host thread; a ctx is not re-entrant (the reference's E-step
+ *     mutates `self` and is not re-entrant either, hmmsgd_metaobs.py:487-519).
+ *   - There is NO CPU fallback: every entry point that computes needs a CUDA device.
+ *
+ * Packed layouts (all float64)
+ *   emission parameters, per state k, `svihmm_emit_param_len()` doubles:
+ *     SVIHMM_EMIT_NIW_FULL : [ mu (D) | sigma (D*D) | kappa | nu ]        Gaussian mu_mf,
+ *                            sigma_mf, kappa_mf, nu_mf (pybasicbayes/distributions.py:195-212)
+ *     SVIHMM_EMIT_NIW_DIAG : [ mu (D) | sigma (D) | kappa (D) | nu (D) ]  D independent 1-D NIWs
+ *   sufficient statistics, `svihmm_stats_len()` doubles:
+ *     [ A (K*K) | n (K) | sx (K*D) | sxx (K*D*D, or K*D for DIAG) | q0 (K) | tail (4) ]
+ *     A    = sum_b sum_t outer(q[t-1], q[t])         (hmmsgd_metaobs.py:876-878)
+ *            (+ B*(prior_tran-1) with SVIHMM_ADD_PRIOR, quirk Q5, :876,881)
+ *     n,sx,sxx = sum over unmasked rows of q[t,k]*[1, x, x x^T]   (util.py:73-83)
+ *     q0   = sum_b q[b,0,:]                           (hmmbatchcd.py:179)
+ *     tail = [ sum_b logZ_b, sum_b Q4_b (hmmsgd_metaobs.py:257-271), B, 0 ]
+ */
+#ifndef SVIHMM_H_
+#define SVIHMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svihmm_ctx svihmm_ctx;
+
+enum { SVIHMM_OK = 0, SVIHMM_EINVAL = -1, SVIHMM_ECUDA = -2, SVIHMM_ENOMEM = -3, SVIHMM_ESTATE = -4,
+       SVIHMM_EUNSUPPORTED = -5 };
+enum { SVIHMM_EMIT_NIW_FULL = 0, SVIHMM_EMIT_NIW_DIAG = 1 };
+enum { SVIHMM_F32 = 0, SVIHMM_F64 = 1 };
+enum { SVIHMM_LOC_DEVICE = 0, SVIHMM_LOC_HOST = 1 };
+
+/* svihmm_estep flags */
+enum {
+  SVIHMM_WRAP        = 1u << 0, /* include outer(q[T-1], q[0]) (quirk Q2, hmmsgd_metaobs.py:877-878) */
+  SVIHMM_ADD_PRIOR   = 1u << 1, /* add (prior_tran-1) once per window (quirk Q5, :876,881)           */
+  SVIHMM_MASK_LL     = 1u << 2, /* masked rows carry no evidence: ll[t,:]=0 (:1167-1168,1176)        */
+  SVIHMM_EXACT_XI    = 1u << 3  /* A = sum_t true pairwise posterior instead of outer(q,q) (NOT ref) */
+};
+
+const char* svihmm_last_error(void);
+int svihmm_version(void);
+
+/* Lifetime.  Replaces VariationalHMMBase.__init__ state (hmmbase.py:67-136). */
+int svihmm_create(svihmm_ctx** out, int device, int K, int D, int emission_kind);
+int svihmm_destroy(svihmm_ctx* ctx);
+size_t svihmm_emit_param_len(const svihmm_ctx* ctx); /* doubles per state */
+size_t svihmm_stats_len(const svihmm_ctx* ctx);      /* doubles           */
+
+/* Observation series obs (T_full x D, dtype f32/f64) and optional mask (T_full bytes, 1 = missing,
+ * hmmbase.py:60-65).  Replaces set_data (hmmbase.py:138-143).
+ * loc = DEVICE: pointers are borrowed (caller keeps them alive).  loc = HOST: copied into HBM. */
+int svihmm_set_series(svihmm_ctx* ctx, const void* obs, int64_t T_full, int dtype,
+                      const uint8_t* mask, int loc, void* stream);
+
+/* Host-resident series for streaming: the buffer is page-locked and mapped so that each step's
+ * windows are gathered over PCIe/NVLink-C2C by the GPU itself (gen_synthetic.read_data_mmap
+ * feeder, gen_synthetic.py:188-191).  Used by svihmm_estep_host. */
+int svihmm_set_series_streamed(svihmm_ctx* ctx, const void* obs_host, int64_t T_full, int dtype,
+                               const uint8_t* mask_host);
+
+/* Priors: prior_tran (K*K), prior_init (K, may be NULL = ones), prior_emit (K*param_len).
+ * hmmbase.py:102-104. */
+int svihmm_set_prior(svihmm_ctx* ctx, const double* prior_tran, const double* prior_init,
+                     const double* prior_emit, int loc, void* stream);
+
+/* Global variational parameters: var_tran (K*K Dirichlet), var_init (K, or NULL = recompute the
+ * |top eigenvector| of the mean transition matrix each time var_tran changes, quirk Q3,
+ * hmmsgd_metaobs.py:413-418), emit (K*param_len).  Derives on device mod_init/mod_tran
+ * (hmmsgd_metaobs.py:502-504) and the Cholesky-based emission constants
+ * (pybasicbayes/distributions.py:351-366). */
+int svihmm_set_globals(svihmm_ctx* ctx, const double* var_tran, const double* var_init,
+                       const double* emit, int loc, void* stream);
+int svihmm_get_globals(svihmm_ctx* ctx, double* var_tran, double* var_init, double* emit,
+                       int loc, void* stream);
+
+/* The E-step for a minibatch of B windows obs[starts[b] : starts[b]+T] of the resident series.
+ * Replaces, for all B meta-observations at once, local_update (hmmsgd_metaobs.py:487-519:
+ * lliks :508-509, forward_msgs :775-803, backward_msgs :828-855, marginals :516-519),
+ * intermediate_pars (:857-904), the accumulation :430-433 and local_lower_bound (:257-271).
+ *   starts    : B int64 (device)
+ *   var_x_out : B*T*K float32 posterior marginals (device), or NULL
+ *   stats_out : svihmm_stats_len() doubles (device)                                         */
+int svihmm_estep(svihmm_ctx* ctx, const int64_t* starts, int B, int T, float* var_x_out,
+                 double* stats_out, unsigned flags, void* stream);
+
+/* Same with HOST buffers (the reference-facing call): windows are gathered from the streamed host
+ * series (svihmm_set_series_streamed) host->device, the E-step runs, stats (and var_x if not
+ * NULL) are copied device->host, and the stream is synchronised. */
+int svihmm_estep_host(svihmm_ctx* ctx, const int64_t* starts_host, int B, int T,
+                      float* var_x_host, double* stats_host, unsigned flags, void* stream);
+
+/* Stochastic natural-gradient step on the resident globals from (all-reduced) statistics:
+ * hmmsgd_metaobs.py:1010-1069 with util.py:28-60.  stats on device.
+ *   var_tran <- (1-lrate)(var_tran-1) + lrate*bfact_A*A + 1
+ *   eta_k    <- (1-lrate) eta_k + lrate (eta_prior + bfact_E * e_k)                          */
+int svihmm_global_update(svihmm_ctx* ctx, const double* stats, double lrate, double bfact_A,
+                         double bfact_E, void* stream);
+
+/* Batch coordinate-ascent step, hmmbatchcd.py:172-189 + distributions.py:240-276,324-329:
+ * var_init = prior_init + q0, var_tran = prior_tran + A, conjugate NIW update per state.
+ * stats must come from svihmm_estep with B = 1, flags without WRAP / ADD_PRIOR. */
+int svihmm_batch_update(svihmm_ctx* ctx, const double* stats, void* stream);
+
+/* Local tables of the last svihmm_estep (valid until the next one; device -> dst at loc):
+ *   lliks  B*T*K float64  expected log-likelihoods (self.lliks, hmmsgd_metaobs.py:508-509)
+ *   alpha  B*T*K float32  normalised forward messages = softmax_k(self.lalpha[t])
+ *   mx     B*T   float64  max_k lliks[t,k]
+ *   cs     B*T   float32  forward scale factors c_t, so that
+ *                         self.lalpha[t,k] = log alpha[t,k] + sum_{u<=t} (log cs[u] + mx[u])
+ *   logz   B*2   float64  per window [logZ, Q4 bound (hmmsgd_metaobs.py:257-271)]
+ * Any of them may be NULL. */
+int svihmm_get_locals(svihmm_ctx* ctx, double* lliks, float* alpha, double* mx, float* cs,
+                      double* logz, int loc, void* stream);
+
+/* Number of kernels the engine launched on this ctx since creation (bench bookkeeping). */
+int64_t svihmm_launch_count(const svihmm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIHMM_H_ */

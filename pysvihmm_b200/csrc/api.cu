@@ -1,0 +1,519 @@
+// libsvihmm.so: C ABI (include/svihmm.h) over the sm_100a kernels.  No CPU fallback anywhere:
+// every compute entry point enqueues CUDA kernels and fails if there is no device.
+#include <string>
+#include <string.h>
+#include <stdlib.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "prep.cuh"
+#include "emit.cuh"
+#include "fb.cuh"
+#include "stats.cuh"
+#include "update.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(SVIHMM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define LAUNCHED(ctx) do { (ctx)->launches++; CU(cudaGetLastError()); } while (0)
+
+extern "C" const char* svihmm_last_error(void) { return g_err.c_str(); }
+extern "C" int svihmm_version(void) { return 100; }
+
+static int next_pow2(int k) { int p = 2; while (p < k) p <<= 1; return p; }
+
+template <typename Tp> static cudaError_t dalloc(Tp** p, size_t n) {
+  return cudaMalloc((void**)p, (n ? n : 1) * sizeof(Tp));
+}
+
+extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kind) {
+  if (!out) return fail(SVIHMM_EINVAL, "out is NULL");
+  if (K < 1 || D < 1) return fail(SVIHMM_EINVAL, "K (%d) and D (%d) must be >= 1", K, D);
+  if (kind != SVIHMM_EMIT_NIW_FULL && kind != SVIHMM_EMIT_NIW_DIAG)
+    return fail(SVIHMM_EINVAL, "unknown emission kind %d", kind);
+  if (K > 232) return fail(SVIHMM_EUNSUPPORTED, "K = %d > 232 needs the dense tensor-core path (not built yet)", K);
+  if (kind == SVIHMM_EMIT_NIW_FULL && D > 96) return fail(SVIHMM_EUNSUPPORTED, "full-covariance D = %d > 96", D);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SVIHMM_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  svihmm_ctx* c = (svihmm_ctx*)calloc(1, sizeof(svihmm_ctx));
+  if (!c) return fail(SVIHMM_ENOMEM, "calloc");
+  c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
+  c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : D;
+  c->plen = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)D + (size_t)D * D + 2 : (size_t)4 * D;
+  c->nfeat = K + 1 + D + c->DD;
+  c->slen = (size_t)K * K + K + (size_t)K * D + (size_t)K * c->DD + K + 4;
+  const size_t KK = (size_t)K * K;
+  const size_t rs = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)K * D * (D + 1) / 2 : (size_t)K * D;
+  CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, K * c->plen));
+  CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, K * c->plen));
+  CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
+  CU(dalloc(&c->lu, (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K));
+  CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, (size_t)K * D)); CU(dalloc(&c->ck, (size_t)K));
+  CU(dalloc(&c->stage_stats, c->slen));
+  *out = c;
+  return SVIHMM_OK;
+}
+
+static void free_streamed(svihmm_ctx* c) {
+  if (c->h_reg_obs) cudaHostUnregister((void*)c->hobs);
+  if (c->h_reg_mask) cudaHostUnregister((void*)c->hmask);
+  c->h_reg_obs = c->h_reg_mask = 0; c->hobs = nullptr; c->hmask = nullptr;
+  c->hobs_dev = nullptr; c->hmask_dev = nullptr;
+}
+
+extern "C" int svihmm_destroy(svihmm_ctx* c) {
+  if (!c) return SVIHMM_OK;
+  cudaSetDevice(c->device);
+  free_streamed(c);
+  void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
+                  c->pi0, c->lu, c->rowsum, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
+                  c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws,
+                  c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->pin_obs) cudaFreeHost(c->pin_obs);
+  if (c->pin_mask) cudaFreeHost(c->pin_mask);
+  free(c);
+  return SVIHMM_OK;
+}
+
+extern "C" size_t svihmm_emit_param_len(const svihmm_ctx* c) { return c ? c->plen : 0; }
+extern "C" size_t svihmm_stats_len(const svihmm_ctx* c) { return c ? c->slen : 0; }
+extern "C" int64_t svihmm_launch_count(const svihmm_ctx* c) { return c ? c->launches : 0; }
+
+static size_t esize(int dtype) { return dtype == SVIHMM_F32 ? 4 : 8; }
+
+extern "C" int svihmm_set_series(svihmm_ctx* c, const void* obs, int64_t T_full, int dtype,
+                                 const uint8_t* mask, int loc, void* stream) {
+  if (!c || !obs) return fail(SVIHMM_EINVAL, "ctx/obs is NULL");
+  if (T_full < 1) return fail(SVIHMM_EINVAL, "T_full = %lld", (long long)T_full);
+  if (dtype != SVIHMM_F32 && dtype != SVIHMM_F64) return fail(SVIHMM_EINVAL, "dtype %d", dtype);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->obs_own) { CU(cudaFree(c->obs_own)); c->obs_own = nullptr; }
+  if (c->mask_own) { CU(cudaFree(c->mask_own)); c->mask_own = nullptr; }
+  if (loc == SVIHMM_LOC_DEVICE) {
+    c->obs = obs; c->mask = mask;
+  } else {
+    const size_t nb = (size_t)T_full * c->D * esize(dtype);
+    CU(cudaMalloc(&c->obs_own, nb));
+    CU(cudaMemcpyAsync(c->obs_own, obs, nb, cudaMemcpyHostToDevice, st));
+    c->obs = c->obs_own; c->mask = nullptr;
+    if (mask) {
+      CU(cudaMalloc((void**)&c->mask_own, (size_t)T_full));
+      CU(cudaMemcpyAsync(c->mask_own, mask, (size_t)T_full, cudaMemcpyHostToDevice, st));
+      c->mask = c->mask_own;
+    }
+    CU(cudaStreamSynchronize(st));
+  }
+  c->obs_dtype = dtype; c->T_full = T_full;
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_set_series_streamed(svihmm_ctx* c, const void* obs_host, int64_t T_full, int dtype,
+                                          const uint8_t* mask_host) {
+  if (!c || !obs_host) return fail(SVIHMM_EINVAL, "ctx/obs is NULL");
+  if (dtype != SVIHMM_F32 && dtype != SVIHMM_F64) return fail(SVIHMM_EINVAL, "dtype %d", dtype);
+  CU(cudaSetDevice(c->device));
+  free_streamed(c);
+  c->hobs = obs_host; c->hmask = mask_host; c->h_dtype = dtype; c->hT_full = T_full;
+  // Page-lock + map the caller's buffer so the GPU gathers each step's windows itself.  If the
+  // registration is refused (e.g. read-only mapping) the CPU-gather + pinned-staging path is used.
+  const size_t nb = (size_t)T_full * c->D * esize(dtype);
+  if (cudaHostRegister((void*)obs_host, nb, cudaHostRegisterMapped) == cudaSuccess) {
+    c->h_reg_obs = 1;
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, (void*)obs_host, 0) == cudaSuccess) c->hobs_dev = dp;
+  }
+  (void)cudaGetLastError();
+  if (mask_host && c->hobs_dev) {
+    if (cudaHostRegister((void*)mask_host, (size_t)T_full, cudaHostRegisterMapped) == cudaSuccess) {
+      c->h_reg_mask = 1;
+      void* dp = nullptr;
+      if (cudaHostGetDevicePointer(&dp, (void*)mask_host, 0) == cudaSuccess) c->hmask_dev = (const uint8_t*)dp;
+    }
+    (void)cudaGetLastError();
+    if (!c->hmask_dev) c->hobs_dev = nullptr;   // all-or-nothing: fall back to the CPU gather
+  }
+  return SVIHMM_OK;
+}
+
+static int copy_in(void* dst, const void* src, size_t nb, int loc, cudaStream_t st) {
+  CU(cudaMemcpyAsync(dst, src, nb, loc == SVIHMM_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));   // caller may free its buffer on return
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_set_prior(svihmm_ctx* c, const double* prior_tran, const double* prior_init,
+                                const double* prior_emit, int loc, void* stream) {
+  if (!c || !prior_tran || !prior_emit) return fail(SVIHMM_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = copy_in(c->prior_tran, prior_tran, sizeof(double) * c->K * c->K, loc, st))) return rc;
+  if ((rc = copy_in(c->prior_emit, prior_emit, sizeof(double) * c->K * c->plen, loc, st))) return rc;
+  if (prior_init) { if ((rc = copy_in(c->prior_init, prior_init, sizeof(double) * c->K, loc, st))) return rc; }
+  else {
+    double* ones = (double*)malloc(sizeof(double) * c->K);
+    for (int i = 0; i < c->K; ++i) ones[i] = 1.0;
+    rc = copy_in(c->prior_init, ones, sizeof(double) * c->K, SVIHMM_LOC_HOST, st);
+    free(ones);
+    if (rc) return rc;
+  }
+  c->have_prior = 1;
+  return SVIHMM_OK;
+}
+
+// globals -> derived constants (3 tiny kernels)
+static int run_prep(svihmm_ctx* c, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  k_prep_tran<<<1, 256, 0, st>>>(K, c->W, c->vinit + K, c->user_init, c->lu, c->rowsum, c->vinit,
+                                 c->Pt, c->PtT, c->pi0);
+  LAUNCHED(c);
+  if (c->kind == SVIHMM_EMIT_NIW_FULL) {
+    const size_t smem = 2 * (size_t)D * D * sizeof(double);
+    if (smem > 48 * 1024)
+      CU(cudaFuncSetAttribute(k_prep_emit_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_prep_emit_full<<<K, 128, smem, st>>>(D, c->plen, c->emit, c->Rs, c->gk, c->ck);
+  } else {
+    k_prep_emit_diag<<<(K + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->Rs, c->gk, c->ck);
+  }
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_set_globals(svihmm_ctx* c, const double* var_tran, const double* var_init,
+                                  const double* emit, int loc, void* stream) {
+  if (!c || !var_tran || !emit) return fail(SVIHMM_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = copy_in(c->W, var_tran, sizeof(double) * c->K * c->K, loc, st))) return rc;
+  if ((rc = copy_in(c->emit, emit, sizeof(double) * c->K * c->plen, loc, st))) return rc;
+  c->user_init = var_init != nullptr;
+  if (var_init && (rc = copy_in(c->vinit + c->K, var_init, sizeof(double) * c->K, loc, st))) return rc;
+  c->have_globals = 1;
+  return run_prep(c, st);
+}
+
+extern "C" int svihmm_get_globals(svihmm_ctx* c, double* var_tran, double* var_init, double* emit,
+                                  int loc, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  if (!c->have_globals) return fail(SVIHMM_ESTATE, "svihmm_set_globals has not been called");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaMemcpyKind kd = loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (var_tran) CU(cudaMemcpyAsync(var_tran, c->W, sizeof(double) * c->K * c->K, kd, st));
+  if (var_init) CU(cudaMemcpyAsync(var_init, c->vinit, sizeof(double) * c->K, kd, st));
+  if (emit) CU(cudaMemcpyAsync(emit, c->emit, sizeof(double) * c->K * c->plen, kd, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+static int ensure_ws(svihmm_ctx* c, int B, int T, bool need_r) {
+  const size_t rows = (size_t)B * T, K = c->K;
+  if (rows > c->cap_rows) {
+    void* olds[] = {c->ll_ws, c->mx_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws};
+    for (void* p : olds) if (p) CU(cudaFree(p));
+    c->ll_ws = nullptr; c->mx_ws = nullptr; c->b_ws = nullptr; c->alpha_ws = nullptr; c->q_ws = nullptr; c->r_ws = nullptr;
+    c->cap_rows = 0;
+    CU(dalloc(&c->ll_ws, rows * K)); CU(dalloc(&c->mx_ws, 2 * rows));
+    CU(dalloc(&c->b_ws, rows * K)); CU(dalloc(&c->alpha_ws, rows * K)); CU(dalloc(&c->q_ws, rows * K));
+    c->cap_rows = rows;
+  }
+  if (need_r && !c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
+  if ((size_t)B > c->cap_B) {
+    if (c->seq_ws) CU(cudaFree(c->seq_ws));
+    c->seq_ws = nullptr; c->cap_B = 0;
+    CU(dalloc(&c->seq_ws, 2 * (size_t)B));
+    c->cap_B = B;
+  }
+  return SVIHMM_OK;
+}
+
+template <int KP>
+static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStream_t st) {
+  const int G = 32 / KP;
+  const int warps = (B + G - 1) / G;
+  // few chains: one warp per CTA so that every chain gets a scheduler of its own
+  const int wpb = warps <= 4 * 148 ? 1 : 4;
+  const int grid = (warps + wpb - 1) / wpb;
+  float* cs = (float*)(c->mx_ws + (size_t)B * T);   // second half of mx_ws holds the scale factors
+  k_forward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
+  c->launches++;
+  k_backward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->b_ws, c->alpha_ws, q, r);
+  c->launches++;
+}
+
+static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
+                      const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
+                      unsigned flags, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  const bool xi = flags & SVIHMM_EXACT_XI;
+  int rc = ensure_ws(c, B, T, xi);
+  if (rc) return rc;
+  const int64_t R = (int64_t)B * T;
+  const int mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
+  // K1: expected log-likelihoods (fp64) -> scaled likelihoods b (fp32) + row maxima
+  if (c->kind == SVIHMM_EMIT_NIW_FULL) {
+    const size_t smem = ((size_t)EMIT_ROWS * D + (size_t)D * (D + 1) / 2 + D) * sizeof(double);
+    if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the emission kernel", D);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_emit_full<<<(unsigned)((R + EMIT_ROWS - 1) / EMIT_ROWS), EMIT_ROWS, smem, st>>>(
+        B, T, K, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, c->ll_ws);
+  } else {
+    const size_t smem = 2 * (size_t)K * D * sizeof(double);
+    if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "K*D = %d too large for the diagonal emission kernel", K * D);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_emit_diag<<<(unsigned)((R * K + 255) / 256), 256, smem, st>>>(
+        B, T, K, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, c->ll_ws);
+  }
+  LAUNCHED(c);
+  k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
+  LAUNCHED(c);
+  // K2/K3: forward, backward + marginals
+  float* q = var_x_out ? var_x_out : c->q_ws;
+  float* r = xi ? c->r_ws : nullptr;
+  float* cs = (float*)(c->mx_ws + (size_t)B * T);
+  if (K <= 32) {
+    switch (c->KP) {
+      case 2: launch_fb<2>(c, B, T, q, r, st); break;
+      case 4: launch_fb<4>(c, B, T, q, r, st); break;
+      case 8: launch_fb<8>(c, B, T, q, r, st); break;
+      case 16: launch_fb<16>(c, B, T, q, r, st); break;
+      default: launch_fb<32>(c, B, T, q, r, st); break;
+    }
+  } else {
+    const int KT = (K + 31) / 32 * 32;
+    const size_t smem = ((size_t)K * K + 2 * KT + 64) * sizeof(float);
+    if (smem > 48 * 1024) {
+      CU(cudaFuncSetAttribute(k_forward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(cudaFuncSetAttribute(k_backward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
+    c->launches++;
+    k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
+  LAUNCHED(c);
+  // K4: statistics
+  StatsArgs a;
+  a.B = B; a.T = T; a.K = K; a.D = D; a.DD = c->DD; a.N = c->nfeat;
+  a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.R = R;
+  a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
+  const int TM = K <= 16 ? 16 : (K <= 32 ? 32 : 64);
+  const int tiles_m = (K + TM - 1) / TM;
+  const int tiles_n = (c->nfeat + ST_TN - 1) / ST_TN;
+  const int64_t chunks = (R + ST_RC - 1) / ST_RC;
+  int64_t nsplit = (4 * 148 + (int64_t)tiles_m * tiles_n - 1) / ((int64_t)tiles_m * tiles_n);
+  if (nsplit > chunks) nsplit = chunks;
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = ((chunks + nsplit - 1) / nsplit) * ST_RC;
+  nsplit = (R + rps - 1) / rps;
+  a.rows_per_split = rps;
+  const size_t need_part = (size_t)nsplit * K * c->nfeat;
+  if (need_part > c->cap_part) {
+    if (c->part_ws) CU(cudaFree(c->part_ws));
+    c->part_ws = nullptr; c->cap_part = 0;
+    CU(dalloc(&c->part_ws, need_part));
+    c->cap_part = need_part;
+  }
+  a.part = c->part_ws;
+  const size_t xsm = (size_t)ST_RC * D * sizeof(float);
+  auto launch_stats = [&](const float* left, const float* next, int n_lo, int n_hi, int wrap) {
+    a.left = left; a.next = next; a.n_lo = n_lo; a.n_hi = n_hi; a.wrap = wrap;
+    dim3 grid((n_hi - n_lo + ST_TN - 1) / ST_TN, tiles_m, (unsigned)nsplit);
+    if (TM == 16) k_stats<16><<<grid, 256, xsm, st>>>(a);
+    else if (TM == 32) k_stats<32><<<grid, 256, xsm, st>>>(a);
+    else k_stats<64><<<grid, 256, xsm, st>>>(a);
+    c->launches++;
+  };
+  if (xi) {
+    launch_stats(c->alpha_ws, c->r_ws, 0, K, 0);
+    launch_stats(q, q, K, c->nfeat, 0);
+  } else {
+    launch_stats(q, q, 0, c->nfeat, (flags & SVIHMM_WRAP) ? 1 : 0);
+  }
+  CU(cudaGetLastError());
+  k_stats_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+      B, T, K, D, c->DD, c->nfeat, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
+      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, c->Pt, xi ? 1 : 0, stats_out, c->slen);
+  LAUNCHED(c);
+  c->last_B = B; c->last_T = T;
+  return SVIHMM_OK;
+}
+
+static int check_estep_args(svihmm_ctx* c, const void* starts, int B, int T, const void* stats, unsigned flags) {
+  if (!c || !starts || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (B < 1 || T < 1) return fail(SVIHMM_EINVAL, "B (%d) and T (%d) must be >= 1", B, T);
+  if (!c->have_globals) return fail(SVIHMM_ESTATE, "svihmm_set_globals has not been called");
+  if ((flags & SVIHMM_ADD_PRIOR) && !c->have_prior) return fail(SVIHMM_ESTATE, "SVIHMM_ADD_PRIOR needs svihmm_set_prior");
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_estep(svihmm_ctx* c, const int64_t* starts, int B, int T, float* var_x_out,
+                            double* stats_out, unsigned flags, void* stream) {
+  int rc = check_estep_args(c, starts, B, T, stats_out, flags);
+  if (rc) return rc;
+  if (!c->obs) return fail(SVIHMM_ESTATE, "svihmm_set_series has not been called");
+  if (T > c->T_full) return fail(SVIHMM_EINVAL, "T (%d) exceeds the series length (%lld)", T, (long long)c->T_full);
+  CU(cudaSetDevice(c->device));
+  return estep_impl(c, c->obs, c->obs_dtype, c->mask, starts, B, T, var_x_out, stats_out, flags,
+                    (cudaStream_t)stream);
+}
+
+// gather B windows of T rows (row = rowbytes) from a mapped host (or device) series into a dense
+// [B][T] staging buffer, 16 bytes per thread when alignment allows; also the mask bytes.
+__global__ void __launch_bounds__(256)
+k_gather_windows(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const uint8_t* __restrict__ msrc,
+                 const int64_t* __restrict__ starts, uint8_t* __restrict__ dst, uint8_t* __restrict__ mdst,
+                 int64_t* __restrict__ dense_starts, int vec16) {
+  const int b = blockIdx.y;
+  const int64_t s0 = starts[b];
+  const size_t wbytes = (size_t)T * rowbytes;
+  const uint8_t* sp = src + (size_t)s0 * rowbytes;
+  uint8_t* dp = dst + (size_t)b * wbytes;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if (vec16) {
+    const int4* s4 = (const int4*)sp; int4* d4 = (int4*)dp;
+    for (size_t i = tid; i < wbytes / 16; i += nth) d4[i] = s4[i];
+  } else {
+    const uint32_t* s1 = (const uint32_t*)sp; uint32_t* d1 = (uint32_t*)dp;
+    for (size_t i = tid; i < wbytes / 4; i += nth) d1[i] = s1[i];
+  }
+  if (msrc) for (size_t i = tid; i < (size_t)T; i += nth) mdst[(size_t)b * T + i] = msrc[s0 + i];
+  if (tid == 0) dense_starts[b] = (int64_t)b * T;
+}
+
+extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int B, int T,
+                                 float* var_x_host, double* stats_host, unsigned flags, void* stream) {
+  int rc = check_estep_args(c, starts_host, B, T, stats_host, flags);
+  if (rc) return rc;
+  if (!c->hobs) return fail(SVIHMM_ESTATE, "svihmm_set_series_streamed has not been called");
+  for (int b = 0; b < B; ++b)
+    if (starts_host[b] < 0 || starts_host[b] + T > c->hT_full)
+      return fail(SVIHMM_EINVAL, "window %d = [%lld, +%d) outside the series of length %lld", b,
+                  (long long)starts_host[b], T, (long long)c->hT_full);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rows = (size_t)B * T, es = esize(c->h_dtype), rowbytes = (size_t)c->D * es;
+  if (rows > c->stage_rows) {
+    if (c->stage_obs) CU(cudaFree(c->stage_obs));
+    if (c->stage_mask) CU(cudaFree(c->stage_mask));
+    c->stage_obs = nullptr; c->stage_mask = nullptr; c->stage_rows = 0;
+    CU(cudaMalloc(&c->stage_obs, rows * c->D * 8));
+    CU(cudaMalloc((void**)&c->stage_mask, rows));
+    c->stage_rows = rows;
+  }
+  if ((size_t)B > c->stage_B) {
+    if (c->stage_src) CU(cudaFree(c->stage_src));
+    if (c->stage_starts) CU(cudaFree(c->stage_starts));
+    c->stage_src = nullptr; c->stage_starts = nullptr; c->stage_B = 0;
+    CU(dalloc(&c->stage_src, (size_t)B)); CU(dalloc(&c->stage_starts, (size_t)B));
+    c->stage_B = B;
+  }
+  const bool has_mask = c->hmask != nullptr;
+  if (c->hobs_dev) {
+    // GPU-side gather straight out of the page-locked host series
+    CU(cudaMemcpyAsync(c->stage_src, starts_host, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+    const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
+    const size_t units = (size_t)T * rowbytes / (vec16 ? 16 : 4);
+    dim3 grid((unsigned)((units + 255) / 256 > 64 ? 64 : (units + 255) / 256), B);
+    k_gather_windows<<<grid, 256, 0, st>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
+                                           has_mask ? c->hmask_dev : nullptr, c->stage_src,
+                                           (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, vec16);
+    LAUNCHED(c);
+  } else {
+    // CPU gather into pinned staging, one H2D copy
+    if (rows > c->pin_rows) {
+      if (c->pin_obs) CU(cudaFreeHost(c->pin_obs));
+      if (c->pin_mask) CU(cudaFreeHost(c->pin_mask));
+      c->pin_obs = nullptr; c->pin_mask = nullptr; c->pin_rows = 0;
+      CU(cudaMallocHost(&c->pin_obs, rows * c->D * 8 + sizeof(int64_t) * B));
+      CU(cudaMallocHost((void**)&c->pin_mask, rows));
+      c->pin_rows = rows;
+    }
+    CU(cudaStreamSynchronize(st));    // the previous step may still be reading the pinned staging
+    for (int b = 0; b < B; ++b) {
+      memcpy((uint8_t*)c->pin_obs + (size_t)b * T * rowbytes,
+             (const uint8_t*)c->hobs + (size_t)starts_host[b] * rowbytes, (size_t)T * rowbytes);
+      if (has_mask) memcpy(c->pin_mask + (size_t)b * T, c->hmask + starts_host[b], (size_t)T);
+    }
+    int64_t* ds = (int64_t*)((uint8_t*)c->pin_obs + rows * c->D * 8);
+    for (int b = 0; b < B; ++b) ds[b] = (int64_t)b * T;
+    CU(cudaMemcpyAsync(c->stage_obs, c->pin_obs, rows * rowbytes, cudaMemcpyHostToDevice, st));
+    if (has_mask) CU(cudaMemcpyAsync(c->stage_mask, c->pin_mask, rows, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->stage_starts, ds, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
+  }
+  rc = estep_impl(c, c->stage_obs, c->h_dtype, has_mask ? c->stage_mask : nullptr, c->stage_starts, B, T,
+                  nullptr, c->stage_stats, flags, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(stats_host, c->stage_stats, sizeof(double) * c->slen, cudaMemcpyDeviceToHost, st));
+  if (var_x_host)
+    CU(cudaMemcpyAsync(var_x_host, c->q_ws, sizeof(float) * rows * c->K, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_global_update(svihmm_ctx* c, const double* stats, double lrate, double bA,
+                                    double bE, void* stream) {
+  if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = c->K, D = c->D;
+  k_update_tran_svi<<<(K * K + 255) / 256, 256, 0, st>>>(K * K, c->W, stats, lrate, bA);
+  LAUNCHED(c);
+  if (c->kind == SVIHMM_EMIT_NIW_FULL)
+    k_update_emit_svi_full<<<K, 128, 3 * D * sizeof(double), st>>>(K, D, c->plen, c->emit, c->prior_emit, stats, lrate, bE);
+  else
+    k_update_emit_svi_diag<<<(K * D + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->prior_emit, stats, lrate, bE);
+  LAUNCHED(c);
+  return run_prep(c, st);
+}
+
+extern "C" int svihmm_batch_update(svihmm_ctx* c, const double* stats, void* stream) {
+  if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = c->K, D = c->D;
+  k_update_tran_batch<<<(K * K + 255) / 256, 256, 0, st>>>(K, c->W, c->vinit + K, c->prior_tran,
+                                                          c->prior_init, stats, D, c->DD);
+  LAUNCHED(c);
+  c->user_init = 1;    // hmmbatchcd.py:179: var_init becomes an explicit Dirichlet parameter
+  if (c->kind == SVIHMM_EMIT_NIW_FULL)
+    k_update_emit_batch_full<<<K, 128, D * sizeof(double), st>>>(K, D, c->plen, c->emit, c->prior_emit, stats);
+  else
+    k_update_emit_batch_diag<<<(K * D + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->prior_emit, stats);
+  LAUNCHED(c);
+  return run_prep(c, st);
+}
+
+extern "C" int svihmm_get_locals(svihmm_ctx* c, double* lliks, float* alpha, double* mx, float* cs,
+                                 double* logz, int loc, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  if (c->last_B == 0) return fail(SVIHMM_ESTATE, "no E-step has run yet");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaMemcpyKind kd = loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const size_t n = (size_t)c->last_B * c->last_T * c->K;
+  if (lliks) CU(cudaMemcpyAsync(lliks, c->ll_ws, sizeof(double) * n, kd, st));
+  if (alpha) CU(cudaMemcpyAsync(alpha, c->alpha_ws, sizeof(float) * n, kd, st));
+  const size_t bt = (size_t)c->last_B * c->last_T;
+  if (mx) CU(cudaMemcpyAsync(mx, c->mx_ws, sizeof(double) * bt, kd, st));
+  if (cs) CU(cudaMemcpyAsync(cs, (const float*)(c->mx_ws + bt), sizeof(float) * bt, kd, st));
+  if (logz) CU(cudaMemcpyAsync(logz, c->seq_ws, sizeof(double) * 2 * c->last_B, kd, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}

@@ -1,0 +1,62 @@
+// Shared declarations for libsvihmm.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/svihmm.h"
+
+#define SVIHMM_EPS 1e-9      /* hmmbase.py:30 / hmmsgd_metaobs.py:26 */
+#define SVIHMM_WEPS 1e-12    /* pybasicbayes/distributions.py:22     */
+
+struct svihmm_ctx {
+  int device, K, D, kind, KP;
+  size_t plen;    // doubles per state in the packed emission parameters
+  size_t slen;    // doubles in the packed statistics
+  int nfeat;      // columns of the statistics contraction: K + 1 + D + DD
+  int DD;         // D*D (full) or D (diag)
+  // master copies of the global variational parameters and priors (device, f64)
+  double *W, *vinit, *emit, *prior_tran, *prior_init, *prior_emit;
+  int user_init, have_globals, have_prior;
+  // derived per-global-step constants
+  float *Pt, *PtT, *pi0;          // exp(E[log A]) row-major, its transpose, exp(E[log pi])
+  double *lu, *rowsum;            // scratch of the stationary solve
+  double *Rs, *gk, *ck;           // emission constants (see prep.cuh)
+  // resident series
+  const void* obs; const uint8_t* mask; int obs_dtype; int64_t T_full;
+  void* obs_own; uint8_t* mask_own;
+  // host-streamed series
+  const void* hobs; const uint8_t* hmask; const void* hobs_dev; const uint8_t* hmask_dev;
+  int h_dtype; int64_t hT_full; int h_reg_obs, h_reg_mask;
+  void* stage_obs; uint8_t* stage_mask; int64_t* stage_src; int64_t* stage_starts;
+  double* stage_stats; size_t stage_rows, stage_B;
+  void* pin_obs; uint8_t* pin_mask; size_t pin_rows;
+  // workspaces
+  size_t cap_rows, cap_B, cap_part;
+  double *ll_ws, *mx_ws, *seq_ws;
+  float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws;
+  int last_B, last_T;
+  int64_t launches;
+};
+
+__device__ __forceinline__ double ld_obs(const void* obs, int dtype, int64_t idx) {
+  return dtype == SVIHMM_F32 ? (double)__ldg((const float*)obs + idx) : __ldg((const double*)obs + idx);
+}
+
+// psi(x), float64.  Recurrence up to x >= 10, then the asymptotic series through B14
+// (truncation error < 5e-17 there); reflection for x <= 0.
+__device__ inline double digamma_d(double x) {
+  double r = 0.0;
+  if (x <= 0.0) {
+    if (x == floor(x)) return nan("");
+    r = -M_PI / tan(M_PI * x);
+    x = 1.0 - x;
+  }
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double xi = 1.0 / x, x2 = xi * xi;
+  r += log(x) - 0.5 * xi
+     - x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240
+     - x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
+  return r;
+}

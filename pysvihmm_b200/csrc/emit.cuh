@@ -1,0 +1,105 @@
+// K1: per-timestep expected log-likelihoods of the observation models, float64 accumulation
+// (fp32 rounding of the quadratic form is the precision bottleneck of the whole E-step, SURVEY
+// section 7), replacing the per-state loop hmmsgd_metaobs.py:508-509 over
+// Gaussian.expected_log_likelihood (pybasicbayes/distributions.py:351-359) + np.nan_to_num.
+#pragma once
+#include "common.cuh"
+
+#define EMIT_ROWS 128   // rows (b,t) per CTA, one per thread
+
+// ll[r][k] = ck - || Rs_k x_r - gk ||^2 ; x staged in smem as doubles, Rs_k staged per state.
+// dynamic smem: (EMIT_ROWS*D + D(D+1)/2 + D) doubles.
+__global__ void __launch_bounds__(EMIT_ROWS)
+k_emit_full(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
+            const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+            const double* __restrict__ Rs, const double* __restrict__ gk,
+            const double* __restrict__ ck, double* __restrict__ ll) {
+  extern __shared__ double sm[];
+  double* xs = sm;                               // [D][EMIT_ROWS]
+  double* Rk = sm + (size_t)EMIT_ROWS * D;       // packed lower
+  const int tri = D * (D + 1) / 2;
+  double* gg = Rk + tri;                         // [D]
+  const int tid = threadIdx.x;
+  const int64_t R = (int64_t)B * T;
+  const int64_t r0 = (int64_t)blockIdx.x * EMIT_ROWS;
+  // stage x (coalesced over the D contiguous values of consecutive rows of one window)
+  bool dead = false;     // row carries no evidence: NaN anywhere or masked with MASK_LL
+  for (int idx = tid; idx < EMIT_ROWS * D; idx += EMIT_ROWS) {
+    const int rr = idx / D, d = idx - rr * D;
+    const int64_t r = r0 + rr;
+    double v = 0.0;
+    if (r < R) {
+      const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+      v = ld_obs(obs, dtype, (starts[b] + t) * D + d);
+    }
+    xs[d * EMIT_ROWS + rr] = v;
+  }
+  __syncthreads();
+  const int64_t r = r0 + tid;
+  if (r < R) {
+    const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+    if (mask_ll && mask && mask[starts[b] + t]) dead = true;
+    for (int d = 0; d < D; ++d) if (isnan(xs[d * EMIT_ROWS + tid])) dead = true;
+  }
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+    for (int idx = tid; idx < tri; idx += EMIT_ROWS) Rk[idx] = Rs[(size_t)k * tri + idx];
+    for (int idx = tid; idx < D; idx += EMIT_ROWS) gg[idx] = gk[(size_t)k * D + idx];
+    __syncthreads();
+    if (r < R) {
+      double acc = 0.0;
+      int o = 0;
+      for (int i = 0; i < D; ++i) {
+        double s = -gg[i];
+        for (int j = 0; j <= i; ++j) s = fma(Rk[o + j], xs[j * EMIT_ROWS + tid], s);
+        o += i + 1;
+        acc = fma(s, s, acc);
+      }
+      ll[r * K + k] = dead ? 0.0 : ck[k] - acc;
+    }
+  }
+}
+
+// Diagonal emissions: one thread per (row, state); parameters in smem.
+// dynamic smem: 2*K*D doubles.
+__global__ void __launch_bounds__(256)
+k_emit_diag(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
+            const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+            const double* __restrict__ Rs, const double* __restrict__ gk,
+            const double* __restrict__ ck, double* __restrict__ ll) {
+  extern __shared__ double sm[];
+  double* rr_ = sm; double* mm_ = sm + (size_t)K * D;
+  for (int idx = threadIdx.x; idx < K * D; idx += blockDim.x) { rr_[idx] = Rs[idx]; mm_[idx] = gk[idx]; }
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t R = (int64_t)B * T;
+  if (e >= R * K) return;
+  const int64_t r = e / K; const int k = (int)(e - r * K);
+  const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+  const int64_t gi = starts[b] + t;
+  bool dead = mask_ll && mask && mask[gi];
+  double acc = 0.0;
+  for (int d = 0; d < D; ++d) {
+    const double x = ld_obs(obs, dtype, gi * D + d);
+    if (isnan(x)) dead = true;
+    const double df = x - mm_[k * D + d];
+    acc = fma(rr_[k * D + d] * df, df, acc);
+  }
+  ll[e] = dead ? 0.0 : ck[k] - acc;
+}
+
+// b[r][k] = exp(ll[r][k] - max_k ll[r][k]) (fp32), mx[r] = the max (fp64).
+// One warp per row, lanes stride over k.
+__global__ void __launch_bounds__(256)
+k_ll_to_b(int64_t R, int K, const double* __restrict__ ll, float* __restrict__ b,
+          double* __restrict__ mx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  double m = -INFINITY;
+  for (int k = lane; k < K; k += 32) m = fmax(m, ll[r * K + k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int k = lane; k < K; k += 32) b[r * K + k] = (float)exp(ll[r * K + k] - m);
+  if (lane == 0) mx[r] = m;
+}

@@ -1,0 +1,215 @@
+"""EStepEngine: thin Python holder of PyTorch tensors around the C ABI of libsvihmm.so.
+
+PyTorch is used for device memory, streams and (by the callers) torch.distributed only; all
+arithmetic of the path happens in the hand-written CUDA kernels behind include/svihmm.h.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_KINDS = {"niw_full": L.EMIT_NIW_FULL, "niw_diag": L.EMIT_NIW_DIAG}
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class EStepEngine(object):
+    """One engine = one svihmm_ctx on one GPU.
+
+    Replaces, for a whole minibatch at once, the reference's local_update + intermediate_pars
+    (hmmsgd_metaobs.py:405-436) and global_update (:1010-1069) / hmmbatchcd.global_update
+    (hmmbatchcd.py:172-189).
+    """
+
+    def __init__(self, K, D, emission="niw_full", device=None):
+        if not torch.cuda.is_available():
+            raise L.SvihmmError("pysvihmm_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = L.load()
+        self.K, self.D = int(K), int(D)
+        self.emission = emission
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+            if not isinstance(device, torch.device) else device
+        h = C.c_void_p()
+        L.check(self.lib.svihmm_create(C.byref(h), self.device.index, self.K, self.D, _KINDS[emission]))
+        self._h = h
+        self.plen = int(self.lib.svihmm_emit_param_len(h))
+        self.slen = int(self.lib.svihmm_stats_len(h))
+        self.DD = self.D * self.D if emission == "niw_full" else self.D
+        self._keep = {}          # borrowed tensors / host arrays the C side points into
+        self.T_full = None
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.svihmm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ data
+    def set_series(self, obs, mask=None, dtype=None):
+        """obs: (T_full, D) torch CUDA tensor (borrowed) or numpy array (copied to HBM).
+        mask: (T_full,) bool, True = missing (hmmbase.py:60-65).  dtype: 'f32'/'f64' to convert."""
+        if isinstance(obs, np.ndarray):
+            obs = torch.from_numpy(np.ascontiguousarray(obs.reshape(obs.shape[0], -1)))
+        if dtype is not None:
+            obs = obs.to(torch.float32 if dtype == "f32" else torch.float64)
+        if obs.dtype not in (torch.float32, torch.float64):
+            obs = obs.to(torch.float64)
+        obs = obs.to(self.device).contiguous().reshape(obs.shape[0], -1)
+        if obs.shape[1] != self.D:
+            raise ValueError("obs has D=%d, engine D=%d" % (obs.shape[1], self.D))
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(np.asarray(mask, dtype=np.uint8) if not isinstance(mask, torch.Tensor)
+                                else mask.to(torch.uint8)).to(self.device).contiguous()
+        self._keep["obs"], self._keep["mask"] = obs, m
+        self.T_full = int(obs.shape[0])
+        L.check(self.lib.svihmm_set_series(self._h, _ptr(obs), self.T_full,
+                                           L.F32 if obs.dtype == torch.float32 else L.F64,
+                                           _ptr(m), L.LOC_DEVICE, self._stream()))
+
+    def set_series_streamed(self, obs_host, mask_host=None):
+        """Host-resident series (numpy, C-contiguous f32/f64): windows are gathered per step by
+        estep_host (gen_synthetic.read_data_mmap feeder, gen_synthetic.py:188-191)."""
+        obs_host = np.ascontiguousarray(obs_host)
+        if obs_host.dtype not in (np.float32, np.float64):
+            obs_host = obs_host.astype(np.float64)
+        obs_host = obs_host.reshape(obs_host.shape[0], -1)
+        m = None if mask_host is None else np.ascontiguousarray(np.asarray(mask_host, dtype=np.uint8))
+        self._keep["hobs"], self._keep["hmask"] = obs_host, m
+        self.hT_full = int(obs_host.shape[0])
+        L.check(self.lib.svihmm_set_series_streamed(
+            self._h, _ptr(obs_host), self.hT_full, L.F32 if obs_host.dtype == np.float32 else L.F64,
+            _ptr(m)))
+
+    # ------------------------------------------------------------------ parameters
+    def set_prior(self, prior_tran, prior_emit, prior_init=None):
+        pt, pe = _f64(prior_tran), _f64(prior_emit)
+        assert pt.shape == (self.K, self.K) and pe.size == self.K * self.plen
+        pi = None if prior_init is None else _f64(prior_init)
+        L.check(self.lib.svihmm_set_prior(self._h, _ptr(pt), _ptr(pi), _ptr(pe), L.LOC_HOST, self._stream()))
+
+    def set_globals(self, var_tran, emit, var_init=None):
+        vt, em = _f64(var_tran), _f64(emit)
+        assert vt.shape == (self.K, self.K) and em.size == self.K * self.plen
+        vi = None if var_init is None else _f64(var_init)
+        L.check(self.lib.svihmm_set_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
+
+    def get_globals(self):
+        vt = np.empty((self.K, self.K)); vi = np.empty(self.K); em = np.empty((self.K, self.plen))
+        L.check(self.lib.svihmm_get_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
+        return vt, vi, em
+
+    # ------------------------------------------------------------------ the hot path
+    def new_stats(self):
+        return torch.empty(self.slen, dtype=torch.float64, device=self.device)
+
+    def estep(self, starts, T, flags=0, var_x=None, stats=None, want_var_x=True):
+        """E-step over windows obs[starts[b]:starts[b]+T] of the resident series.
+        Returns (var_x (B,T,K) float32 CUDA tensor or None, stats float64 CUDA tensor)."""
+        if not isinstance(starts, torch.Tensor):
+            starts = torch.as_tensor(np.asarray(starts, dtype=np.int64))
+        starts = starts.to(device=self.device, dtype=torch.int64).contiguous()
+        B = int(starts.numel())
+        if var_x is None and want_var_x:
+            var_x = torch.empty((B, T, self.K), dtype=torch.float32, device=self.device)
+        if stats is None:
+            stats = self.new_stats()
+        L.check(self.lib.svihmm_estep(self._h, _ptr(starts), B, int(T), _ptr(var_x), _ptr(stats),
+                                      int(flags), self._stream()))
+        self._keep["starts"] = starts
+        return var_x, stats
+
+    def estep_host(self, starts, T, flags=0, want_var_x=False, stats_out=None, var_x_out=None):
+        """Reference-facing call with HOST buffers: gathers the windows from the streamed host
+        series host->device, runs the E-step, copies stats (and var_x) back, synchronises."""
+        starts = np.ascontiguousarray(np.asarray(starts, dtype=np.int64))
+        B = int(starts.size)
+        stats = np.empty(self.slen) if stats_out is None else stats_out
+        vx = var_x_out
+        if vx is None and want_var_x:
+            vx = np.empty((B, T, self.K), dtype=np.float32)
+        L.check(self.lib.svihmm_estep_host(self._h, _ptr(starts), B, int(T), _ptr(vx), _ptr(stats),
+                                           int(flags), self._stream()))
+        return vx, stats
+
+    def global_update(self, stats, lrate, bfact_A, bfact_E):
+        """hmmsgd_metaobs.py:1010-1069 on the device-resident globals."""
+        L.check(self.lib.svihmm_global_update(self._h, _ptr(stats), float(lrate), float(bfact_A),
+                                              float(bfact_E), self._stream()))
+
+    def batch_update(self, stats):
+        """hmmbatchcd.py:172-189 on the device-resident globals."""
+        L.check(self.lib.svihmm_batch_update(self._h, _ptr(stats), self._stream()))
+
+    def get_locals(self, B, T):
+        ll = np.empty((B, T, self.K)); al = np.empty((B, T, self.K), dtype=np.float32)
+        mx = np.empty((B, T)); cs = np.empty((B, T), dtype=np.float32); lz = np.empty((B, 2))
+        L.check(self.lib.svihmm_get_locals(self._h, _ptr(ll), _ptr(al), _ptr(mx), _ptr(cs), _ptr(lz),
+                                           L.LOC_HOST, self._stream()))
+        return dict(lliks=ll, alpha=al, mx=mx, cs=cs, logZ=lz[:, 0], lb_q4=lz[:, 1])
+
+    def launch_count(self):
+        return int(self.lib.svihmm_launch_count(self._h))
+
+    # ------------------------------------------------------------------ packing helpers
+    def unpack_stats(self, stats):
+        s = stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) else np.asarray(stats)
+        K, D, DD = self.K, self.D, self.DD
+        o = 0
+        out = {}
+        out["A"] = s[o:o + K * K].reshape(K, K); o += K * K
+        out["n"] = s[o:o + K]; o += K
+        out["sx"] = s[o:o + K * D].reshape(K, D); o += K * D
+        out["sxx"] = s[o:o + K * DD].reshape((K, D, D) if self.emission == "niw_full" else (K, D)); o += K * DD
+        out["q0"] = s[o:o + K]; o += K
+        out["logZ"], out["lb_q4"], out["B"] = float(s[o]), float(s[o + 1]), int(round(s[o + 2]))
+        return out
+
+    def pack_emit(self, mu, sigma, kappa, nu):
+        """(K,D), (K,D,D)|(K,D), (K,)|(K,D), (K,)|(K,D) -> (K, plen) float64."""
+        K, D = self.K, self.D
+        out = np.empty((K, self.plen))
+        mu = _f64(mu).reshape(K, D)
+        if self.emission == "niw_full":
+            out[:, :D] = mu
+            out[:, D:D + D * D] = _f64(sigma).reshape(K, D * D)
+            out[:, D + D * D] = _f64(kappa).reshape(K)
+            out[:, D + D * D + 1] = _f64(nu).reshape(K)
+        else:
+            out[:, :D] = mu
+            out[:, D:2 * D] = _f64(sigma).reshape(K, D)
+            out[:, 2 * D:3 * D] = np.broadcast_to(_f64(kappa).reshape(K, -1), (K, D))
+            out[:, 3 * D:] = np.broadcast_to(_f64(nu).reshape(K, -1), (K, D))
+        return out
+
+    def unpack_emit(self, em):
+        K, D = self.K, self.D
+        em = np.asarray(em).reshape(K, self.plen)
+        if self.emission == "niw_full":
+            return dict(mu=em[:, :D].copy(), sigma=em[:, D:D + D * D].reshape(K, D, D).copy(),
+                        kappa=em[:, D + D * D].copy(), nu=em[:, D + D * D + 1].copy())
+        return dict(mu=em[:, :D].copy(), sigma=em[:, D:2 * D].copy(), kappa=em[:, 2 * D:3 * D].copy(),
+                    nu=em[:, 3 * D:].copy())
