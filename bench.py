@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the SVI-HMM local E-step path: meta-observation E-steps/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|...]
+
+One "step" = one global step of hmmsgd_metaobs.VBHMM.infer for a minibatch of B windows per GPU:
+the batched E-step (emission log-likelihoods, forward, backward, marginals, sufficient statistics;
+reference hmmsgd_metaobs.py:405-436), the all-reduce of the packed statistics when N > 1, and the
+natural-gradient update (:1010-1069).  value = windows processed by all ranks / time (weak
+scaling: B windows per GPU).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "meta-obs E-steps/sec (batched fwd-bwd, K states)"
+CONFIGS = {
+    # name: K, D, T, B per GPU, emission kind          (BASELINE.json configs[1] / configs[2])
+    "c2": dict(K=16, D=8, T=512, B=256, kind="niw_diag",
+               workload="configs[1]: K=16 diag-Gaussian, D=8, T=512, 256 meta-obs minibatch per GPU"),
+    "c3": dict(K=64, D=32, T=1024, B=512, kind="niw_full",
+               workload="configs[2]: K=64 full-cov Gaussian, D=32, T=1024, 512 meta-obs per GPU"),
+}
+T_FULL = 1 << 23          # rows of the synthetic series: 8.4M x D fp32 (268 MB at D=8) > 126 MB of L2
+
+
+def synthetic_series(K, D, T_full, seed, sep=3.0):
+    """Sticky-chain Gaussian HMM series, vectorised (state changes with prob 0.1 per step)."""
+    rs = np.random.RandomState(seed)
+    mus = sep * rs.randn(K, D)
+    change = rs.rand(T_full) < 0.1
+    seg = np.cumsum(change)
+    seg_state = rs.randint(0, K, seg[-1] + 1)
+    sts = seg_state[seg]
+    obs = (mus[sts] + rs.standard_normal((T_full, D))).astype(np.float32)
+    return obs, mus
+
+
+def globals_for(K, D, kind, mus, seed):
+    """var_tran = 1 + 5 rand; NIW per state around the true means."""
+    rs = np.random.RandomState(seed + 1)
+    var_tran = 1. + 5. * rs.rand(K, K)
+    emit, prior = [], []
+    for k in range(K):
+        mu = mus[k] + 0.5 * rs.randn(D)
+        if kind == "niw_full":
+            nu = D + 3.
+            emit.append(dict(mu=mu, sigma=(nu - D - 1) * np.eye(D), kappa=1., nu=nu))
+            prior.append(dict(mu=np.zeros(D), sigma=np.eye(D), kappa=0.01, nu=D + 2.))
+        else:
+            emit.append(dict(mu=mu, sigma=2. * np.ones(D), kappa=np.ones(D), nu=4. * np.ones(D)))
+            prior.append(dict(mu=np.zeros(D), sigma=np.ones(D), kappa=0.01 * np.ones(D), nu=3. * np.ones(D)))
+    return var_tran, emit, prior
+
+
+class ClockSampler(object):
+    """SM clock and throttle reasons DURING the timed region, polled through NVML (the same
+    counters as the nvidia-smi line of B200_PROFILING.md, at ~1 ms instead of >=50 ms period so
+    that a timed region of a few milliseconds still gets samples)."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.stop_flag, self.thr, self.err = gpu_index, [], False, None, None
+
+    def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.N, self.h = N, N.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
+
+    def _poll(self):
+        N = self.N
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                rs = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.perf_counter(), float(sm), int(rs)))
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.0005)
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self.thr.join(1.0)
+        N = self.N
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-1:]
+        names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference / CPU arm
+# ------------------------------------------------------------------------------------------------
+def _load_reference():
+    """The reference's own classes (oracle/_ref = its sources patched mechanically to Python 3 by
+    oracle/build_ref.py), or None."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "hmmsgd_metaobs.py")):
+        return None
+    import warnings
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ref)
+    try:
+        import hmmsgd_metaobs as HS
+        from pybasicbayes.distributions import Gaussian
+        return HS, Gaussian
+    except Exception:
+        sys.path.remove(ref)
+        return None
+
+
+def cpu_estep_rate(cfg, budget_s, max_windows, seed=0):
+    """E-steps/sec of the reference CPU path on a bounded sample of the workload: the loop body of
+    hmmsgd_metaobs.py:405-436 (eig init, local_update, intermediate_pars, local_lower_bound) per
+    window, float64, numpy with all the BLAS threads it takes.  The reference needs odd windows
+    T = 2L+1, so it runs T-1 (=511 for c2) timesteps per E-step."""
+    K, D, T = cfg["K"], cfg["D"], cfg["T"]
+    Lh = (T - 1) // 2
+    n = 200000
+    obs32, mus = synthetic_series(K, D, n, seed)
+    obs = obs32.astype(np.float64)
+    var_tran, emit, prior = globals_for(K, D, cfg["kind"], mus, seed)
+    starts = np.random.RandomState(seed + 2).randint(0, n - (2 * Lh + 1), max_windows)
+    ref = _load_reference()
+    done, t0 = 0, time.perf_counter()
+    if ref is not None:
+        HS, Gaussian = ref
+        full = lambda v: np.diag(v) if np.ndim(v) == 1 else v          # diag config == full-cov with diagonal scale
+        sc = lambda v: float(np.ravel(v)[0])
+        objs = np.array([Gaussian(mu=e["mu"].copy(), sigma=full(e["sigma"]).copy(), mu_0=p["mu"],
+                                  sigma_0=full(p["sigma"]), kappa_0=sc(p["kappa"]), nu_0=sc(p["nu"]) + D - 1,
+                                  kappa_mf=sc(e["kappa"]), nu_mf=sc(e["nu"]) + D - 1)
+                         for e, p in zip(emit, prior)])
+        hmm = HS.VBHMM(obs, np.ones(K), np.ones((K, K)), objs, metaobs_half=Lh, mb_sz=max_windows,
+                       init_tran=var_tran, maxit=1, seed=seed)
+        t0 = time.perf_counter()
+        for s in starts:
+            mo = HS.MetaObs(int(s), int(s) + 2 * Lh)
+            A_mean = hmm.var_tran / np.sum(hmm.var_tran, axis=1)[:, np.newaxis]     # :413-418
+            ew, ev = np.linalg.eig(A_mean.T)
+            hmm.var_init = np.abs(ev[:, np.argsort(ew)[::-1][0]])
+            hmm.local_update(metaobs=mo)                                            # :422
+            hmm.intermediate_pars(mo)                                               # :428
+            hmm.local_lower_bound()                                                 # :436
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        kind = "reference"
+    else:
+        from oracle import svihmm_oracle as O
+        t0 = time.perf_counter()
+        for s in starts:
+            O.svi_minibatch_step(obs, None, [int(s)], 2 * Lh + 1, var_tran, emit, np.ones((K, K)), prior,
+                                 0.5, Lh)
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        kind = "port"
+    dt = time.perf_counter() - t0
+    return dict(value=done / dt, unit="E-steps/s", cores=os.cpu_count(), kind=kind,
+                sample="%d windows of T=%d (reference needs odd 2L+1), K=%d D=%d, float64, %.1f s; "
+                       "numpy/BLAS threads as the reference runs (single Python process)" % (
+                           done, 2 * Lh + 1, K, D, dt)), done, dt
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2, int(12.0 / max(args.steps, 1) * 36))      # ~12 s/step budget caps below
+    t_all0 = time.perf_counter()
+    tot, tt = 0, 0.0
+    for i in range(args.warmup):
+        cpu_estep_rate(cfg, 1.0, 8, seed=100 + i)
+    budget = min(10.0, 150.0 / max(args.steps, 1))
+    cb = None
+    for i in range(args.steps):
+        cb, done, dt = cpu_estep_rate(cfg, budget, per_step, seed=i)
+        tot += done; tt += dt
+    val = tot / tt
+    cb["value"] = val
+    cb["sample"] = "%d steps, each a sample of <=%d windows (%.0f s cap): " % (args.steps, per_step, budget) + cb["sample"]
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "E-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": cfg["workload"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "E-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine, pack_emit_dicts as pack_emit_np
+    from pysvihmm_b200.sharding import allreduce_stats
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], cfg["B"], cfg["kind"]
+    obs_host, mus = synthetic_series(K, D, T_FULL, seed=8675309)       # same series on every rank
+    var_tran, emit, prior = globals_for(K, D, kind, mus, seed=8675309)
+    eng = EStepEngine(K, D, kind, device=local)
+    eng.set_series(torch.from_numpy(obs_host).to(dev))
+    eng.set_prior(np.ones((K, K)), pack_emit_np(prior))
+    em0 = pack_emit_np(emit)
+    eng.set_globals(var_tran, em0)
+    flags = L.WRAP | L.ADD_PRIOR
+    Lh, S = T // 2, B * world
+    bA = (T_FULL - 2 * Lh - 1) / (2. * Lh * S)
+    bE = (T_FULL - 2 * Lh - 1) / ((2. * Lh + 1.) * S)
+    nst = args.warmup + args.steps
+    # every step draws fresh windows (as metaobs_unif does): rank r takes its own B of the N*B
+    g = torch.Generator().manual_seed(1234)
+    all_starts = torch.randint(0, T_FULL - T, (nst, world, B), generator=g)[:, rank].contiguous()
+    starts_dev = all_starts.to(dev)
+    var_x = torch.empty((B, T, K), dtype=torch.float32, device=dev)
+    stats = eng.new_stats()
+
+    def step(i, it):
+        eng.estep(starts_dev[i], T, flags=flags, var_x=var_x, stats=stats)
+        if world > 1:
+            allreduce_stats(stats, dist)
+        eng.global_update(stats, (it + 1.) ** -0.7, bA, bE)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i, i)
+    sync()
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    eng.set_profiling(True)
+    eng.phase_ms()
+    l0 = eng.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record()
+    for i in range(args.warmup, nst):
+        step(i, i)
+    e1.record()
+    sync()
+    tw1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    phases = eng.phase_ms()
+    eng.set_profiling(False)
+    clk = clocks.stop(tw0, tw1) if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- timed region 2: end to end through the host-buffer call --------------------------------
+    eng.set_globals(var_tran, em0)
+    eng.set_series_streamed(obs_host)
+    stats_h = np.empty(eng.slen)
+    starts_h = all_starts.numpy()
+    stats_d = eng.new_stats()
+    stats_pin = torch.empty(eng.slen, dtype=torch.float64).pin_memory()
+
+    def step_host(i, it):
+        eng.estep_host(starts_h[i], T, flags=flags, stats_out=stats_h)      # H2D windows, D2H stats, sync
+        if world > 1:
+            stats_pin.copy_(torch.from_numpy(stats_h))
+            stats_d.copy_(stats_pin, non_blocking=True)
+            allreduce_stats(stats_d, dist)
+        else:
+            stats_d.copy_(torch.from_numpy(stats_h), non_blocking=False)
+        eng.global_update(stats_d, (it + 1.) ** -0.7, bA, bE)
+
+    for i in range(args.warmup):
+        step_host(i, i)
+    sync()
+    e0.record()
+    for i in range(args.warmup, nst):
+        step_host(i, i)
+    e1.record()
+    sync()
+    ms2 = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms2 = float(tmax.item())
+    e2e = world * B * args.steps / (ms2 * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg_bytes = T * (D * 4 + K * 4)                      # read window once, write var_x once
+        dom = max(phases.items(), key=lambda kv: kv[1][0]) if phases else ("none", (0.0, 0))
+        dom_ms = dom[1][0] / max(dom[1][1], 1)
+        ach = B * alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        step_ach = B * alg_bytes / (ms / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "E-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 recursions, f64 emission log-lik + statistics",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "K": K, "D": D, "T": T, "B_per_gpu": B,
+                       "series": "%d x %d fp32 (%.0f MB) resident in HBM, larger than L2; fresh random "
+                                 "windows every step (no L2 flush needed)" % (T_FULL, D, T_FULL * D * 4 / 1e6),
+                       "step": "E-step (B windows) + %sglobal natural-gradient update" % (
+                           "NCCL all-reduce of packed statistics + " if world > 1 else ""),
+                       "var_x_written": True},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_estep": alg_bytes,
+                         "whole_step_achieved": step_ach, "whole_step_frac": step_ach / peak,
+                         "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}},
+            "e2e": {"value": e2e, "unit": "E-steps/s", "ms_per_step": ms2 / args.steps,
+                    "h2d_bytes_per_step": B * T * D * 4 + B * 8, "d2h_bytes_per_step": eng.slen * 8},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _, _ = cpu_estep_rate(cfg, 12.0, 400)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,16 @@ int svihmm_get_locals(svihmm_ctx* ctx, double* lliks, float* alpha, double* mx, 
 /* Number of kernels the engine launched on this ctx since creation (bench bookkeeping). */
 int64_t svihmm_launch_count(const svihmm_ctx* ctx);
 
+/* Optional per-phase device timing (bench bookkeeping; the reference's only instrumentation is
+ * the wall clock iter_time, hmmsgd_metaobs.py:348,441).  While enabled every compute entry point
+ * brackets its phases with CUDA events on the caller's stream.  svihmm_get_phase_ms waits for the
+ * recorded events, returns the summed milliseconds and the number of recorded intervals per phase
+ * since the last call, and resets.  Phases are named by svihmm_phase_name(i), i < SVIHMM_N_PHASES. */
+enum { SVIHMM_N_PHASES = 8 };
+int svihmm_set_profiling(svihmm_ctx* ctx, int on);
+int svihmm_get_phase_ms(svihmm_ctx* ctx, double* ms, int64_t* counts);
+const char* svihmm_phase_name(int phase);
+
 #ifdef __cplusplus
 }
 #endif

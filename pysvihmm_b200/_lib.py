@@ -11,6 +11,7 @@ EMIT_NIW_FULL, EMIT_NIW_DIAG = 0, 1
 F32, F64 = 0, 1
 LOC_DEVICE, LOC_HOST = 0, 1
 WRAP, ADD_PRIOR, MASK_LL, EXACT_XI = 1, 2, 4, 8
+N_PHASES = 8
 
 _vp, _i, _i64, _d, _u = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint
 # name -> (restype, argtypes); must list every symbol include/svihmm.h declares
@@ -32,6 +33,9 @@ SYMBOLS = {
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_launch_count": (_i64, [_vp]),
+    "svihmm_set_profiling": (_i, [_vp, _i]),
+    "svihmm_get_phase_ms": (_i, [_vp, _vp, _vp]),
+    "svihmm_phase_name": (C.c_char_p, [_i]),
 }
 
 _lib = None

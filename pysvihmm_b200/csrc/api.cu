@@ -27,6 +27,51 @@ static int fail(int code, const char* fmt, ...) {
 extern "C" const char* svihmm_last_error(void) { return g_err.c_str(); }
 extern "C" int svihmm_version(void) { return 100; }
 
+// ---- per-phase event timing ------------------------------------------------------------------
+struct PhaseTimer {
+  svihmm_ctx* c; cudaStream_t st; cudaEvent_t stop; bool on;
+  PhaseTimer(svihmm_ctx* c_, int phase, cudaStream_t st_) : c(c_), st(st_), stop(nullptr), on(false) {
+    if (!c->profiling) return;
+    auto& pool = *c->ev_pool;
+    while (pool.size() < c->ev_used + 2) {
+      cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; pool.push_back(e);
+    }
+    cudaEventRecord(pool[c->ev_used], st);
+    stop = pool[c->ev_used + 1];
+    c->ev_used += 2;
+    c->ev_phase->push_back(phase);
+    on = true;
+  }
+  ~PhaseTimer() { if (on) cudaEventRecord(stop, st); }
+};
+
+extern "C" int svihmm_set_profiling(svihmm_ctx* c, int on) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  c->profiling = on ? 1 : 0;
+  return SVIHMM_OK;
+}
+
+extern "C" const char* svihmm_phase_name(int p) {
+  static const char* names[SVIHMM_N_PHASES] = {"emit", "forward", "backward", "stats", "update",
+                                               "gather", "fused", "other"};
+  return (p >= 0 && p < SVIHMM_N_PHASES) ? names[p] : "?";
+}
+
+extern "C" int svihmm_get_phase_ms(svihmm_ctx* c, double* ms, int64_t* counts) {
+  if (!c || !ms || !counts) return fail(SVIHMM_EINVAL, "NULL argument");
+  for (int i = 0; i < SVIHMM_N_PHASES; ++i) { ms[i] = 0.0; counts[i] = 0; }
+  CU(cudaSetDevice(c->device));
+  for (size_t i = 0; i < c->ev_phase->size(); ++i) {
+    cudaEvent_t a = (*c->ev_pool)[2 * i], b = (*c->ev_pool)[2 * i + 1];
+    CU(cudaEventSynchronize(b));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, a, b));
+    ms[(*c->ev_phase)[i]] += t; counts[(*c->ev_phase)[i]]++;
+  }
+  c->ev_phase->clear(); c->ev_used = 0;
+  return SVIHMM_OK;
+}
+
 static int next_pow2(int k) { int p = 2; while (p < k) p <<= 1; return p; }
 
 template <typename Tp> static cudaError_t dalloc(Tp** p, size_t n) {
@@ -46,6 +91,7 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(cudaSetDevice(device));
   svihmm_ctx* c = (svihmm_ctx*)calloc(1, sizeof(svihmm_ctx));
   if (!c) return fail(SVIHMM_ENOMEM, "calloc");
+  c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : D;
   c->plen = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)D + (size_t)D * D + 2 : (size_t)4 * D;
@@ -81,6 +127,8 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
+  for (cudaEvent_t e : *c->ev_pool) cudaEventDestroy(e);
+  delete c->ev_pool; delete c->ev_phase;
   free(c);
   return SVIHMM_OK;
 }
@@ -247,10 +295,12 @@ static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStrea
   const int wpb = warps <= 4 * 148 ? 1 : 4;
   const int grid = (warps + wpb - 1) / wpb;
   float* cs = (float*)(c->mx_ws + (size_t)B * T);   // second half of mx_ws holds the scale factors
-  k_forward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
-  c->launches++;
-  k_backward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->b_ws, c->alpha_ws, q, r);
-  c->launches++;
+  { PhaseTimer pt(c, PH_FORWARD, st);
+    k_forward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
+    c->launches++; }
+  { PhaseTimer pt(c, PH_BACKWARD, st);
+    k_backward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->b_ws, c->alpha_ws, q, r);
+    c->launches++; }
 }
 
 static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
@@ -263,6 +313,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   const int64_t R = (int64_t)B * T;
   const int mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
   // K1: expected log-likelihoods (fp64) -> scaled likelihoods b (fp32) + row maxima
+  { PhaseTimer pt(c, PH_EMIT, st);
   if (c->kind == SVIHMM_EMIT_NIW_FULL) {
     const size_t smem = ((size_t)EMIT_ROWS * D + (size_t)D * (D + 1) / 2 + D) * sizeof(double);
     if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the emission kernel", D);
@@ -279,6 +330,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   LAUNCHED(c);
   k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
   LAUNCHED(c);
+  }
   // K2/K3: forward, backward + marginals
   float* q = var_x_out ? var_x_out : c->q_ws;
   float* r = xi ? c->r_ws : nullptr;
@@ -298,12 +350,15 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       CU(cudaFuncSetAttribute(k_forward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(cudaFuncSetAttribute(k_backward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
-    c->launches++;
-    k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r);
-    c->launches++;
+    { PhaseTimer pt(c, PH_FORWARD, st);
+      k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
+      c->launches++; }
+    { PhaseTimer pt(c, PH_BACKWARD, st);
+      k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r);
+      c->launches++; }
   }
   CU(cudaGetLastError());
+  PhaseTimer pt_stats(c, PH_STATS, st);
   k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
   LAUNCHED(c);
   // K4: statistics
@@ -429,6 +484,7 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
     const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
     const size_t units = (size_t)T * rowbytes / (vec16 ? 16 : 4);
     dim3 grid((unsigned)((units + 255) / 256 > 64 ? 64 : (units + 255) / 256), B);
+    PhaseTimer pt(c, PH_GATHER, st);
     k_gather_windows<<<grid, 256, 0, st>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
                                            has_mask ? c->hmask_dev : nullptr, c->stage_src,
                                            (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, vec16);
@@ -472,6 +528,7 @@ extern "C" int svihmm_global_update(svihmm_ctx* c, const double* stats, double l
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int K = c->K, D = c->D;
+  PhaseTimer pt(c, PH_UPDATE, st);
   k_update_tran_svi<<<(K * K + 255) / 256, 256, 0, st>>>(K * K, c->W, stats, lrate, bA);
   LAUNCHED(c);
   if (c->kind == SVIHMM_EMIT_NIW_FULL)
@@ -488,6 +545,7 @@ extern "C" int svihmm_batch_update(svihmm_ctx* c, const double* stats, void* str
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int K = c->K, D = c->D;
+  PhaseTimer pt(c, PH_UPDATE, st);
   k_update_tran_batch<<<(K * K + 255) / 256, 256, 0, st>>>(K, c->W, c->vinit + K, c->prior_tran,
                                                           c->prior_init, stats, D, c->DD);
   LAUNCHED(c);

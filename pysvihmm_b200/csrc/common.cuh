@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <vector>
 
 #include "../../include/svihmm.h"
 
@@ -38,7 +39,14 @@ struct svihmm_ctx {
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws;
   int last_B, last_T;
   int64_t launches;
+  // optional per-phase event timing
+  int profiling;
+  std::vector<cudaEvent_t>* ev_pool;                 // all events ever created (reused after a read)
+  std::vector<int>* ev_phase;                        // phase of each recorded (start, stop) pair
+  size_t ev_used;
 };
+
+enum { PH_EMIT = 0, PH_FORWARD, PH_BACKWARD, PH_STATS, PH_UPDATE, PH_GATHER, PH_FUSED, PH_OTHER };
 
 __device__ __forceinline__ double ld_obs(const void* obs, int dtype, int64_t idx) {
   return dtype == SVIHMM_F32 ? (double)__ldg((const float*)obs + idx) : __ldg((const double*)obs + idx);

@@ -27,6 +27,22 @@ def _f64(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
 
 
+def pack_emit_dicts(emit):
+    """list of dict(mu, sigma, kappa, nu) -> (K, plen) float64 in the layout of include/svihmm.h
+    (sigma 2-D = full NIW, 1-D = diagonal)."""
+    rows = []
+    for e in emit:
+        mu = np.asarray(e["mu"], dtype=np.float64).ravel()
+        D = mu.size
+        sg = np.asarray(e["sigma"], dtype=np.float64)
+        if sg.ndim == 2:
+            rows.append(np.concatenate([mu, sg.ravel(), [float(e["kappa"])], [float(e["nu"])]]))
+        else:
+            rows.append(np.concatenate([mu, sg, np.broadcast_to(np.asarray(e["kappa"], float), (D,)),
+                                        np.broadcast_to(np.asarray(e["nu"], float), (D,))]))
+    return np.array(rows)
+
+
 class EStepEngine(object):
     """One engine = one svihmm_ctx on one GPU.
 
@@ -173,6 +189,17 @@ class EStepEngine(object):
 
     def launch_count(self):
         return int(self.lib.svihmm_launch_count(self._h))
+
+    def set_profiling(self, on=True):
+        L.check(self.lib.svihmm_set_profiling(self._h, int(bool(on))))
+
+    def phase_ms(self):
+        """{phase name: (summed device ms, intervals)} since the last call (waits for the events)."""
+        ms = (C.c_double * L.N_PHASES)()
+        cnt = (C.c_int64 * L.N_PHASES)()
+        L.check(self.lib.svihmm_get_phase_ms(self._h, ms, cnt))
+        return {self.lib.svihmm_phase_name(i).decode(): (ms[i], int(cnt[i])) for i in range(L.N_PHASES)
+                if cnt[i]}
 
     # ------------------------------------------------------------------ packing helpers
     def unpack_stats(self, stats):

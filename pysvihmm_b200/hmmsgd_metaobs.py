@@ -14,6 +14,7 @@ import numpy.random as npr
 
 from . import _lib as L
 from .hmmbase import VariationalHMMBase
+from .sharding import allreduce_stats, dist_or_none as _dist, shard_starts
 
 eps = 1e-9
 tau0 = 1.
@@ -28,16 +29,6 @@ class MetaObs(object):
     def __init__(self, i1, i2):
         self.i1 = i1
         self.i2 = i2
-
-
-def _dist():
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist
-    except Exception:
-        pass
-    return None
 
 
 class VBHMM(VariationalHMMBase):
@@ -159,10 +150,9 @@ class VBHMM(VariationalHMMBase):
         T = int(minibatch[0].i2 - minibatch[0].i1 + 1)
         dist = _dist()
         if dist is not None:
-            starts = starts[dist.get_rank()::dist.get_world_size()]
+            starts = shard_starts(starts, dist.get_rank(), dist.get_world_size())
         vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x)
-        if dist is not None:
-            dist.all_reduce(stats)          # one sum all-reduce of the packed statistics per step
+        allreduce_stats(stats, dist)        # one sum all-reduce of the packed statistics per step
         self._var_x_batch = vx
         self._last_B, self._last_T = len(starts), T
         return stats

@@ -1,0 +1,315 @@
+"""Parity of the CUDA path (through the C ABI of libsvihmm.so) against
+ (a) outputs of the reference itself (tests/golden/*.npz), and
+ (b) the float64 oracle on seeded inputs at sizes the oracle finishes in seconds.
+
+Tolerances (north_star: state marginals within 1e-5 relative of the reference):
+  var_x        |q - q_ref| <= 1e-5 * q_ref + 2e-7       (float32 output; 2e-7 ~ 2 ulp of 1.0)
+  statistics   rtol 1e-5 relative to the largest entry of each block
+  new globals  rtol 1e-5 (sigma: relative to its largest entry, eta3 - kappa mu mu^T cancels)
+  lliks        float64 kernel: rtol 1e-11
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import (SVI_CASES, emit_list, frac_soft, golden_prior_emit, load_golden,
+                           make_random_problem, pack_emit_np)
+
+pytestmark = pytest.mark.gpu
+
+Q_RTOL, Q_ATOL = 1e-5, 2e-7
+S_RTOL = 1e-5
+
+
+def _engine(K, D, kind="niw_full"):
+    from pysvihmm_b200.engine import EStepEngine
+    return EStepEngine(K, D, kind)
+
+
+def assert_q(q, q_ref):
+    err = np.abs(q.astype(np.float64) - q_ref)
+    bound = Q_RTOL * q_ref + Q_ATOL
+    worst = float(np.max(err - bound))
+    assert worst <= 0, "marginals off: max excess %.3e, max abs err %.3e" % (worst, err.max())
+
+
+def assert_block(a, ref, rtol=S_RTOL, what=""):
+    scale = max(float(np.max(np.abs(ref))), 1e-30)
+    err = float(np.max(np.abs(np.asarray(a, dtype=np.float64) - ref))) / scale
+    assert err <= rtol, "%s: relative-to-max error %.3e > %.1e" % (what, err, rtol)
+
+
+def oracle_stats(O, r, obs, mask, starts, T, wrap):
+    """Summed (over the minibatch) statistics from oracle marginals."""
+    K = r["var_x"].shape[-1]
+    A = O.tran_stat(r["var_x"], wrap).sum(0)
+    n = np.zeros(K); sx = np.zeros((K, obs.shape[1])); sxx = np.zeros((K, obs.shape[1], obs.shape[1]))
+    for b, s in enumerate(starts):
+        inds = ~mask[s:s + T]
+        x = np.nan_to_num(obs[s:s + T][inds])
+        w = r["var_x"][b][inds]
+        n += w.sum(0)
+        sx += w.T.dot(x)
+        sxx += np.einsum("tk,ti,tj->kij", w, x, x)
+    return A, n, sx, sxx
+
+
+@pytest.mark.parametrize("obs_dtype", ["f64", "f32"])
+@pytest.mark.parametrize("name", SVI_CASES)
+def test_svi_step_matches_reference_golden(name, obs_dtype):
+    """One engine call per global step reproduces the reference's per-window tables, summed
+    statistics (quirks Q1/Q2/Q5) and natural-gradient update (hmmsgd_metaobs.py:405-439)."""
+    from pysvihmm_b200 import _lib as L
+    g = load_golden(name)
+    obs, mask = g["obs"], g["mask"]
+    Lh, S = int(g["L"]), int(g["mb_sz"])
+    T = 2 * Lh + 1
+    K, D = g["init_tran"].shape[0], obs.shape[1]
+    eng = _engine(K, D)
+    eng.set_series(obs, mask, dtype=obs_dtype)
+    pe = golden_prior_emit(g, K)
+    eng.set_prior(g["prior_tran"], pack_emit_np(pe))
+    eng.set_globals(g["init_tran"], pack_emit_np(emit_list(g["init_mu"], g["init_sigma"],
+                                                            g["init_kappa"], g["init_nu"])))
+    f32 = obs_dtype == "f32"
+    for it in range(int(g["maxit"])):
+        starts = g["w_starts"][it]
+        vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+        q = vx.cpu().numpy()
+        # float32 storage of the series perturbs ll by ~|x| * 6e-8 * |dll/dx|: not a kernel error
+        if f32:
+            assert np.max(np.abs(q - g["w_var_x"][it])) < 2e-4
+        else:
+            assert_q(q, g["w_var_x"][it])
+            loc = eng.get_locals(S, T)
+            np.testing.assert_allclose(loc["lliks"], g["w_ll"][it], rtol=1e-11, atol=1e-11)
+            la = g["w_lalpha"][it]
+            np.testing.assert_allclose(loc["logZ"], np.logaddexp.reduce(la[:, -1], axis=-1), rtol=2e-6)
+            np.testing.assert_allclose(loc["lb_q4"], g["w_lb"][it], rtol=2e-6)
+            # softmax(lalpha[t]) == normalised forward message
+            sm = np.exp(la - np.logaddexp.reduce(la, axis=-1)[..., None])
+            assert np.max(np.abs(loc["alpha"] - sm)) < 2e-6
+        s = eng.unpack_stats(stats)
+        tol = 2e-4 if f32 else S_RTOL
+        assert_block(s["A"], g["w_A_i"][it].sum(0), tol, "A_inter")
+        assert_block(s["n"], g["w_e2"][it].sum(0), tol, "n")
+        assert_block(s["sx"], g["w_e1"][it].sum(0), tol, "sx")
+        assert_block(s["sxx"], g["w_e3"][it].sum(0), tol, "sxx")
+        assert s["B"] == S
+        bA = (obs.shape[0] - 2 * Lh - 1) / (2. * Lh * S)
+        bE = (obs.shape[0] - 2 * Lh - 1) / ((2. * Lh + 1.) * S)
+        eng.global_update(stats, float(g["g_lrate"][it]), bA, bE)
+        vt, vi, em = eng.get_globals()
+        e = eng.unpack_emit(em)
+        gtol = 5e-4 if f32 else S_RTOL
+        assert_block(vt, g["g_var_tran"][it], gtol, "var_tran")
+        assert_block(e["mu"], g["g_mu"][it], gtol, "mu")
+        assert_block(e["sigma"], g["g_sigma"][it], gtol, "sigma")
+        assert_block(e["kappa"], g["g_kappa"][it], gtol, "kappa")
+        assert_block(e["nu"], g["g_nu"][it], gtol, "nu")
+        if it + 1 < int(g["maxit"]):
+            np.testing.assert_allclose(vi, g["w_var_init"][it + 1][0], rtol=1e-5, atol=1e-9)
+        if not f32:
+            # keep the next iteration on the reference's trajectory (isolates per-step error)
+            eng.set_globals(g["g_var_tran"][it], pack_emit_np(emit_list(
+                g["g_mu"][it], g["g_sigma"][it], g["g_kappa"][it], g["g_nu"][it])))
+    eng.close()
+
+
+def test_stationary_init_matches_reference():
+    """Quirk Q3 (hmmsgd_metaobs.py:413-418): |top eigenvector|, unit L2 norm."""
+    g = load_golden("svi_k16_d8_l50")
+    K, D = 16, 8
+    eng = _engine(K, D)
+    eng.set_globals(g["init_tran"], pack_emit_np(emit_list(g["init_mu"], g["init_sigma"],
+                                                            g["init_kappa"], g["init_nu"])))
+    _, vi, _ = eng.get_globals()
+    np.testing.assert_allclose(vi, g["w_var_init"][0][0], rtol=1e-9)
+    assert abs(np.linalg.norm(vi) - 1.0) < 1e-12
+    eng.close()
+
+
+def test_batch_cavi_matches_reference_golden():
+    """hmmbatchcd.VBHMM.infer iterations (hmmbatchcd.py:135-141,172-189) on device."""
+    g = load_golden("cavi_k2_d2_t200")
+    K, D, T = 2, 2, g["obs"].shape[0]
+    eng = _engine(K, D)
+    eng.set_series(g["obs"], g["mask"], dtype="f64")
+    eng.set_prior(g["prior_tran"], pack_emit_np(golden_prior_emit(g, K)), g["prior_init"])
+    eng.set_globals(g["init_var_tran"], pack_emit_np(emit_list(
+        g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])), g["init_var_init"])
+    for it in range(len(g["it_lZ"])):
+        vx, stats = eng.estep([0], T, flags=0)
+        assert_q(vx[0].cpu().numpy(), g["it_var_x"][it])
+        s = eng.unpack_stats(stats)
+        np.testing.assert_allclose(s["lb_q4"], g["it_lZ"][it], rtol=2e-6)
+        eng.batch_update(stats)
+        vt, vi, em = eng.get_globals()
+        e = eng.unpack_emit(em)
+        assert_block(vi, g["it_var_init"][it], S_RTOL, "var_init")
+        assert_block(vt, g["it_var_tran"][it], S_RTOL, "var_tran")
+        assert_block(e["mu"], g["it_mu"][it], S_RTOL, "mu")
+        assert_block(e["sigma"], g["it_sigma"][it], S_RTOL, "sigma")
+        assert_block(e["kappa"], g["it_kappa"][it], S_RTOL, "kappa")
+        assert_block(e["nu"], g["it_nu"][it], S_RTOL, "nu")
+    eng.close()
+
+
+# (K, D, T, B, kind): covers every kernel mapping (lane groups KP=2..32, wide K>32), odd sizes
+ORACLE_CASES = [
+    (2, 1, 7, 3, "niw_full"),
+    (3, 2, 1, 4, "niw_full"),          # T = 1: no transitions at all
+    (7, 5, 33, 9, "niw_full"),
+    (16, 8, 512, 12, "niw_diag"),      # BASELINE config 2 shape (reduced B)
+    (16, 8, 511, 6, "niw_full"),
+    (32, 16, 129, 5, "niw_full"),
+    (33, 4, 64, 5, "niw_full"),        # first wide size
+    (64, 32, 257, 4, "niw_full"),      # BASELINE config 3 shape (reduced B, T)
+    (100, 3, 50, 3, "niw_diag"),
+]
+
+
+@pytest.mark.parametrize("K,D,T,B,kind", ORACLE_CASES)
+def test_estep_matches_oracle(K, D, T, B, kind):
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    p = make_random_problem(seed=K * 1000 + T, K=K, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1)
+    starts = np.random.RandomState(5).randint(0, p["obs"].shape[0] - T + 1, B)
+    eng = _engine(K, D, kind)
+    eng.set_series(p["obs"], p["mask"], dtype="f64")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    for flags, wrap, mask_ll in [(L.WRAP | L.ADD_PRIOR, True, False), (L.MASK_LL, False, True)]:
+        vx, stats = eng.estep(starts, T, flags=flags)
+        r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"],
+                                 p["prior_tran"], p["prior_emit"], 0.5, max(T // 2, 1), wrap=wrap,
+                                 mask_ll=mask_ll)
+        q = vx.cpu().numpy()
+        assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+        assert_q(q, r["var_x"])
+        loc = eng.get_locals(B, T)
+        np.testing.assert_allclose(loc["lliks"], r["ll"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(loc["logZ"], r["logZ"], rtol=3e-6, atol=1e-4)
+        s = eng.unpack_stats(stats)
+        A = np.zeros((K, K)); n = np.zeros(K); sx = np.zeros((K, D))
+        sxx = np.zeros((K, D, D) if kind == "niw_full" else (K, D))
+        A = O.tran_stat(r["var_x"], wrap).sum(0) + (B * (p["prior_tran"] - 1.) if wrap else 0.)
+        for k in range(K):
+            n[k] = r["emit_inter"][k][1]
+            sx[k] = r["emit_inter"][k][0]
+            sxx[k] = r["emit_inter"][k][2]
+        assert_block(s["A"], A, S_RTOL, "A")
+        assert_block(s["n"], n, S_RTOL, "n")
+        assert_block(s["sx"], sx, S_RTOL, "sx")
+        assert_block(s["sxx"], sxx, S_RTOL, "sxx")
+        assert_block(s["q0"], r["var_x"][:, 0].sum(0), S_RTOL, "q0")
+        np.testing.assert_allclose(s["logZ"], r["logZ"].sum(), rtol=3e-6)
+        np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=3e-6)
+    # natural-gradient step from the (WRAP|ADD_PRIOR) statistics
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+    r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"],
+                             p["prior_tran"], p["prior_emit"], 0.37, max(T // 2, 1), wrap=True)
+    Lh, Tf = max(T // 2, 1), p["obs"].shape[0]
+    eng.global_update(stats, 0.37, (Tf - 2 * Lh - 1) / (2. * Lh * B), (Tf - 2 * Lh - 1) / ((2. * Lh + 1.) * B))
+    vt, vi, em = eng.get_globals()
+    e = eng.unpack_emit(em)
+    assert_block(vt, r["var_tran_new"], S_RTOL, "var_tran")
+    for key in ("mu", "sigma", "kappa", "nu"):
+        ref = np.array([np.broadcast_to(x[key], e[key][0].shape) for x in r["emit_new"]])
+        assert_block(e[key], ref, S_RTOL, key)
+    np.testing.assert_allclose(vi, O.stationary_init(r["var_tran_new"]), rtol=1e-5, atol=1e-9)
+    eng.close()
+
+
+def test_exact_xi_option_matches_oracle():
+    """SVIHMM_EXACT_XI (not reference behaviour): sum_t of the true pairwise posteriors."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    for K, D, T, B in [(5, 3, 40, 6), (40, 4, 30, 3)]:
+        p = make_random_problem(seed=77 + K, K=K, D=D, T_full=400, kind="niw_full", miss=0.0)
+        starts = np.arange(B) * 17
+        eng = _engine(K, D)
+        eng.set_series(p["obs"], None, dtype="f64")
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        _, stats = eng.estep(starts, T, flags=L.EXACT_XI)
+        xw = p["obs"][starts[:, None] + np.arange(T)[None]]
+        r = O.local_update(xw, O.stationary_init(p["var_tran"]), p["var_tran"], p["emit"])
+        assert_block(eng.unpack_stats(stats)["A"], O.exact_xi_stat(r).sum(0), S_RTOL, "xi")
+        eng.close()
+
+
+def test_nan_rows_carry_no_evidence():
+    """np.nan_to_num semantics (hmmsgd_metaobs.py:508-509): a NaN row gives ll[t,:] = 0 and is
+    dropped from the emission statistics."""
+    from oracle import svihmm_oracle as O
+    K, D, T = 4, 3, 60
+    p = make_random_problem(seed=3, K=K, D=D, T_full=T, kind="niw_full", miss=0.0)
+    obs = p["obs"].copy()
+    obs[[0, 7, 8, 30, T - 1]] = np.nan
+    obs[12, 1] = np.nan
+    eng = _engine(K, D)
+    eng.set_series(obs, None, dtype="f64")
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep([0], T, flags=0)
+    r = O.local_update(obs[None], O.stationary_init(p["var_tran"]), p["var_tran"], p["emit"])
+    assert np.all(r["ll"][0, 7] == 0)
+    assert_q(vx.cpu().numpy(), r["var_x"])
+    s = eng.unpack_stats(stats)
+    good = ~np.isnan(obs).any(1)
+    assert_block(s["n"], r["var_x"][0][good].sum(0), S_RTOL, "n")
+    assert_block(s["sx"], r["var_x"][0][good].T.dot(obs[good]), S_RTOL, "sx")
+    eng.close()
+
+
+def test_all_masked_window_and_b1():
+    from pysvihmm_b200 import _lib as L
+    K, D, T = 3, 2, 20
+    p = make_random_problem(seed=4, K=K, D=D, T_full=T, kind="niw_full", miss=0.0)
+    eng = _engine(K, D)
+    eng.set_series(p["obs"], np.ones(T, bool), dtype="f64")
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep([0], T, flags=L.MASK_LL)
+    s = eng.unpack_stats(stats)
+    assert np.all(s["n"] == 0) and np.all(s["sx"] == 0) and np.all(s["sxx"] == 0)
+    q = vx.cpu().numpy()
+    assert np.allclose(q.sum(-1), 1, atol=1e-6) and np.isfinite(q).all()
+    eng.close()
+
+
+def test_host_call_equals_device_call():
+    """svihmm_estep_host (host buffers, windows gathered host->device inside the call) gives the
+    same statistics and marginals as svihmm_estep on the HBM-resident series."""
+    from pysvihmm_b200 import _lib as L
+    K, D, T, B = 16, 8, 128, 37
+    for dt in (np.float32, np.float64):
+        p = make_random_problem(seed=9, K=K, D=D, T_full=5000, kind="niw_diag", miss=0.05)
+        obs = p["obs"].astype(dt)
+        starts = np.random.RandomState(1).randint(0, 5000 - T + 1, B)
+        eng = _engine(K, D, "niw_diag")
+        eng.set_series(obs, p["mask"])
+        eng.set_series_streamed(obs, p["mask"])
+        eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+        vxh, sh = eng.estep_host(starts, T, flags=L.WRAP | L.ADD_PRIOR, want_var_x=True)
+        assert np.array_equal(vx.cpu().numpy(), vxh)
+        assert np.array_equal(stats.cpu().numpy(), sh)
+        eng.close()
+
+
+def test_error_paths():
+    from pysvihmm_b200 import SvihmmError
+    eng = _engine(3, 2)
+    with pytest.raises(SvihmmError):
+        eng.estep([0], 5)                      # no globals yet
+    p = make_random_problem(seed=1, K=3, D=2, T_full=30, kind="niw_full")
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    with pytest.raises(SvihmmError):
+        eng.estep([0], 5)                      # no series yet
+    eng.set_series(p["obs"], None)
+    with pytest.raises(SvihmmError):
+        eng.estep([0], 31)                     # window longer than the series
+    with pytest.raises(SvihmmError):
+        eng.estep([0], 5, flags=2)             # ADD_PRIOR without priors
+    eng.close()
+    with pytest.raises(SvihmmError):
+        _engine(0, 2)
