@@ -59,7 +59,8 @@ enum {
   SVIHMM_WRAP        = 1u << 0, /* include outer(q[T-1], q[0]) (quirk Q2, hmmsgd_metaobs.py:877-878) */
   SVIHMM_ADD_PRIOR   = 1u << 1, /* add (prior_tran-1) once per window (quirk Q5, :876,881)           */
   SVIHMM_MASK_LL     = 1u << 2, /* masked rows carry no evidence: ll[t,:]=0 (:1167-1168,1176)        */
-  SVIHMM_EXACT_XI    = 1u << 3  /* A = sum_t true pairwise posterior instead of outer(q,q) (NOT ref) */
+  SVIHMM_EXACT_XI    = 1u << 3, /* A = sum_t true pairwise posterior instead of outer(q,q) (NOT ref) */
+  SVIHMM_KEEP_LOCALS = 1u << 4  /* keep lliks/alpha/cs tables for svihmm_get_locals (unfused kernels) */
 };
 
 const char* svihmm_last_error(void);
@@ -133,7 +134,8 @@ int svihmm_batch_update(svihmm_ctx* ctx, const double* stats, void* stream);
  *   cs     B*T   float32  forward scale factors c_t, so that
  *                         self.lalpha[t,k] = log alpha[t,k] + sum_{u<=t} (log cs[u] + mx[u])
  *   logz   B*2   float64  per window [logZ, Q4 bound (hmmsgd_metaobs.py:257-271)]
- * Any of them may be NULL. */
+ * Any of them may be NULL.  lliks/alpha/mx/cs need the last E-step to have run with
+ * SVIHMM_KEEP_LOCALS (the fused single-kernel path keeps these tables on chip only). */
 int svihmm_get_locals(svihmm_ctx* ctx, double* lliks, float* alpha, double* mx, float* cs,
                       double* logz, int loc, void* stream);
 

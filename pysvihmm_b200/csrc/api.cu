@@ -4,6 +4,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <stdarg.h>
+#include <algorithm>
 
 #include "common.cuh"
 #include "prep.cuh"
@@ -11,6 +12,7 @@
 #include "fb.cuh"
 #include "stats.cuh"
 #include "update.cuh"
+#include "fused.cuh"
 
 static thread_local std::string g_err;
 
@@ -91,6 +93,7 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(cudaSetDevice(device));
   svihmm_ctx* c = (svihmm_ctx*)calloc(1, sizeof(svihmm_ctx));
   if (!c) return fail(SVIHMM_ENOMEM, "calloc");
+  CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : D;
@@ -123,7 +126,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
                   c->pi0, c->lu, c->rowsum, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws,
-                  c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws};
+                  c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -303,11 +306,87 @@ static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStrea
     c->launches++; }
 }
 
+template <int KP>
+static cudaError_t launch_fused(const FusedArgs& fa, size_t smem, cudaStream_t st, bool set_attr) {
+  if (set_attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_estep_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_estep_fused<KP><<<fa.B, FUSED_NT, smem, st>>>(fa);
+  return cudaGetLastError();
+}
+
+// Single-kernel E-step (fused.cuh) when the window fits in shared memory: K <= 32, the three
+// T*K float tables + per-row scalars + emission constants <= the opt-in limit.
+static bool fused_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
+  if (c->K > 32 || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+  const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
+  const FusedSmem L = fused_smem_layout(T, c->K, c->D, tri, diag);
+  if (L.total > (size_t)c->max_smem_optin) return false;
+  *smem_out = L.total;
+  return true;
+}
+
+static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
+                       const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
+                       unsigned flags, size_t smem, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  if ((size_t)B > c->cap_B) {
+    if (c->seq_ws) CU(cudaFree(c->seq_ws));
+    c->seq_ws = nullptr; c->cap_B = 0;
+    CU(dalloc(&c->seq_ws, 2 * (size_t)B));
+    c->cap_B = B;
+  }
+  PhaseTimer pt(c, PH_FUSED, st);
+  CU(cudaMemsetAsync(stats_out, 0, sizeof(double) * c->slen, st));
+  FusedArgs fa;
+  fa.B = B; fa.T = T; fa.K = K; fa.D = D; fa.DD = c->DD;
+  fa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+  fa.wrap = (flags & SVIHMM_WRAP) ? 1 : 0; fa.add_prior = (flags & SVIHMM_ADD_PRIOR) ? 1 : 0;
+  fa.mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
+  fa.tri = fa.diag ? D : D * (D + 1) / 2;
+  fa.obs = obs; fa.dtype = dtype; fa.mask = mask; fa.starts = starts;
+  fa.Pt = c->Pt; fa.pi0 = c->pi0; fa.Rs = c->Rs; fa.gk = c->gk; fa.ck = c->ck; fa.prior_tran = c->prior_tran;
+  fa.var_x_out = var_x_out; fa.stats_out = stats_out; fa.seq = c->seq_ws;
+  fa.o_n = (size_t)K * K; fa.o_sx = fa.o_n + K; fa.o_sxx = fa.o_sx + (size_t)K * D;
+  fa.o_q0 = fa.o_sxx + (size_t)K * c->DD; fa.o_tail = fa.o_q0 + K;
+  static const bool dbg_on = getenv("SVIHMM_FUSED_DBG") != nullptr;
+  fa.dbg = nullptr;
+  if (dbg_on) CU(cudaMalloc((void**)&fa.dbg, sizeof(long long) * 8 * B));
+  const bool set_attr = smem > 48 * 1024;
+  cudaError_t e;
+  switch (c->KP) {
+    case 2:
+    case 4: e = launch_fused<4>(fa, smem, st, set_attr); break;
+    case 8: e = launch_fused<8>(fa, smem, st, set_attr); break;
+    case 16: e = launch_fused<16>(fa, smem, st, set_attr); break;
+    default: e = launch_fused<32>(fa, smem, st, set_attr); break;
+  }
+  if (e != cudaSuccess) return fail(SVIHMM_ECUDA, "fused E-step launch failed: %s", cudaGetErrorString(e));
+  if (dbg_on) {            // debug: mean clock cycles per phase over the CTAs of this launch
+    std::vector<long long> h((size_t)8 * B);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h.data(), fa.dbg, sizeof(long long) * 8 * B, cudaMemcpyDeviceToHost));
+    CU(cudaFree(fa.dbg));
+    double ph[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) for (int i = 0; i < 5; ++i) ph[i] += (double)(h[8 * b + i + 1] - h[8 * b + i]) / B;
+    fprintf(stderr, "[fused dbg] B=%d T=%d smem=%zu cycles: A(emit)=%.0f B(chains)=%.0f C1(q,out,logZ)=%.0f C2(tran stat)=%.0f C3(emit stats)=%.0f\n",
+            B, T, smem, ph[0], ph[1], ph[2], ph[3], ph[4]);
+  }
+  c->launches++;
+  c->last_B = B; c->last_T = T; c->last_fused = 1;
+  return SVIHMM_OK;
+}
+
 static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                       const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
                       unsigned flags, cudaStream_t st) {
   const int K = c->K, D = c->D;
   const bool xi = flags & SVIHMM_EXACT_XI;
+  size_t fsmem = 0;
+  if (fused_eligible(c, T, flags, &fsmem))
+    return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st);
   int rc = ensure_ws(c, B, T, xi);
   if (rc) return rc;
   const int64_t R = (int64_t)B * T;
@@ -404,7 +483,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       B, T, K, D, c->DD, c->nfeat, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
       (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, c->Pt, xi ? 1 : 0, stats_out, c->slen);
   LAUNCHED(c);
-  c->last_B = B; c->last_T = T;
+  c->last_B = B; c->last_T = T; c->last_fused = 0;
   return SVIHMM_OK;
 }
 
@@ -511,12 +590,18 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
     if (has_mask) CU(cudaMemcpyAsync(c->stage_mask, c->pin_mask, rows, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->stage_starts, ds, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
   }
+  if (var_x_host && rows * c->K > c->hostq_cap) {
+    if (c->hostq_ws) CU(cudaFree(c->hostq_ws));
+    c->hostq_ws = nullptr; c->hostq_cap = 0;
+    CU(dalloc(&c->hostq_ws, rows * c->K));
+    c->hostq_cap = rows * c->K;
+  }
   rc = estep_impl(c, c->stage_obs, c->h_dtype, has_mask ? c->stage_mask : nullptr, c->stage_starts, B, T,
-                  nullptr, c->stage_stats, flags, st);
+                  var_x_host ? c->hostq_ws : nullptr, c->stage_stats, flags, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(stats_host, c->stage_stats, sizeof(double) * c->slen, cudaMemcpyDeviceToHost, st));
   if (var_x_host)
-    CU(cudaMemcpyAsync(var_x_host, c->q_ws, sizeof(float) * rows * c->K, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(var_x_host, c->hostq_ws, sizeof(float) * rows * c->K, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return SVIHMM_OK;
 }
@@ -562,6 +647,8 @@ extern "C" int svihmm_get_locals(svihmm_ctx* c, double* lliks, float* alpha, dou
                                  double* logz, int loc, void* stream) {
   if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
   if (c->last_B == 0) return fail(SVIHMM_ESTATE, "no E-step has run yet");
+  if (c->last_fused && (lliks || alpha || mx || cs))
+    return fail(SVIHMM_ESTATE, "lliks/alpha/mx/cs need the last E-step to run with SVIHMM_KEEP_LOCALS");
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const cudaMemcpyKind kd = loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;

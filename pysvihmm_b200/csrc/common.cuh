@@ -36,8 +36,10 @@ struct svihmm_ctx {
   // workspaces
   size_t cap_rows, cap_B, cap_part;
   double *ll_ws, *mx_ws, *seq_ws;
-  float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws;
-  int last_B, last_T;
+  float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
+  size_t hostq_cap;
+  int last_B, last_T, last_fused;
+  int max_smem_optin, fused_attr_set;
   int64_t launches;
   // optional per-phase event timing
   int profiling;

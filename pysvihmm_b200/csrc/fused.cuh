@@ -1,0 +1,525 @@
+// Fused E-step for K <= 32: ONE kernel launch per minibatch, one CTA per window, everything
+// between the coalesced read of the window and the write of the posterior marginals stays in
+// shared memory.  Replaces, per window, the whole body of the reference's per-meta-observation
+// loop hmmsgd_metaobs.py:405-436:
+//   phase A  expected log-likelihoods (float64; pybasicbayes/distributions.py:351-366 via the
+//            constants of prep.cuh) + np.nan_to_num semantics (hmmsgd_metaobs.py:508-509),
+//            b[t][k] = exp(ll - max_k ll) (float32), row maxima (float64); one thread per row,
+//            so the row maximum needs no cross-lane traffic
+//   phase B  forward (hmmsgd_metaobs.py:775-803) and backward (:828-855) recursions, run
+//            CONCURRENTLY by the two lane groups of one warp (the two chains are independent).
+//            Only the matvec is on the dependent chain: the K-vector is exchanged through a
+//            double-buffered shared-memory slot (STS + 128-bit broadcast loads: ~30 cycles measured,
+//            against ~100 for 16 shuffles), the dot product runs on packed fma.rn.f32x2, and
+//            instead of a per-step normaliser the messages are rescaled by exact powers of two
+//            chosen from the group-max exponent seen two steps earlier (deadbeat controller), so
+//            no reduction sits on the critical path and the rescaling adds no rounding error
+//   phase C  marginals q[t] = norm(alpha[t]*beta[t]) (:516-519), log normalisers (:257-271),
+//            transition statistic sum_t outer(q[t-1],q[t]) with the reference's wrap-around
+//            (:876-878) and the weighted NIW statistics (util.py:73-83) as register-blocked 4x4
+//            tiles split over row chunks, accumulated over the minibatch (:430-433) with float64
+//            atomics into the packed statistics buffer.
+//
+// Shared memory: [ b | beta | alpha->q ] each T*KS floats (KS = K rounded up to 4) + per-row
+// scalars.  The window's observations are staged (float64 for phase A, float32 for phase C) into
+// regions that are dead at that point, so HBM traffic is the algorithmic minimum: T*D reads and
+// T*K writes per window.
+#pragma once
+#include "common.cuh"
+
+#define FUSED_NT 256
+#define FUSED_XTB 157          // target biased exponent of the group max: 2^30
+#define FUSED_RED_BYTES (FUSED_NT * 16 * 4)
+
+struct FusedArgs {
+  int B, T, K, D, DD, diag, wrap, add_prior, mask_ll;
+  int tri;                   // D(D+1)/2 (full) or D (diag): emission params per state besides gk
+  const void* obs; int dtype; const uint8_t* mask; const int64_t* starts;
+  const float* Pt; const float* pi0;
+  const double* Rs; const double* gk; const double* ck; const double* prior_tran;
+  float* var_x_out; double* stats_out; double* seq;
+  size_t o_n, o_sx, o_sxx, o_q0, o_tail;
+  long long* dbg;            // optional [B][8] clock64 stamps at phase boundaries (debug)
+};
+
+struct FusedSmem {           // byte offsets into the dynamic shared memory
+  int KS, DS, XP;
+  size_t b, c, a, xs, xf, red, mx, late, flags, bc, total;
+};
+
+__host__ __device__ inline size_t fused_al16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+__host__ __device__ inline FusedSmem fused_smem_layout(int T, int K, int D, int tri, int diag) {
+  FusedSmem s;
+  s.KS = (K + 3) & ~3;
+  s.DS = (D + 1 + 3) & ~3;                          // float columns of phase C: x_0..x_{D-1}, w, pad
+  s.XP = D | 1;                                     // double columns of phase A (odd: conflict-free)
+  const size_t R = (size_t)T * s.KS * sizeof(float);
+  const size_t xf_bytes = fused_al16((size_t)T * s.DS * sizeof(float));
+  const size_t scratchC = xf_bytes + FUSED_RED_BYTES;
+  s.b = 0; s.c = R;
+  s.a = 2 * R > scratchC ? 2 * R : scratchC;
+  s.xs = s.c;                                       // phase A staging over [beta | alpha]
+  s.xf = 0; s.red = xf_bytes;                       // phase C scratch over [b | beta]
+  size_t end = s.a + R;
+  const size_t endA = s.xs + (size_t)T * s.XP * 8;
+  if (endA > end) end = endA;
+  s.mx = fused_al16(end);                           // T doubles: row maxima of ll
+  s.late = fused_al16(s.mx + (size_t)T * 8);        // phase A: emission constants; B/C: lt (T doubles) + E (T ints)
+  const size_t params = diag ? ((size_t)K * D * 16 + (size_t)K * 8) : ((size_t)K * (tri + D + 1) * 8);
+  const size_t late = (size_t)T * 12;
+  s.flags = s.late + fused_al16(params > late ? params : late);
+  s.bc = fused_al16(s.flags + (size_t)T);           // 2 parities x (fwd, bwd, dump) x 32 floats
+  s.total = s.bc + 2 * 3 * 32 * sizeof(float);
+  return s;
+}
+
+__device__ __forceinline__ void ffma2(unsigned long long& acc, const unsigned long long a, const unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(const float x, const float y) {
+  return (unsigned long long)__float_as_uint(x) | ((unsigned long long)__float_as_uint(y) << 32);
+}
+__device__ __forceinline__ float lo32(const unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(const unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// One step of either chain (see the header comment).  v: this lane's component of the recursion
+// vector (alpha~ for the forward group, b*beta~ for the backward group).  With x_s the biased
+// exponent of max_j v_s[j] and d_s the exponent shift applied at step s,
+//     d_s = (x_{s-2} - XTB) - d_{s-1}      =>      x_s = XTB + g_{s-1} + g_s
+// (g = log2 of the per-step growth, bounded): the shift already in flight is subtracted, so the
+// two-step-old measurement keeps the exponent bounded while the max is computed off the chain.
+template <int KP>
+__device__ __forceinline__ void chain_step(float& v, const unsigned long long (&col2)[KP / 2], const float bt,
+                                           const bool fwd, const bool st, float* bcw, const float* bcr,
+                                           float* op, int* ep, const bool lead, int& xa, int& da, int& E) {
+  constexpr int NV = KP / 4;
+  *bcw = v;
+  __syncwarp();
+  float4 x[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) x[q] = reinterpret_cast<const float4*>(bcr)[q];
+  int d = xa - FUSED_XTB - da;
+  d = max(-60, min(60, d));
+  const float r = __uint_as_float((unsigned)(127 - d) << 23);
+  const float br = bt * r;
+  unsigned long long acc0 = 0ull, acc1 = 0ull;
+  unsigned mx = 0u;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    ffma2(acc0, pack2(x[q].x, x[q].y), col2[2 * q]);
+    ffma2(acc1, pack2(x[q].z, x[q].w), col2[2 * q + 1]);
+    mx = max(mx, __vimax3_u32(__float_as_uint(x[q].x), __float_as_uint(x[q].y), __float_as_uint(x[q].z)));
+    mx = max(mx, __float_as_uint(x[q].w));
+  }
+  const float m = (lo32(acc0) + hi32(acc0)) + (lo32(acc1) + hi32(acc1));
+  v = m * br;
+  E += d;
+  if (st) *op = fwd ? v : m * r;
+  if (lead) *ep = E;
+  xa = (int)(mx >> 23); da = d;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int T = a.T, K = a.K, D = a.D;
+  const FusedSmem L = fused_smem_layout(T, K, D, a.tri, a.diag);
+  const int KS = L.KS, DS = L.DS, XP = L.XP;
+  float* bS = reinterpret_cast<float*>(smem + L.b);
+  float* cS = reinterpret_cast<float*>(smem + L.c);
+  float* aS = reinterpret_cast<float*>(smem + L.a);
+  double* xs = reinterpret_cast<double*>(smem + L.xs);
+  float* xf = reinterpret_cast<float*>(smem + L.xf);
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  double* mxS = reinterpret_cast<double*>(smem + L.mx);
+  double* parS = reinterpret_cast<double*>(smem + L.late);           // phase A only
+  double* ltS = reinterpret_cast<double*>(smem + L.late);            // phase B/C
+  int* ES = reinterpret_cast<int*>(smem + L.late + (size_t)T * 8);
+  unsigned char* fl = smem + L.flags;
+  float* bcS = reinterpret_cast<float*>(smem + L.bc);
+  const int tid = threadIdx.x, w = blockIdx.x;
+  const int64_t s0 = a.starts[w];
+
+#define FUSED_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)w * 8 + (i)] = clock64(); } while (0)
+  FUSED_STAMP(0);
+  // ---------------------------------------------------------------- phase A: emissions
+  {
+    // stage the window as float64 rows of XP (odd) doubles: coalesced 128-bit global loads
+    const int64_t e0 = s0 * D;
+    const int n = T * D;
+    if (a.dtype == SVIHMM_F32) {
+      const float* src = (const float*)a.obs + e0;
+      if ((((uintptr_t)src) & 15) == 0 && (D & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int i = tid; i < n / 4; i += FUSED_NT) {
+          const float4 q = __ldg(s4 + i);
+          const int r = (4 * i) / D, d = 4 * i - r * D;
+          double* dst = xs + (size_t)r * XP + d;
+          dst[0] = q.x; dst[1] = q.y; dst[2] = q.z; dst[3] = q.w;
+        }
+      } else {
+        for (int i = tid; i < n; i += FUSED_NT) { const int r = i / D; xs[(size_t)r * XP + (i - r * D)] = __ldg(src + i); }
+      }
+    } else {
+      const double* src = (const double*)a.obs + e0;
+      if ((((uintptr_t)src) & 15) == 0 && (D & 1) == 0) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        for (int i = tid; i < n / 2; i += FUSED_NT) {
+          const double2 q = __ldg(s2 + i);
+          const int r = (2 * i) / D, d = 2 * i - r * D;
+          double* dst = xs + (size_t)r * XP + d;
+          dst[0] = q.x; dst[1] = q.y;
+        }
+      } else {
+        for (int i = tid; i < n; i += FUSED_NT) { const int r = i / D; xs[(size_t)r * XP + (i - r * D)] = __ldg(src + i); }
+      }
+    }
+    // emission constants.  diagonal: (c2, c1) = (Rs, -2 Rs mu) per (k,d) and ck' = ck - sum Rs mu^2, so
+    // ll = ck' - sum_d (c2 x^2 + c1 x) (float64: the expansion costs ~1e-12 absolute, two DFMA per term)
+    if (a.diag) {
+      for (int i = tid; i < K * D; i += FUSED_NT) {
+        const double rs = a.Rs[i], mu = a.gk[i];
+        parS[2 * i] = rs; parS[2 * i + 1] = -2.0 * rs * mu;
+      }
+      for (int kk = tid; kk < K; kk += FUSED_NT) {
+        double c = a.ck[kk];
+        for (int d = 0; d < D; ++d) { const double mu = a.gk[kk * D + d]; c -= a.Rs[kk * D + d] * mu * mu; }
+        parS[2 * K * D + kk] = c;
+      }
+    } else {
+      const int np = a.tri + D + 1;
+      for (int i = tid; i < K * np; i += FUSED_NT) {
+        const int kk = i / np, p = i - kk * np;
+        parS[i] = p < a.tri ? a.Rs[(size_t)kk * a.tri + p] : (p < a.tri + D ? a.gk[(size_t)kk * D + (p - a.tri)] : a.ck[kk]);
+      }
+    }
+    __syncthreads();
+    constexpr int CH = KP >= 32 ? 4 : 8;              // observation dims held in registers at a time
+    for (int row = tid; row < T; row += FUSED_NT) {
+      const double* x = xs + (size_t)row * XP;
+      bool bad = false;
+      for (int d = 0; d < D; ++d) bad |= isnan(x[d]);
+      const bool mk = a.mask && a.mask[s0 + row];
+      const bool noev = bad || (a.mask_ll && mk);
+      fl[row] = (unsigned char)(((bad || mk) ? 1 : 0) | (noev ? 2 : 0));
+      double ll[KP];
+      if (a.diag) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) ll[k] = k < K ? parS[2 * K * D + k] : -INFINITY;
+        for (int d0 = 0; d0 < D; d0 += CH) {
+          double xd[CH], xx[CH];
+#pragma unroll
+          for (int dd = 0; dd < CH; ++dd) { xd[dd] = d0 + dd < D ? x[d0 + dd] : 0.0; xx[dd] = xd[dd] * xd[dd]; }
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            if (k < K) {
+              const double2* pp = reinterpret_cast<const double2*>(parS) + (size_t)k * D + d0;
+              double acc = ll[k];
+#pragma unroll
+              for (int dd = 0; dd < CH; ++dd) {
+                if (d0 + dd < D) { const double2 c = pp[dd]; acc = fma(-c.x, xx[dd], acc); acc = fma(-c.y, xd[dd], acc); }
+              }
+              ll[k] = acc;
+            }
+          }
+        }
+      } else {
+        const int np = a.tri + D + 1;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          ll[k] = -INFINITY;
+          if (k < K) {
+            const double* pr = parS + (size_t)k * np;
+            double acc = 0.0;
+            int o = 0;
+            for (int i = 0; i < D; ++i) {
+              double s = -pr[a.tri + i];
+              for (int j = 0; j <= i; ++j) s = fma(pr[o + j], x[j], s);
+              o += i + 1;
+              acc = fma(s, s, acc);
+            }
+            ll[k] = pr[a.tri + D] - acc;
+          }
+        }
+      }
+      double m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { if (k < K) { if (noev) ll[k] = 0.0; m = fmax(m, ll[k]); } }
+      mxS[row] = m;
+      float* bp = bS + (size_t)row * KS;
+#pragma unroll
+      for (int k4 = 0; k4 < KP; k4 += 4) {
+        if (k4 < KS) {
+          float4 o;
+          o.x = k4 < K ? __expf((float)(ll[k4] - m)) : 0.f;
+          o.y = k4 + 1 < K ? __expf((float)(ll[k4 + 1] - m)) : 0.f;
+          o.z = k4 + 2 < K ? __expf((float)(ll[k4 + 2] - m)) : 0.f;
+          o.w = k4 + 3 < K ? __expf((float)(ll[k4 + 3] - m)) : 0.f;
+          *reinterpret_cast<float4*>(bp + k4) = o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  FUSED_STAMP(1);
+
+  // ---------------------------------------------------------------- phase B: the two chains
+  {
+    constexpr int GPW = 32 / KP;                        // lane groups per warp
+    const int lane = tid & 31, wp = tid >> 5;
+    const int j = lane % KP, grp = wp * GPW + lane / KP;
+    if (wp < (KP == 32 ? 2 : 1)) {                      // whole warps only (__syncwarp inside)
+      const bool live = grp < 2;                        // lane groups >= 2 of warp 0 (KP < 16) idle along
+      const bool fwd = grp == 0;
+      const bool act = live && j < K;
+      const bool st = live && j < KS;                   // columns K..KS-1 of the tables are kept at zero
+      const bool lead = fwd && j == 0;
+      unsigned long long col2[KP / 2];
+#pragma unroll
+      for (int i = 0; i < KP; i += 2) {
+        const float p0 = (act && i < K) ? (fwd ? __ldg(a.Pt + i * K + j) : __ldg(a.Pt + j * K + i)) : 0.f;
+        const float p1 = (act && i + 1 < K) ? (fwd ? __ldg(a.Pt + (i + 1) * K + j) : __ldg(a.Pt + j * K + i + 1)) : 0.f;
+        col2[i / 2] = pack2(p0, p1);
+      }
+      // broadcast slots: [parity][fwd, bwd, dump][32]; idle groups write the dump slot
+      const int wslot = live ? grp : 2, rslot = live ? grp : 1;
+      float* w0 = bcS + wslot * 32 + (live ? j : lane);
+      float* w1 = w0 + 96;
+      const float* r0 = bcS + rslot * 32;
+      const float* r1 = r0 + 96;
+      const int jj = st ? j : 0;
+      const int dt = fwd ? KS : -KS;
+      const int tb = fwd ? 0 : T - 1;
+      const float* bp = bS + (size_t)tb * KS + jj;
+      float* op = (fwd ? aS : cS) + (size_t)tb * KS + jj;
+      int* ep = ES + tb;
+      const int de = fwd ? 1 : 0;                       // only the forward group's exponents are kept
+      float v;
+      if (fwd) { v = act ? __ldg(a.pi0 + j) * bp[0] : 0.f; if (st) *op = v; }
+      else { v = act ? bp[0] : 0.f; if (st) *op = act ? 1.f : 0.f; }
+      if (lead) *ep = 0;
+      int xa = FUSED_XTB, da = 0, E = 0;
+      int s = 1;
+      float bn = (T > 1 && st) ? bp[dt] : 0.f;
+      for (; s + 3 < T; s += 4) {                       // s is odd here: parities 1,0,1,0
+        const float b0 = bn;
+        const float b1 = st ? bp[2 * dt] : 0.f, b2 = st ? bp[3 * dt] : 0.f, b3 = st ? bp[4 * dt] : 0.f;
+        bn = (s + 4 < T && st) ? bp[5 * dt] : 0.f;
+        chain_step<KP>(v, col2, b0, fwd, st, w1, r1, op + dt, ep + de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b1, fwd, st, w0, r0, op + 2 * dt, ep + 2 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b2, fwd, st, w1, r1, op + 3 * dt, ep + 3 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b3, fwd, st, w0, r0, op + 4 * dt, ep + 4 * de, lead, xa, da, E);
+        bp += 4 * dt; op += 4 * dt; ep += 4 * de;
+      }
+      for (; s < T; ++s) {
+        const float b0 = bn;
+        bn = (s + 1 < T && st) ? bp[2 * dt] : 0.f;
+        if (s & 1) chain_step<KP>(v, col2, b0, fwd, st, w1, r1, op + dt, ep + de, lead, xa, da, E);
+        else chain_step<KP>(v, col2, b0, fwd, st, w0, r0, op + dt, ep + de, lead, xa, da, E);
+        bp += dt; op += dt; ep += de;
+      }
+    }
+  }
+  __syncthreads();
+  FUSED_STAMP(2);
+
+  // ---------------------------------------------------------------- phase C1: marginals (thread per row)
+  for (int row = tid; row < T; row += FUSED_NT) {
+    float* ap = aS + (size_t)row * KS;
+    const float* cp = cS + (size_t)row * KS;
+    float p[KP];
+    float sa = 0.f, sp = 0.f;
+#pragma unroll
+    for (int k4 = 0; k4 < KP; k4 += 4) {
+      if (k4 < KS) {
+        const float4 al = *reinterpret_cast<const float4*>(ap + k4);
+        const float4 be = *reinterpret_cast<const float4*>(cp + k4);
+        p[k4] = al.x * be.x; p[k4 + 1] = al.y * be.y; p[k4 + 2] = al.z * be.z; p[k4 + 3] = al.w * be.w;
+        sa += (al.x + al.y) + (al.z + al.w);
+        sp += (p[k4] + p[k4 + 1]) + (p[k4 + 2] + p[k4 + 3]);
+      }
+    }
+    const float inv = 1.f / sp;
+#pragma unroll
+    for (int k4 = 0; k4 < KP; k4 += 4) {
+      if (k4 < KS) {
+        float4 o;
+        o.x = p[k4] * inv; o.y = p[k4 + 1] * inv; o.z = p[k4 + 2] * inv; o.w = p[k4 + 3] * inv;
+        *reinterpret_cast<float4*>(ap + k4) = o;
+      }
+    }
+    ltS[row] = log((double)sa) + (double)ES[row] * M_LN2;
+  }
+  __syncthreads();
+  // posterior marginals out: coalesced copy of the q table
+  if (a.var_x_out) {
+    float* dst = a.var_x_out + (size_t)w * T * K;
+    if (KS == K && (((uintptr_t)dst) & 15) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(aS);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (int i = tid; i < T * K / 4; i += FUSED_NT) d4[i] = s4[i];
+    } else {
+      for (int i = tid; i < T * K; i += FUSED_NT) { const int t = i / K; dst[i] = aS[(size_t)t * KS + (i - t * K)]; }
+    }
+  }
+  // log normalisers: logZ = lt[T-1] + sum_t mx[t];  Q4 = sum_t (lt[t] + sum_{s<=t} mx[s])
+  if (tid < 32) {
+    double smx = 0.0, q4 = 0.0;
+    for (int t = tid; t < T; t += 32) { smx += mxS[t]; q4 += ltS[t] + (double)(T - t) * mxS[t]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      smx += __shfl_xor_sync(0xffffffffu, smx, o);
+      q4 += __shfl_xor_sync(0xffffffffu, q4, o);
+    }
+    if (tid == 0) {
+      const double lz = ltS[T - 1] + smx;
+      a.seq[2 * (size_t)w] = lz; a.seq[2 * (size_t)w + 1] = q4;
+      atomicAdd(a.stats_out + a.o_tail, lz);
+      atomicAdd(a.stats_out + a.o_tail + 1, q4);
+      atomicAdd(a.stats_out + a.o_tail + 2, 1.0);
+    }
+  }
+  if (tid >= 32 && tid < 32 + K) atomicAdd(a.stats_out + a.o_q0 + (tid - 32), (double)aS[tid - 32]);
+  FUSED_STAMP(3);
+
+  // ---------------------------------------------------------------- phase C2: transition statistic
+  // A[i][j] = sum_t q[t-1][i] q[t][j]: 4x4 register tiles, T split over row chunks, float32 partials
+  // (<= T/chunks terms each) reduced across chunks in float64.
+  const int nbi = KS / 4;
+  {
+    const int nb = nbi * nbi;
+    int chunks = FUSED_NT / nb;
+    if (chunks > (T + 7) / 8) chunks = (T + 7) / 8;
+    if (chunks < 1) chunks = 1;
+    const int len = (T + chunks - 1) / chunks;
+    __syncthreads();                                   // b/beta (under the scratch) are dead from here on
+    if (tid < nb * chunks) {
+      const int c = tid / nb, blk = tid - c * nb;
+      const int i0 = (blk / nbi) * 4, j0 = (blk % nbi) * 4;
+      float acc[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+      const int tb = c * len, te = min(T, tb + len);
+      for (int t = tb; t < te; ++t) {
+        int tp = t - 1;
+        if (t == 0) { if (!a.wrap) continue; tp = T - 1; }
+        const float4 pv = *reinterpret_cast<const float4*>(aS + (size_t)tp * KS + i0);
+        const float4 cv = *reinterpret_cast<const float4*>(aS + (size_t)t * KS + j0);
+        const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v2 = 0; v2 < 4; ++v2) acc[u * 4 + v2] = fmaf(pa[u], ca[v2], acc[u * 4 + v2]);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; u += 4)
+        *reinterpret_cast<float4*>(red + (size_t)tid * 16 + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * 16; e += FUSED_NT) {
+      const int blk = e / 16, u = e - blk * 16;
+      const int i = (blk / nbi) * 4 + u / 4, jq = (blk % nbi) * 4 + (u & 3);
+      if (i < K && jq < K) {
+        double tot = 0.0;
+        for (int c = 0; c < chunks; ++c) tot += (double)red[((size_t)c * nb + blk) * 16 + u];
+        if (a.add_prior) tot += a.prior_tran[i * K + jq] - 1.0;
+        atomicAdd(a.stats_out + i * K + jq, tot);
+      }
+    }
+  }
+  FUSED_STAMP(4);
+
+  // ---------------------------------------------------------------- phase C3: emission statistics
+  // columns of the float32 window tile: [x_0..x_{D-1} (zero on dropped rows) | w | 0-pad]
+  //   pass 0:  S1[k][c]  = sum_t q[t][k] * X[t][c]            -> sx (c < D), n (c = D)
+  //   pass 1:  diagonal: S2[k][d] = sum_t q[t][k] X[t][d]^2   -> sxx
+  //            full:     S2[k][d][e] = sum_t q[t][k] X[t][d] X[t][e], one d per pass
+  {
+    {
+      const int64_t e0 = s0 * D;
+      for (int i = tid; i < T * DS; i += FUSED_NT) {     // xf overlaps the dead b table only
+        const int r = i / DS, c = i - r * DS;
+        const bool drop = fl[r] & 1;
+        float v = 0.f;
+        if (c < D) v = drop ? 0.f : (float)ld_obs(a.obs, a.dtype, e0 + (int64_t)r * D + c);
+        else if (c == D) v = drop ? 0.f : 1.f;
+        xf[i] = v;
+      }
+    }
+    const int ncb = DS / 4;
+    const int nb = nbi * ncb;                           // 4x4 tiles of the (KS x DS) output
+    int chunks = FUSED_NT / nb;
+    if (chunks > (T + 7) / 8) chunks = (T + 7) / 8;
+    if (chunks < 1) chunks = 1;
+    const int len = (T + chunks - 1) / chunks;
+    const bool via_red = nb * chunks <= FUSED_NT;       // else (large K*D) partials go straight to atomics
+    const int npass = a.diag ? 2 : 1 + D;
+    for (int pass = 0; pass < npass; ++pass) {
+      __syncthreads();
+      const int dsel = pass - 1;                        // full covariance: the fixed left factor x_d
+      for (int it0 = 0; it0 < nb * chunks; it0 += FUSED_NT) {
+        const int item = it0 + tid;
+        if (item < nb * chunks) {
+          const int c = item / nb, blk = item - c * nb;
+          const int k0 = (blk / ncb) * 4, c0 = (blk % ncb) * 4;
+          float acc[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+          const int tb = c * len, te = min(T, tb + len);
+          for (int t = tb; t < te; ++t) {
+            const float4 qv = *reinterpret_cast<const float4*>(aS + (size_t)t * KS + k0);
+            float4 xv = *reinterpret_cast<const float4*>(xf + (size_t)t * DS + c0);
+            if (pass > 0) {
+              if (a.diag) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
+              else { const float xd = xf[(size_t)t * DS + dsel]; xv.x *= xd; xv.y *= xd; xv.z *= xd; xv.w *= xd; }
+            }
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, xa4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v2 = 0; v2 < 4; ++v2) acc[u * 4 + v2] = fmaf(qa[u], xa4[v2], acc[u * 4 + v2]);
+          }
+          if (via_red) {
+#pragma unroll
+            for (int u = 0; u < 16; u += 4)
+              *reinterpret_cast<float4*>(red + (size_t)item * 16 + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int kq = k0 + u / 4, cc = c0 + (u & 3);
+              if (kq < K) {
+                if (pass == 0) {
+                  if (cc < D) atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + cc, (double)acc[u]);
+                  else if (cc == D) atomicAdd(a.stats_out + a.o_n + kq, (double)acc[u]);
+                } else if (cc < D) {
+                  const size_t o = a.diag ? (size_t)kq * D + cc : ((size_t)kq * D + dsel) * D + cc;
+                  atomicAdd(a.stats_out + a.o_sxx + o, (double)acc[u]);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (via_red) {
+        __syncthreads();
+        for (int e = tid; e < nb * 16; e += FUSED_NT) {
+          const int blk = e / 16, u = e - blk * 16;
+          const int kq = (blk / ncb) * 4 + u / 4, cc = (blk % ncb) * 4 + (u & 3);
+          if (kq < K && cc <= D) {
+            double tot = 0.0;
+            for (int c = 0; c < chunks; ++c) tot += (double)red[((size_t)c * nb + blk) * 16 + u];
+            if (pass == 0) {
+              if (cc < D) atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + cc, tot);
+              else atomicAdd(a.stats_out + a.o_n + kq, tot);
+            } else if (cc < D) {
+              const size_t o = a.diag ? (size_t)kq * D + cc : ((size_t)kq * D + dsel) * D + cc;
+              atomicAdd(a.stats_out + a.o_sxx + o, tot);
+            }
+          }
+        }
+      }
+    }
+  }
+  FUSED_STAMP(5);
+}

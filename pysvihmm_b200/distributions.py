@@ -58,7 +58,7 @@ class Gaussian(object):
         try:
             eng.set_series(x)
             eng.set_globals(np.ones((1, 1)), eng.pack_emit(*self._mf_arrays()))
-            eng.estep([0], x.shape[0], want_var_x=False)
+            eng.estep([0], x.shape[0], want_var_x=False, keep_locals=True)
             return eng.get_locals(1, x.shape[0])["lliks"][0, :, 0]
         finally:
             eng.close()

@@ -142,9 +142,12 @@ class EStepEngine(object):
     def new_stats(self):
         return torch.empty(self.slen, dtype=torch.float64, device=self.device)
 
-    def estep(self, starts, T, flags=0, var_x=None, stats=None, want_var_x=True):
+    def estep(self, starts, T, flags=0, var_x=None, stats=None, want_var_x=True, keep_locals=False):
         """E-step over windows obs[starts[b]:starts[b]+T] of the resident series.
-        Returns (var_x (B,T,K) float32 CUDA tensor or None, stats float64 CUDA tensor)."""
+        Returns (var_x (B,T,K) float32 CUDA tensor or None, stats float64 CUDA tensor).
+        keep_locals: keep the lliks/alpha/scale tables for get_locals (unfused kernels)."""
+        if keep_locals:
+            flags = int(flags) | L.KEEP_LOCALS
         if not isinstance(starts, torch.Tensor):
             starts = torch.as_tensor(np.asarray(starts, dtype=np.int64))
         starts = starts.to(device=self.device, dtype=torch.int64).contiguous()
@@ -180,9 +183,16 @@ class EStepEngine(object):
         """hmmbatchcd.py:172-189 on the device-resident globals."""
         L.check(self.lib.svihmm_batch_update(self._h, _ptr(stats), self._stream()))
 
-    def get_locals(self, B, T):
+    def get_locals(self, B, T, tables=True):
+        """Per-window [logZ, Q4 bound]; with tables=True also lliks/alpha/mx/cs (needs the last
+        estep to have run with keep_locals=True)."""
+        lz = np.empty((B, 2))
+        if not tables:
+            L.check(self.lib.svihmm_get_locals(self._h, None, None, None, None, _ptr(lz), L.LOC_HOST,
+                                               self._stream()))
+            return dict(logZ=lz[:, 0], lb_q4=lz[:, 1])
         ll = np.empty((B, T, self.K)); al = np.empty((B, T, self.K), dtype=np.float32)
-        mx = np.empty((B, T)); cs = np.empty((B, T), dtype=np.float32); lz = np.empty((B, 2))
+        mx = np.empty((B, T)); cs = np.empty((B, T), dtype=np.float32)
         L.check(self.lib.svihmm_get_locals(self._h, _ptr(ll), _ptr(al), _ptr(mx), _ptr(cs), _ptr(lz),
                                            L.LOC_HOST, self._stream()))
         return dict(lliks=ll, alpha=al, mx=mx, cs=cs, logZ=lz[:, 0], lb_q4=lz[:, 1])

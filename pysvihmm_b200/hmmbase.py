@@ -143,7 +143,7 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
         if obs is not None or mask is not None:
             self.set_data(self.obs if obs is None else obs, self.mask if mask is None else mask)
         eng = self._ensure_engine()
-        vx, stats = eng.estep([0], self.T, flags=self._local_flags())
+        vx, stats = eng.estep([0], self.T, flags=self._local_flags(), keep_locals=True)
         self._stats = stats
         self._materialise_locals(eng, vx, 1, self.T)
 

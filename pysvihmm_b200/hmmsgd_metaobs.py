@@ -199,7 +199,7 @@ class VBHMM(VariationalHMMBase):
             metaobs = MetaObs(0, self.T - 1)
         eng = self._ensure_engine()
         T = metaobs.i2 - metaobs.i1 + 1
-        vx, stats = eng.estep([metaobs.i1], T, flags=self._flags())
+        vx, stats = eng.estep([metaobs.i1], T, flags=self._flags(), keep_locals=True)
         self._stats = stats
         self._pull_globals()
         self.var_init = eng.get_globals()[1]        # the stationary vector that was used (:418)

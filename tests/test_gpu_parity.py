@@ -53,9 +53,13 @@ def oracle_stats(O, r, obs, mask, starts, T, wrap):
     return A, n, sx, sxx
 
 
+PATHS = ["fused", "unfused"]     # single-kernel path (fused.cuh) / per-phase kernels (KEEP_LOCALS)
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("obs_dtype", ["f64", "f32"])
 @pytest.mark.parametrize("name", SVI_CASES)
-def test_svi_step_matches_reference_golden(name, obs_dtype):
+def test_svi_step_matches_reference_golden(name, obs_dtype, path):
     """One engine call per global step reproduces the reference's per-window tables, summed
     statistics (quirks Q1/Q2/Q5) and natural-gradient update (hmmsgd_metaobs.py:405-439)."""
     from pysvihmm_b200 import _lib as L
@@ -73,21 +77,23 @@ def test_svi_step_matches_reference_golden(name, obs_dtype):
     f32 = obs_dtype == "f32"
     for it in range(int(g["maxit"])):
         starts = g["w_starts"][it]
-        vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+        unf = path == "unfused"
+        vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR, keep_locals=unf)
         q = vx.cpu().numpy()
         # float32 storage of the series perturbs ll by ~|x| * 6e-8 * |dll/dx|: not a kernel error
         if f32:
             assert np.max(np.abs(q - g["w_var_x"][it])) < 2e-4
         else:
             assert_q(q, g["w_var_x"][it])
-            loc = eng.get_locals(S, T)
-            np.testing.assert_allclose(loc["lliks"], g["w_ll"][it], rtol=1e-11, atol=1e-11)
+            loc = eng.get_locals(S, T, tables=unf)
             la = g["w_lalpha"][it]
             np.testing.assert_allclose(loc["logZ"], np.logaddexp.reduce(la[:, -1], axis=-1), rtol=2e-6)
             np.testing.assert_allclose(loc["lb_q4"], g["w_lb"][it], rtol=2e-6)
-            # softmax(lalpha[t]) == normalised forward message
-            sm = np.exp(la - np.logaddexp.reduce(la, axis=-1)[..., None])
-            assert np.max(np.abs(loc["alpha"] - sm)) < 2e-6
+            if unf:
+                np.testing.assert_allclose(loc["lliks"], g["w_ll"][it], rtol=1e-11, atol=1e-11)
+                # softmax(lalpha[t]) == normalised forward message
+                sm = np.exp(la - np.logaddexp.reduce(la, axis=-1)[..., None])
+                assert np.max(np.abs(loc["alpha"] - sm)) < 2e-6
         s = eng.unpack_stats(stats)
         tol = 2e-4 if f32 else S_RTOL
         assert_block(s["A"], g["w_A_i"][it].sum(0), tol, "A_inter")
@@ -165,11 +171,17 @@ ORACLE_CASES = [
     (33, 4, 64, 5, "niw_full"),        # first wide size
     (64, 32, 257, 4, "niw_full"),      # BASELINE config 3 shape (reduced B, T)
     (100, 3, 50, 3, "niw_diag"),
+    (32, 4, 100, 3, "niw_diag"),       # fused path, one chain per warp (KP = 32)
+    (20, 3, 300, 4, "niw_full"),       # fused path, K not a power of two
+    (4, 12, 40, 3, "niw_diag"),        # fused path, D > K: observation staging in several tiles
+    (5, 9, 23, 2, "niw_full"),
+    (2, 2, 20000, 1, "niw_full"),      # too long for shared memory: per-phase kernels either way
 ]
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("K,D,T,B,kind", ORACLE_CASES)
-def test_estep_matches_oracle(K, D, T, B, kind):
+def test_estep_matches_oracle(K, D, T, B, kind, path):
     from oracle import svihmm_oracle as O
     from pysvihmm_b200 import _lib as L
     p = make_random_problem(seed=K * 1000 + T, K=K, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1)
@@ -179,15 +191,17 @@ def test_estep_matches_oracle(K, D, T, B, kind):
     eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
     eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
     for flags, wrap, mask_ll in [(L.WRAP | L.ADD_PRIOR, True, False), (L.MASK_LL, False, True)]:
-        vx, stats = eng.estep(starts, T, flags=flags)
+        unf = path == "unfused"
+        vx, stats = eng.estep(starts, T, flags=flags, keep_locals=unf)
         r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"],
                                  p["prior_tran"], p["prior_emit"], 0.5, max(T // 2, 1), wrap=wrap,
                                  mask_ll=mask_ll)
         q = vx.cpu().numpy()
         assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
         assert_q(q, r["var_x"])
-        loc = eng.get_locals(B, T)
-        np.testing.assert_allclose(loc["lliks"], r["ll"], rtol=1e-10, atol=1e-10)
+        loc = eng.get_locals(B, T, tables=unf)
+        if unf:
+            np.testing.assert_allclose(loc["lliks"], r["ll"], rtol=1e-10, atol=1e-10)
         np.testing.assert_allclose(loc["logZ"], r["logZ"], rtol=3e-6, atol=1e-4)
         s = eng.unpack_stats(stats)
         A = np.zeros((K, K)); n = np.zeros(K); sx = np.zeros((K, D))
@@ -292,7 +306,8 @@ def test_host_call_equals_device_call():
         vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
         vxh, sh = eng.estep_host(starts, T, flags=L.WRAP | L.ADD_PRIOR, want_var_x=True)
         assert np.array_equal(vx.cpu().numpy(), vxh)
-        assert np.array_equal(stats.cpu().numpy(), sh)
+        # statistics are accumulated over windows with float64 atomics: order-dependent last bits
+        np.testing.assert_allclose(stats.cpu().numpy(), sh, rtol=1e-12, atol=1e-12)
         eng.close()
 
 
