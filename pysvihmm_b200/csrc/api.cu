@@ -7,11 +7,10 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "prep.cuh"
 #include "emit.cuh"
 #include "fb.cuh"
 #include "stats.cuh"
-#include "update.cuh"
+#include "global.cuh"
 #include "fused.cuh"
 
 static thread_local std::string g_err;
@@ -105,7 +104,7 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, K * c->plen));
   CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, K * c->plen));
   CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
-  CU(dalloc(&c->lu, (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K));
+  CU(dalloc(&c->lu, (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, (size_t)K * D));
   CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, (size_t)K * D)); CU(dalloc(&c->ck, (size_t)K));
   CU(dalloc(&c->stage_stats, c->slen));
   *out = c;
@@ -124,7 +123,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   cudaSetDevice(c->device);
   free_streamed(c);
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
-                  c->pi0, c->lu, c->rowsum, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
+                  c->pi0, c->lu, c->rowsum, c->ckc, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -223,20 +222,25 @@ extern "C" int svihmm_set_prior(svihmm_ctx* c, const double* prior_tran, const d
   return SVIHMM_OK;
 }
 
-// globals -> derived constants (3 tiny kernels)
-static int run_prep(svihmm_ctx* c, cudaStream_t st) {
+// One launch: (optional) global update of the master parameters + all derived per-step constants.
+static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate, double bA, double bE,
+                      cudaStream_t st) {
   const int K = c->K, D = c->D;
-  k_prep_tran<<<1, 256, 0, st>>>(K, c->W, c->vinit + K, c->user_init, c->lu, c->rowsum, c->vinit,
-                                 c->Pt, c->PtT, c->pi0);
-  LAUNCHED(c);
-  if (c->kind == SVIHMM_EMIT_NIW_FULL) {
-    const size_t smem = 2 * (size_t)D * D * sizeof(double);
-    if (smem > 48 * 1024)
-      CU(cudaFuncSetAttribute(k_prep_emit_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_prep_emit_full<<<K, 128, smem, st>>>(D, c->plen, c->emit, c->Rs, c->gk, c->ck);
-  } else {
-    k_prep_emit_diag<<<(K + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->Rs, c->gk, c->ck);
-  }
+  GlobalArgs ga;
+  ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.mode = mode;
+  ga.user_init = c->user_init; ga.plen = c->plen;
+  ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
+  ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
+  ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
+  ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
+  ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
+  ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck;
+  const int nblk = ga.diag ? std::max(1, std::min(K, (K * D + 255) / 256)) : K;
+  size_t smem = 2 * (size_t)K * sizeof(double);
+  if (!ga.diag) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PhaseTimer pt(c, PH_UPDATE, st);
+  k_global_step<<<1 + nblk, 256, smem, st>>>(ga, nblk);
   LAUNCHED(c);
   return SVIHMM_OK;
 }
@@ -252,7 +256,7 @@ extern "C" int svihmm_set_globals(svihmm_ctx* c, const double* var_tran, const d
   c->user_init = var_init != nullptr;
   if (var_init && (rc = copy_in(c->vinit + c->K, var_init, sizeof(double) * c->K, loc, st))) return rc;
   c->have_globals = 1;
-  return run_prep(c, st);
+  return run_global(c, GM_PREP, nullptr, 0.0, 0.0, 0.0, st);
 }
 
 extern "C" int svihmm_get_globals(svihmm_ctx* c, double* var_tran, double* var_init, double* emit,
@@ -611,36 +615,15 @@ extern "C" int svihmm_global_update(svihmm_ctx* c, const double* stats, double l
   if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
   if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
   CU(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  const int K = c->K, D = c->D;
-  PhaseTimer pt(c, PH_UPDATE, st);
-  k_update_tran_svi<<<(K * K + 255) / 256, 256, 0, st>>>(K * K, c->W, stats, lrate, bA);
-  LAUNCHED(c);
-  if (c->kind == SVIHMM_EMIT_NIW_FULL)
-    k_update_emit_svi_full<<<K, 128, 3 * D * sizeof(double), st>>>(K, D, c->plen, c->emit, c->prior_emit, stats, lrate, bE);
-  else
-    k_update_emit_svi_diag<<<(K * D + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->prior_emit, stats, lrate, bE);
-  LAUNCHED(c);
-  return run_prep(c, st);
+  return run_global(c, GM_SVI, stats, lrate, bA, bE, (cudaStream_t)stream);
 }
 
 extern "C" int svihmm_batch_update(svihmm_ctx* c, const double* stats, void* stream) {
   if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
   if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
   CU(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  const int K = c->K, D = c->D;
-  PhaseTimer pt(c, PH_UPDATE, st);
-  k_update_tran_batch<<<(K * K + 255) / 256, 256, 0, st>>>(K, c->W, c->vinit + K, c->prior_tran,
-                                                          c->prior_init, stats, D, c->DD);
-  LAUNCHED(c);
   c->user_init = 1;    // hmmbatchcd.py:179: var_init becomes an explicit Dirichlet parameter
-  if (c->kind == SVIHMM_EMIT_NIW_FULL)
-    k_update_emit_batch_full<<<K, 128, D * sizeof(double), st>>>(K, D, c->plen, c->emit, c->prior_emit, stats);
-  else
-    k_update_emit_batch_diag<<<(K * D + 127) / 128, 128, 0, st>>>(K, D, c->emit, c->prior_emit, stats);
-  LAUNCHED(c);
-  return run_prep(c, st);
+  return run_global(c, GM_BATCH, stats, 0.0, 0.0, 0.0, (cudaStream_t)stream);
 }
 
 extern "C" int svihmm_get_locals(svihmm_ctx* c, double* lliks, float* alpha, double* mx, float* cs,

@@ -22,7 +22,7 @@ struct svihmm_ctx {
   int user_init, have_globals, have_prior;
   // derived per-global-step constants
   float *Pt, *PtT, *pi0;          // exp(E[log A]) row-major, its transpose, exp(E[log pi])
-  double *lu, *rowsum;            // scratch of the stationary solve
+  double *lu, *rowsum, *ckc;      // scratch of the stationary solve / per-(k,d) constants
   double *Rs, *gk, *ck;           // emission constants (see prep.cuh)
   // resident series
   const void* obs; const uint8_t* mask; int obs_dtype; int64_t T_full;

@@ -29,7 +29,7 @@
 
 #define FUSED_NT 256
 #define FUSED_XTB 157          // target biased exponent of the group max: 2^30
-#define FUSED_RED_BYTES (FUSED_NT * 16 * 4)
+#define FUSED_RED_BYTES (FUSED_NT * 32 * 4)
 
 struct FusedArgs {
   int B, T, K, D, DD, diag, wrap, add_prior, mask_ll;
@@ -69,8 +69,8 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int T, int K, int D, int 
   const size_t params = diag ? ((size_t)K * D * 16 + (size_t)K * 8) : ((size_t)K * (tri + D + 1) * 8);
   const size_t late = (size_t)T * 12;
   s.flags = s.late + fused_al16(params > late ? params : late);
-  s.bc = fused_al16(s.flags + (size_t)T);           // 2 parities x (fwd, bwd, dump) x 32 floats
-  s.total = s.bc + 2 * 3 * 32 * sizeof(float);
+  s.bc = fused_al16(s.flags + (size_t)T);           // 2 parities x 2 warps x 32 floats
+  s.total = s.bc + 2 * 2 * 32 * sizeof(float);
   return s;
 }
 
@@ -91,11 +91,10 @@ __device__ __forceinline__ float hi32(const unsigned long long v) { return __uin
 // two-step-old measurement keeps the exponent bounded while the max is computed off the chain.
 template <int KP>
 __device__ __forceinline__ void chain_step(float& v, const unsigned long long (&col2)[KP / 2], const float bt,
-                                           const bool fwd, const bool st, float* bcw, const float* bcr,
+                                           const bool fwd, const bool st, const float* bcr, float* bcw_next,
                                            float* op, int* ep, const bool lead, int& xa, int& da, int& E) {
   constexpr int NV = KP / 4;
-  *bcw = v;
-  __syncwarp();
+  __syncwarp();                                        // v of the previous step is in the slot
   float4 x[NV];
 #pragma unroll
   for (int q = 0; q < NV; ++q) x[q] = reinterpret_cast<const float4*>(bcr)[q];
@@ -114,6 +113,7 @@ __device__ __forceinline__ void chain_step(float& v, const unsigned long long (&
   }
   const float m = (lo32(acc0) + hi32(acc0)) + (lo32(acc1) + hi32(acc1));
   v = m * br;
+  *bcw_next = v;                                       // the only store on the dependent chain
   E += d;
   if (st) *op = fwd ? v : m * r;
   if (lead) *ep = E;
@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
     // emission constants.  diagonal: (c2, c1) = (Rs, -2 Rs mu) per (k,d) and ck' = ck - sum Rs mu^2, so
     // ll = ck' - sum_d (c2 x^2 + c1 x) (float64: the expansion costs ~1e-12 absolute, two DFMA per term)
     if (a.diag) {
-      for (int i = tid; i < K * D; i += FUSED_NT) {
+      for (int i = tid; i < K * D; i += FUSED_NT) {     // stored [d][k] so that one d serves all states
         const double rs = a.Rs[i], mu = a.gk[i];
-        parS[2 * i] = rs; parS[2 * i + 1] = -2.0 * rs * mu;
+        const int kk = i / D, d = i - kk * D;
+        parS[2 * (d * K + kk)] = -rs; parS[2 * (d * K + kk) + 1] = 2.0 * rs * mu;
       }
       for (int kk = tid; kk < K; kk += FUSED_NT) {
         double c = a.ck[kk];
@@ -195,7 +196,6 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       }
     }
     __syncthreads();
-    constexpr int CH = KP >= 32 ? 4 : 8;              // observation dims held in registers at a time
     for (int row = tid; row < T; row += FUSED_NT) {
       const double* x = xs + (size_t)row * XP;
       bool bad = false;
@@ -207,21 +207,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       if (a.diag) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) ll[k] = k < K ? parS[2 * K * D + k] : -INFINITY;
-        for (int d0 = 0; d0 < D; d0 += CH) {
-          double xd[CH], xx[CH];
-#pragma unroll
-          for (int dd = 0; dd < CH; ++dd) { xd[dd] = d0 + dd < D ? x[d0 + dd] : 0.0; xx[dd] = xd[dd] * xd[dd]; }
+        for (int d = 0; d < D; ++d) {                   // KP independent accumulation chains per d
+          const double xd = x[d], xx = xd * xd;
+          const double2* pp = reinterpret_cast<const double2*>(parS) + (size_t)d * K;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
-            if (k < K) {
-              const double2* pp = reinterpret_cast<const double2*>(parS) + (size_t)k * D + d0;
-              double acc = ll[k];
-#pragma unroll
-              for (int dd = 0; dd < CH; ++dd) {
-                if (d0 + dd < D) { const double2 c = pp[dd]; acc = fma(-c.x, xx[dd], acc); acc = fma(-c.y, xd[dd], acc); }
-              }
-              ll[k] = acc;
-            }
+            if (k < K) { const double2 c = pp[k]; ll[k] = fma(c.x, xx, fma(c.y, xd, ll[k])); }
           }
         }
       } else {
@@ -282,12 +273,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
         const float p1 = (act && i + 1 < K) ? (fwd ? __ldg(a.Pt + (i + 1) * K + j) : __ldg(a.Pt + j * K + i + 1)) : 0.f;
         col2[i / 2] = pack2(p0, p1);
       }
-      // broadcast slots: [parity][fwd, bwd, dump][32]; idle groups write the dump slot
-      const int wslot = live ? grp : 2, rslot = live ? grp : 1;
-      float* w0 = bcS + wslot * 32 + (live ? j : lane);
-      float* w1 = w0 + 96;
-      const float* r0 = bcS + rslot * 32;
-      const float* r1 = r0 + 96;
+      // broadcast slots [parity][warp][32 lanes]: each lane owns one word, a group reads its KP words
+      // (the groups of one warp touch disjoint banks)
+      float* w0 = bcS + wp * 32 + lane;
+      float* w1 = w0 + 64;
+      const float* r0 = bcS + wp * 32 + (lane / KP) * KP;
+      const float* r1 = r0 + 64;
       const int jj = st ? j : 0;
       const int dt = fwd ? KS : -KS;
       const int tb = fwd ? 0 : T - 1;
@@ -299,6 +290,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       if (fwd) { v = act ? __ldg(a.pi0 + j) * bp[0] : 0.f; if (st) *op = v; }
       else { v = act ? bp[0] : 0.f; if (st) *op = act ? 1.f : 0.f; }
       if (lead) *ep = 0;
+      *w1 = v;                                          // step s reads parity s & 1
       int xa = FUSED_XTB, da = 0, E = 0;
       int s = 1;
       float bn = (T > 1 && st) ? bp[dt] : 0.f;
@@ -306,17 +298,17 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
         const float b0 = bn;
         const float b1 = st ? bp[2 * dt] : 0.f, b2 = st ? bp[3 * dt] : 0.f, b3 = st ? bp[4 * dt] : 0.f;
         bn = (s + 4 < T && st) ? bp[5 * dt] : 0.f;
-        chain_step<KP>(v, col2, b0, fwd, st, w1, r1, op + dt, ep + de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b1, fwd, st, w0, r0, op + 2 * dt, ep + 2 * de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b2, fwd, st, w1, r1, op + 3 * dt, ep + 3 * de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b3, fwd, st, w0, r0, op + 4 * dt, ep + 4 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op + dt, ep + de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b1, fwd, st, r0, w1, op + 2 * dt, ep + 2 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b2, fwd, st, r1, w0, op + 3 * dt, ep + 3 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b3, fwd, st, r0, w1, op + 4 * dt, ep + 4 * de, lead, xa, da, E);
         bp += 4 * dt; op += 4 * dt; ep += 4 * de;
       }
       for (; s < T; ++s) {
         const float b0 = bn;
         bn = (s + 1 < T && st) ? bp[2 * dt] : 0.f;
-        if (s & 1) chain_step<KP>(v, col2, b0, fwd, st, w1, r1, op + dt, ep + de, lead, xa, da, E);
-        else chain_step<KP>(v, col2, b0, fwd, st, w0, r0, op + dt, ep + de, lead, xa, da, E);
+        if (s & 1) chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op + dt, ep + de, lead, xa, da, E);
+        else chain_step<KP>(v, col2, b0, fwd, st, r0, w1, op + dt, ep + de, lead, xa, da, E);
         bp += dt; op += dt; ep += de;
       }
     }
@@ -349,7 +341,7 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
         *reinterpret_cast<float4*>(ap + k4) = o;
       }
     }
-    ltS[row] = log((double)sa) + (double)ES[row] * M_LN2;
+    ltS[row] = (double)logf(sa) + (double)ES[row] * M_LN2;
   }
   __syncthreads();
   // posterior marginals out: coalesced copy of the q table
@@ -401,11 +393,26 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
 #pragma unroll
       for (int u = 0; u < 16; ++u) acc[u] = 0.f;
       const int tb = c * len, te = min(T, tb + len);
-      for (int t = tb; t < te; ++t) {
-        int tp = t - 1;
-        if (t == 0) { if (!a.wrap) continue; tp = T - 1; }
-        const float4 pv = *reinterpret_cast<const float4*>(aS + (size_t)tp * KS + i0);
-        const float4 cv = *reinterpret_cast<const float4*>(aS + (size_t)t * KS + j0);
+      int t = tb;
+      if (t == 0 && te > 0) {                            // pair (T-1, 0): the reference's wrap-around
+        if (a.wrap) {
+          const float4 pv = *reinterpret_cast<const float4*>(aS + (size_t)(T - 1) * KS + i0);
+          const float4 cv = *reinterpret_cast<const float4*>(aS + j0);
+          const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v2 = 0; v2 < 4; ++v2) acc[u * 4 + v2] = pa[u] * ca[v2];
+        }
+        t = 1;
+      }
+      const float* pp = aS + (size_t)(t - 1) * KS + i0;
+      const float* pc = aS + (size_t)t * KS + j0;
+#pragma unroll 4
+      for (; t < te; ++t) {
+        const float4 pv = *reinterpret_cast<const float4*>(pp);
+        const float4 cv = *reinterpret_cast<const float4*>(pc);
+        pp += KS; pc += KS;
         const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -432,19 +439,40 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
 
   // ---------------------------------------------------------------- phase C3: emission statistics
   // columns of the float32 window tile: [x_0..x_{D-1} (zero on dropped rows) | w | 0-pad]
-  //   pass 0:  S1[k][c]  = sum_t q[t][k] * X[t][c]            -> sx (c < D), n (c = D)
-  //   pass 1:  diagonal: S2[k][d] = sum_t q[t][k] X[t][d]^2   -> sxx
-  //            full:     S2[k][d][e] = sum_t q[t][k] X[t][d] X[t][e], one d per pass
+  //   S1[k][c] = sum_t q[t][k] X[t][c]                      -> sx (c < D), n (c = D)
+  //   diagonal: S2[k][d] = sum_t q[t][k] X[t][d]^2          -> sxx   (same sweep as S1)
+  //   full:     S2[k][d][e] = sum_t q[t][k] X[t][d] X[t][e] -> sxx   (one extra sweep per d)
   {
-    {
+    {                                                   // refill the window (L2-resident by now) as float32
       const int64_t e0 = s0 * D;
-      for (int i = tid; i < T * DS; i += FUSED_NT) {     // xf overlaps the dead b table only
-        const int r = i / DS, c = i - r * DS;
-        const bool drop = fl[r] & 1;
-        float v = 0.f;
-        if (c < D) v = drop ? 0.f : (float)ld_obs(a.obs, a.dtype, e0 + (int64_t)r * D + c);
-        else if (c == D) v = drop ? 0.f : 1.f;
-        xf[i] = v;
+      const int n = T * D;
+      bool vec = false;
+      if (a.dtype == SVIHMM_F32 && (D & 3) == 0) {
+        const float* src = (const float*)a.obs + e0;
+        if ((((uintptr_t)src) & 15) == 0) {
+          vec = true;
+          const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+          for (int i = tid; i < n / 4; i += FUSED_NT) {
+            float4 q = __ldg(s4 + i);
+            const int r = (4 * i) / D, d = 4 * i - r * D;
+            if (fl[r] & 1) q = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(xf + (size_t)r * DS + d) = q;
+          }
+        }
+      }
+      if (!vec) {
+#pragma unroll 4
+        for (int i = tid; i < n; i += FUSED_NT) {
+          const int r = i / D, d = i - r * D;
+          const float v = (float)ld_obs(a.obs, a.dtype, e0 + i);
+          xf[(size_t)r * DS + d] = (fl[r] & 1) ? 0.f : v;
+        }
+      }
+      const int np = DS - D;                            // w column and padding
+      for (int i = tid; i < T * np; i += FUSED_NT) {
+        const int r = i / np, c = D + (i - r * np);
+        xf[(size_t)r * DS + c] = (c == D && !(fl[r] & 1)) ? 1.f : 0.f;
       }
     }
     const int ncb = DS / 4;
@@ -454,36 +482,48 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
     if (chunks < 1) chunks = 1;
     const int len = (T + chunks - 1) / chunks;
     const bool via_red = nb * chunks <= FUSED_NT;       // else (large K*D) partials go straight to atomics
-    const int npass = a.diag ? 2 : 1 + D;
+    const int npass = a.diag ? 1 : 1 + D;
     for (int pass = 0; pass < npass; ++pass) {
       __syncthreads();
       const int dsel = pass - 1;                        // full covariance: the fixed left factor x_d
+      const bool sq = a.diag != 0;                      // diagonal: second accumulator set for x^2
       for (int it0 = 0; it0 < nb * chunks; it0 += FUSED_NT) {
         const int item = it0 + tid;
         if (item < nb * chunks) {
           const int c = item / nb, blk = item - c * nb;
           const int k0 = (blk / ncb) * 4, c0 = (blk % ncb) * 4;
-          float acc[16];
+          float acc[16], acc2[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+          for (int u = 0; u < 16; ++u) { acc[u] = 0.f; acc2[u] = 0.f; }
           const int tb = c * len, te = min(T, tb + len);
+          const float* qp = aS + (size_t)tb * KS + k0;
+          const float* xp = xf + (size_t)tb * DS + c0;
+          const float* xdp = xf + (size_t)tb * DS + (dsel > 0 ? dsel : 0);
+#pragma unroll 2
           for (int t = tb; t < te; ++t) {
-            const float4 qv = *reinterpret_cast<const float4*>(aS + (size_t)t * KS + k0);
-            float4 xv = *reinterpret_cast<const float4*>(xf + (size_t)t * DS + c0);
-            if (pass > 0) {
-              if (a.diag) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
-              else { const float xd = xf[(size_t)t * DS + dsel]; xv.x *= xd; xv.y *= xd; xv.z *= xd; xv.w *= xd; }
-            }
+            const float4 qv = *reinterpret_cast<const float4*>(qp);
+            float4 xv = *reinterpret_cast<const float4*>(xp);
+            if (pass > 0) { const float xd = *xdp; xv.x *= xd; xv.y *= xd; xv.z *= xd; xv.w *= xd; }
+            qp += KS; xp += DS; xdp += DS;
             const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, xa4[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
               for (int v2 = 0; v2 < 4; ++v2) acc[u * 4 + v2] = fmaf(qa[u], xa4[v2], acc[u * 4 + v2]);
+            if (sq) {
+              const float x2[4] = {xv.x * xv.x, xv.y * xv.y, xv.z * xv.z, xv.w * xv.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v2 = 0; v2 < 4; ++v2) acc2[u * 4 + v2] = fmaf(qa[u], x2[v2], acc2[u * 4 + v2]);
+            }
           }
           if (via_red) {
 #pragma unroll
-            for (int u = 0; u < 16; u += 4)
-              *reinterpret_cast<float4*>(red + (size_t)item * 16 + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+            for (int u = 0; u < 16; u += 4) {
+              *reinterpret_cast<float4*>(red + (size_t)item * 32 + u) = make_float4(acc[u], acc[u + 1], acc[u + 2], acc[u + 3]);
+              *reinterpret_cast<float4*>(red + (size_t)item * 32 + 16 + u) = make_float4(acc2[u], acc2[u + 1], acc2[u + 2], acc2[u + 3]);
+            }
           } else {
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
@@ -492,9 +532,9 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
                 if (pass == 0) {
                   if (cc < D) atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + cc, (double)acc[u]);
                   else if (cc == D) atomicAdd(a.stats_out + a.o_n + kq, (double)acc[u]);
+                  if (sq && cc < D) atomicAdd(a.stats_out + a.o_sxx + (size_t)kq * D + cc, (double)acc2[u]);
                 } else if (cc < D) {
-                  const size_t o = a.diag ? (size_t)kq * D + cc : ((size_t)kq * D + dsel) * D + cc;
-                  atomicAdd(a.stats_out + a.o_sxx + o, (double)acc[u]);
+                  atomicAdd(a.stats_out + a.o_sxx + ((size_t)kq * D + dsel) * D + cc, (double)acc[u]);
                 }
               }
             }
@@ -503,18 +543,18 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       }
       if (via_red) {
         __syncthreads();
-        for (int e = tid; e < nb * 16; e += FUSED_NT) {
-          const int blk = e / 16, u = e - blk * 16;
+        for (int e = tid; e < nb * 32; e += FUSED_NT) {
+          const int blk = e / 32, u2 = e - blk * 32, second = u2 >> 4, u = u2 & 15;
           const int kq = (blk / ncb) * 4 + u / 4, cc = (blk % ncb) * 4 + (u & 3);
-          if (kq < K && cc <= D) {
+          if (kq < K && cc <= D && (!second || (sq && cc < D))) {
             double tot = 0.0;
-            for (int c = 0; c < chunks; ++c) tot += (double)red[((size_t)c * nb + blk) * 16 + u];
-            if (pass == 0) {
+            for (int c = 0; c < chunks; ++c) tot += (double)red[((size_t)c * nb + blk) * 32 + u2];
+            if (second) atomicAdd(a.stats_out + a.o_sxx + (size_t)kq * D + cc, tot);
+            else if (pass == 0) {
               if (cc < D) atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + cc, tot);
               else atomicAdd(a.stats_out + a.o_n + kq, tot);
             } else if (cc < D) {
-              const size_t o = a.diag ? (size_t)kq * D + cc : ((size_t)kq * D + dsel) * D + cc;
-              atomicAdd(a.stats_out + a.o_sxx + o, tot);
+              atomicAdd(a.stats_out + a.o_sxx + ((size_t)kq * D + dsel) * D + cc, tot);
             }
           }
         }
