@@ -104,7 +104,8 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, K * c->plen));
   CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, K * c->plen));
   CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
-  CU(dalloc(&c->lu, (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, (size_t)K * D));
+  CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * (size_t)K * D));
+  CU(dalloc(&c->par2, 2 * (size_t)K * D)); CU(dalloc(&c->ckp, (size_t)K));
   CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, (size_t)K * D)); CU(dalloc(&c->ck, (size_t)K));
   CU(dalloc(&c->stage_stats, c->slen));
   *out = c;
@@ -123,7 +124,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   cudaSetDevice(c->device);
   free_streamed(c);
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
-                  c->pi0, c->lu, c->rowsum, c->ckc, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
+                  c->pi0, c->lu, c->rowsum, c->ckc, c->par2, c->ckp, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -234,9 +235,9 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
   ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
   ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
-  ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck;
+  ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck; ga.par2 = c->par2; ga.ckp = c->ckp;
   const int nblk = ga.diag ? std::max(1, std::min(K, (K * D + 255) / 256)) : K;
-  size_t smem = 2 * (size_t)K * sizeof(double);
+  size_t smem = (2 * (size_t)K + 2) * sizeof(double);
   if (!ga.diag) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PhaseTimer pt(c, PH_UPDATE, st);
@@ -351,7 +352,7 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
   fa.mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
   fa.tri = fa.diag ? D : D * (D + 1) / 2;
   fa.obs = obs; fa.dtype = dtype; fa.mask = mask; fa.starts = starts;
-  fa.Pt = c->Pt; fa.pi0 = c->pi0; fa.Rs = c->Rs; fa.gk = c->gk; fa.ck = c->ck; fa.prior_tran = c->prior_tran;
+  fa.Pt = c->Pt; fa.pi0 = c->pi0; fa.Rs = fa.diag ? c->par2 : c->Rs; fa.gk = c->gk; fa.ck = fa.diag ? c->ckp : c->ck; fa.prior_tran = c->prior_tran;
   fa.var_x_out = var_x_out; fa.stats_out = stats_out; fa.seq = c->seq_ws;
   fa.o_n = (size_t)K * K; fa.o_sx = fa.o_n + K; fa.o_sxx = fa.o_sx + (size_t)K * D;
   fa.o_q0 = fa.o_sxx + (size_t)K * c->DD; fa.o_tail = fa.o_q0 + K;

@@ -23,7 +23,8 @@ struct svihmm_ctx {
   // derived per-global-step constants
   float *Pt, *PtT, *pi0;          // exp(E[log A]) row-major, its transpose, exp(E[log pi])
   double *lu, *rowsum, *ckc;      // scratch of the stationary solve / per-(k,d) constants
-  double *Rs, *gk, *ck;           // emission constants (see prep.cuh)
+  double *Rs, *gk, *ck;           // emission constants (see global.cuh)
+  double *par2, *ckp;             // diagonal emission constants in the fused kernel's form
   // resident series
   const void* obs; const uint8_t* mask; int obs_dtype; int64_t T_full;
   void* obs_own; uint8_t* mask_own;

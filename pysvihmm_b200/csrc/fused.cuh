@@ -92,12 +92,17 @@ __device__ __forceinline__ float hi32(const unsigned long long v) { return __uin
 template <int KP>
 __device__ __forceinline__ void chain_step(float& v, const unsigned long long (&col2)[KP / 2], const float bt,
                                            const bool fwd, const bool st, const float* bcr, float* bcw_next,
-                                           float* op, int* ep, const bool lead, int& xa, int& da, int& E) {
+                                           float* op_prev, int* ep_prev, const bool lead, float& pend, int& xa,
+                                           int& da, int& E) {
   constexpr int NV = KP / 4;
   __syncwarp();                                        // v of the previous step is in the slot
   float4 x[NV];
 #pragma unroll
   for (int q = 0; q < NV; ++q) x[q] = reinterpret_cast<const float4*>(bcr)[q];
+  // side traffic of the PREVIOUS step, queued behind the loads the chain is waiting for (measured:
+  // 114 -> 101 cycles per step against issuing it right after the broadcast store)
+  if (st) *op_prev = pend;
+  if (lead) *ep_prev = E;
   int d = xa - FUSED_XTB - da;
   d = max(-60, min(60, d));
   const float r = __uint_as_float((unsigned)(127 - d) << 23);
@@ -115,8 +120,7 @@ __device__ __forceinline__ void chain_step(float& v, const unsigned long long (&
   v = m * br;
   *bcw_next = v;                                       // the only store on the dependent chain
   E += d;
-  if (st) *op = fwd ? v : m * r;
-  if (lead) *ep = E;
+  pend = fwd ? v : m * r;
   xa = (int)(mx >> 23); da = d;
 }
 
@@ -175,19 +179,12 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
         for (int i = tid; i < n; i += FUSED_NT) { const int r = i / D; xs[(size_t)r * XP + (i - r * D)] = __ldg(src + i); }
       }
     }
-    // emission constants.  diagonal: (c2, c1) = (Rs, -2 Rs mu) per (k,d) and ck' = ck - sum Rs mu^2, so
-    // ll = ck' - sum_d (c2 x^2 + c1 x) (float64: the expansion costs ~1e-12 absolute, two DFMA per term)
+    // emission constants.  diagonal (prepared by the global-step kernel): (c2, c1) = (-Rs, 2 Rs mu) per
+    // [d][k] and ck' = ck - sum Rs mu^2, so ll = ck' + sum_d (c2 x^2 + c1 x) (float64: the expansion
+    // costs ~1e-12 absolute, two DFMA per term)
     if (a.diag) {
-      for (int i = tid; i < K * D; i += FUSED_NT) {     // stored [d][k] so that one d serves all states
-        const double rs = a.Rs[i], mu = a.gk[i];
-        const int kk = i / D, d = i - kk * D;
-        parS[2 * (d * K + kk)] = -rs; parS[2 * (d * K + kk) + 1] = 2.0 * rs * mu;
-      }
-      for (int kk = tid; kk < K; kk += FUSED_NT) {
-        double c = a.ck[kk];
-        for (int d = 0; d < D; ++d) { const double mu = a.gk[kk * D + d]; c -= a.Rs[kk * D + d] * mu * mu; }
-        parS[2 * K * D + kk] = c;
-      }
+      for (int i = tid; i < 2 * K * D; i += FUSED_NT) parS[i] = a.Rs[i];
+      for (int kk = tid; kk < K; kk += FUSED_NT) parS[2 * K * D + kk] = a.ck[kk];
     } else {
       const int np = a.tri + D + 1;
       for (int i = tid; i < K * np; i += FUSED_NT) {
@@ -286,62 +283,66 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       float* op = (fwd ? aS : cS) + (size_t)tb * KS + jj;
       int* ep = ES + tb;
       const int de = fwd ? 1 : 0;                       // only the forward group's exponents are kept
-      float v;
-      if (fwd) { v = act ? __ldg(a.pi0 + j) * bp[0] : 0.f; if (st) *op = v; }
-      else { v = act ? bp[0] : 0.f; if (st) *op = act ? 1.f : 0.f; }
-      if (lead) *ep = 0;
+      float v, pend;
+      if (fwd) { v = act ? __ldg(a.pi0 + j) * bp[0] : 0.f; pend = v; }
+      else { v = act ? bp[0] : 0.f; pend = act ? 1.f : 0.f; }
       *w1 = v;                                          // step s reads parity s & 1
       int xa = FUSED_XTB, da = 0, E = 0;
       int s = 1;
       float bn = (T > 1 && st) ? bp[dt] : 0.f;
+      // each step first flushes the previous step's table entry / exponent (op, ep point at them)
       for (; s + 3 < T; s += 4) {                       // s is odd here: parities 1,0,1,0
         const float b0 = bn;
         const float b1 = st ? bp[2 * dt] : 0.f, b2 = st ? bp[3 * dt] : 0.f, b3 = st ? bp[4 * dt] : 0.f;
         bn = (s + 4 < T && st) ? bp[5 * dt] : 0.f;
-        chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op + dt, ep + de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b1, fwd, st, r0, w1, op + 2 * dt, ep + 2 * de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b2, fwd, st, r1, w0, op + 3 * dt, ep + 3 * de, lead, xa, da, E);
-        chain_step<KP>(v, col2, b3, fwd, st, r0, w1, op + 4 * dt, ep + 4 * de, lead, xa, da, E);
+        chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op, ep, lead, pend, xa, da, E);
+        chain_step<KP>(v, col2, b1, fwd, st, r0, w1, op + dt, ep + de, lead, pend, xa, da, E);
+        chain_step<KP>(v, col2, b2, fwd, st, r1, w0, op + 2 * dt, ep + 2 * de, lead, pend, xa, da, E);
+        chain_step<KP>(v, col2, b3, fwd, st, r0, w1, op + 3 * dt, ep + 3 * de, lead, pend, xa, da, E);
         bp += 4 * dt; op += 4 * dt; ep += 4 * de;
       }
       for (; s < T; ++s) {
         const float b0 = bn;
         bn = (s + 1 < T && st) ? bp[2 * dt] : 0.f;
-        if (s & 1) chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op + dt, ep + de, lead, xa, da, E);
-        else chain_step<KP>(v, col2, b0, fwd, st, r0, w1, op + dt, ep + de, lead, xa, da, E);
+        if (s & 1) chain_step<KP>(v, col2, b0, fwd, st, r1, w0, op, ep, lead, pend, xa, da, E);
+        else chain_step<KP>(v, col2, b0, fwd, st, r0, w1, op, ep, lead, pend, xa, da, E);
         bp += dt; op += dt; ep += de;
       }
+      if (st) *op = pend;                               // entry of the last step
+      if (lead) *ep = E;
     }
   }
   __syncthreads();
   FUSED_STAMP(2);
 
-  // ---------------------------------------------------------------- phase C1: marginals (thread per row)
-  for (int row = tid; row < T; row += FUSED_NT) {
-    float* ap = aS + (size_t)row * KS;
-    const float* cp = cS + (size_t)row * KS;
-    float p[KP];
-    float sa = 0.f, sp = 0.f;
-#pragma unroll
-    for (int k4 = 0; k4 < KP; k4 += 4) {
-      if (k4 < KS) {
-        const float4 al = *reinterpret_cast<const float4*>(ap + k4);
-        const float4 be = *reinterpret_cast<const float4*>(cp + k4);
-        p[k4] = al.x * be.x; p[k4 + 1] = al.y * be.y; p[k4 + 2] = al.z * be.z; p[k4 + 3] = al.w * be.w;
-        sa += (al.x + al.y) + (al.z + al.w);
-        sp += (p[k4] + p[k4 + 1]) + (p[k4 + 2] + p[k4 + 3]);
+  // ---------------------------------------------------------------- phase C1: marginals
+  // KP/4 lanes per row, one float4 of alpha~ and beta~ each: a warp touches contiguous shared memory
+  {
+    constexpr int LPR = KP / 4, RPW = 32 / LPR;
+    const int lane = tid & 31, wp = tid >> 5;
+    const int sub = lane % LPR, rsub = lane / LPR;
+    for (int row0 = wp * RPW; row0 < T; row0 += (FUSED_NT / 32) * RPW) {     // warp-uniform trip count
+      const int row = row0 + rsub;
+      const bool ok = row < T && 4 * sub < KS;
+      float4 al = make_float4(0.f, 0.f, 0.f, 0.f), be = al;
+      if (ok) {
+        al = *reinterpret_cast<const float4*>(aS + (size_t)row * KS + 4 * sub);
+        be = *reinterpret_cast<const float4*>(cS + (size_t)row * KS + 4 * sub);
       }
-    }
-    const float inv = 1.f / sp;
+      float4 p = make_float4(al.x * be.x, al.y * be.y, al.z * be.z, al.w * be.w);
+      float sa = (al.x + al.y) + (al.z + al.w), sp = (p.x + p.y) + (p.z + p.w);
 #pragma unroll
-    for (int k4 = 0; k4 < KP; k4 += 4) {
-      if (k4 < KS) {
-        float4 o;
-        o.x = p[k4] * inv; o.y = p[k4 + 1] * inv; o.z = p[k4 + 2] * inv; o.w = p[k4 + 3] * inv;
-        *reinterpret_cast<float4*>(ap + k4) = o;
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
       }
+      const float inv = 1.f / sp;
+      if (ok) {
+        p.x *= inv; p.y *= inv; p.z *= inv; p.w *= inv;
+        *reinterpret_cast<float4*>(aS + (size_t)row * KS + 4 * sub) = p;
+      }
+      if (sub == 0 && row < T) ltS[row] = (double)logf(sa) + (double)ES[row] * M_LN2;
     }
-    ltS[row] = (double)logf(sa) + (double)ES[row] * M_LN2;
   }
   __syncthreads();
   // posterior marginals out: coalesced copy of the q table

@@ -20,9 +20,10 @@ struct GlobalArgs {
   double *W, *vinit, *emit;                 // vinit: [0,K) the vector in use, [K,2K) the user-given one
   const double *prior_tran, *prior_init, *prior_emit, *stats;
   double lrate, bA, bE;
-  double *gth, *rowsum, *ckc;               // scratch: K*K, K, K*D doubles
+  double *gth, *rowsum, *ckc;               // scratch: 2*K*K, K, 2*K*D doubles
   float *Pt, *PtT, *pi0;
   double *Rs, *gk, *ck;
+  double *par2, *ckp;                       // diagonal, fused-kernel form: [d][k] (-Rs, 2 Rs mu) and ck - sum Rs mu^2
 };
 
 // psi(x), float64: recurrence up to x >= 10 (branch-free, the reciprocals are independent), then the
@@ -60,6 +61,49 @@ __device__ inline GStats gstats(const double* s, int K, int D, int DD) {
 }
 
 // ---- block 0 -------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Perron vector of the row-stochastic G (K <= 32) by repeated squaring: G^(2^m) -> 1 pi^T at the
+// rate lambda_2^(2^m), so ~log2(log(1e-16)/log(lambda_2)) squarings of a K x K matrix (each a
+// fully parallel K^3 product) replace the K-step elimination.  All entries of G are positive
+// (Dirichlet parameters > 0), hence the chain is primitive.  Executed by threads [t0, t0+nt).
+__device__ void stationary_by_squaring(const int K, double* A, double* Bm, double* pi, const int tl, const int nt,
+                                       const int bar_id) {
+  const int KK = K * K;
+  for (int it = 0; it < 60; ++it) {
+    for (int idx = tl; idx < KK; idx += nt) {
+      const int i = idx / K, j = idx - i * K;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int l = 0;
+      for (; l + 3 < K; l += 4) {
+        s0 = fma(A[i * K + l], A[l * K + j], s0);
+        s1 = fma(A[i * K + l + 1], A[(l + 1) * K + j], s1);
+        s2 = fma(A[i * K + l + 2], A[(l + 2) * K + j], s2);
+        s3 = fma(A[i * K + l + 3], A[(l + 3) * K + j], s3);
+      }
+      for (; l < K; ++l) s0 = fma(A[i * K + l], A[l * K + j], s0);
+      Bm[idx] = (s0 + s1) + (s2 + s3);
+    }
+    bar_named(bar_id, nt);
+    // converged when every row agrees with row 0 to 1e-13 relative (rounding noise is ~K eps)
+    int bad = 0;
+    for (int idx = tl; idx < KK; idx += nt) {
+      const int j = idx % K;
+      bad |= fabs(Bm[idx] - Bm[j]) > 1e-13 * Bm[j];
+    }
+    double* t = A; A = Bm; Bm = t;
+    // block-wide OR over the nt participating threads through shared memory
+    if (tl == 0) pi[K] = 0.0;
+    bar_named(bar_id, nt);
+    if (bad) pi[K] = 1.0;
+    bar_named(bar_id, nt);
+    if (pi[K] == 0.0) break;
+  }
+  for (int j = tl; j < K; j += nt) pi[j] = A[j];
+}
+
 __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   const int K = a.K, tid = threadIdx.x, nth = blockDim.x;
   const int KK = K * K;
@@ -81,27 +125,39 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
     if (lane == 0) a.rowsum[i] = s;
   }
   __syncthreads();
-  for (int i = tid; i < K; i += nth) sm[i] = digamma_fast(a.rowsum[i] + SVIHMM_EPS);
-  __syncthreads();
-  double* G = a.gth;                                      // GTH matrix (global scratch, L1/L2 resident)
-  for (int idx = tid; idx < KK; idx += nth) {
-    const int i = idx / K, j = idx - i * K;
-    const double w = a.W[idx];
-    const float v = (float)exp(digamma_fast(w + SVIHMM_EPS) - sm[i]);
-    a.Pt[idx] = v;
-    a.PtT[j * K + i] = v;
-    G[idx] = w / a.rowsum[i];
+  double* pi = sm;                                        // K + 1 doubles
+  double* G = a.gth;                                      // K*K (+ K*K for the squaring) doubles of scratch
+  const bool square = !a.user_init && K <= 32;
+  const int half = nth / 2;
+  // the two halves of the block work concurrently: threads [0, half) the digamma transforms of the
+  // transition matrix, threads [half, nth) the stationary vector
+  if (tid < half || !square) {
+    const int tl = square ? tid : tid, nt = square ? half : nth;
+    for (int idx = tl; idx < KK; idx += nt) {
+      const int i = idx / K, j = idx - i * K;
+      const double w = a.W[idx];
+      const float v = (float)exp(digamma_fast(w + SVIHMM_EPS) - digamma_fast(a.rowsum[i] + SVIHMM_EPS));
+      a.Pt[idx] = v;
+      a.PtT[j * K + i] = v;
+      if (!square) G[idx] = w / a.rowsum[i];
+    }
+  } else {
+    const int tl = tid - half, nt = nth - half;
+    for (int idx = tl; idx < KK; idx += nt) G[idx] = a.W[idx] / a.rowsum[idx / K];
+    bar_named(1, nt);
+    stationary_by_squaring(K, G, G + KK, pi, tl, nt, 1);
   }
   __syncthreads();
-  if (!a.user_init) {
-    // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1
+  if (!a.user_init && !square) {
+    // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
     for (int n = K - 1; n >= 1; --n) {
       if (wp == 0) {
         double s = 0.0;
         for (int j = lane; j < n; j += 32) s += G[n * K + j];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        for (int i = lane; i < n; i += 32) G[i * K + n] /= s;
+        const double rinv = 1.0 / s;
+        for (int i = lane; i < n; i += 32) G[i * K + n] *= rinv;
       }
       __syncthreads();
       for (int idx = tid; idx < n * n; idx += nth) {
@@ -111,7 +167,6 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
       __syncthreads();
     }
     // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]: column j accumulates as the pi[i] become final
-    double* pi = sm + K;                                   // K doubles
     if (wp == 0) {
       for (int j = lane; j < K; j += 32) pi[j] = j == 0 ? 1.0 : 0.0;
       __syncwarp();
@@ -121,19 +176,19 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
         __syncwarp();
       }
     }
-    if (wp == 0) {
+  }
+  if (wp == 0) {
+    if (!a.user_init) {
       double n2 = 0.0;
       for (int j = lane; j < K; j += 32) n2 += pi[j] * pi[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
       n2 = sqrt(n2);
       for (int j = lane; j < K; j += 32) a.vinit[j] = fabs(pi[j]) / n2;
+    } else {
+      for (int j = lane; j < K; j += 32) a.vinit[j] = a.vinit[K + j];
     }
-  } else {
-    for (int i = tid; i < K; i += nth) a.vinit[i] = a.vinit[K + i];
-  }
-  __syncthreads();
-  if (wp == 0) {
+    __syncwarp();
     double n1 = 0.0;
     for (int j = lane; j < K; j += 32) n1 += a.vinit[j];
 #pragma unroll
@@ -266,15 +321,20 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
     }
     if (a.mode != GM_PREP) { p[d] = mu; p[D + d] = sg; p[2 * D + d] = ka; p[3 * D + d] = nu; }
     // ll = ck - sum_d Rs (x_d - mu_d)^2 with Rs = nu / (2 sigma)
-    a.Rs[e] = nu / (2.0 * sg);
+    const double rs = nu / (2.0 * sg);
+    a.Rs[e] = rs;
     a.gk[e] = mu;
-    a.ckc[e] = 0.5 * (digamma_fast(0.5 * nu) + M_LN2 - log(sg)) - 1.0 / (2.0 * ka) - 0.5 * log(2.0 * M_PI);
+    a.par2[2 * ((size_t)d * K + k)] = -rs;
+    a.par2[2 * ((size_t)d * K + k) + 1] = 2.0 * rs * mu;
+    a.ckc[2 * (size_t)e] = 0.5 * (digamma_fast(0.5 * nu) + M_LN2 - log(sg)) - 1.0 / (2.0 * ka) - 0.5 * log(2.0 * M_PI);
+    a.ckc[2 * (size_t)e + 1] = rs * mu * mu;
   }
   __syncthreads();
   for (int k = k0 + tid; k < k1; k += nth) {
-    double c = 0.0;
-    for (int d = 0; d < D; ++d) c += a.ckc[(size_t)k * D + d];
+    double c = 0.0, c0 = 0.0;
+    for (int d = 0; d < D; ++d) { c += a.ckc[2 * ((size_t)k * D + d)]; c0 += a.ckc[2 * ((size_t)k * D + d) + 1]; }
     a.ck[k] = c;
+    a.ckp[k] = c - c0;
   }
 }
 
