@@ -240,9 +240,25 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   size_t smem = (2 * (size_t)K + 2) * sizeof(double);
   if (!ga.diag) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PhaseTimer pt(c, PH_UPDATE, st);
-  k_global_step<<<1 + nblk, 256, smem, st>>>(ga, nblk);
-  LAUNCHED(c);
+  static const bool gdbg = getenv("SVIHMM_GLOBAL_DBG") != nullptr;
+  ga.dbg = nullptr;
+  if (gdbg) CU(cudaMalloc((void**)&ga.dbg, 128));
+  {
+    PhaseTimer pt(c, PH_UPDATE, st);
+    // K*K digamma threads + one warp for the stationary vector
+    const int nthr = std::min(512, ((K * K + 31) / 32) * 32 + 32);
+    k_global_step<<<1 + nblk, std::max(nthr, 128), smem, st>>>(ga, nblk);
+    LAUNCHED(c);
+  }
+  if (gdbg) {
+    long long h[16];
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h, ga.dbg, 128, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[global dbg] squarings=%lld pi0 section: norm2=%lld store=%lld n1=%lld dgs=%lld rest=%lld\n", h[10], h[6] - h[2], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[3] - h[9]);
+    CU(cudaFree(ga.dbg));
+    fprintf(stderr, "[global dbg] mode=%d cycles: update+rowsum=%lld P||stationary=%lld gth=%lld pi0=%lld | emission block=%lld\n", mode,
+            h[1] - h[0], h[2] - h[1], 0LL, h[3] - h[2], h[5] - h[4]);
+  }
   return SVIHMM_OK;
 }
 

@@ -66,7 +66,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(int T, int K, int D, int 
   if (endA > end) end = endA;
   s.mx = fused_al16(end);                           // T doubles: row maxima of ll
   s.late = fused_al16(s.mx + (size_t)T * 8);        // phase A: emission constants; B/C: lt (T doubles) + E (T ints)
-  const size_t params = diag ? ((size_t)K * D * 16 + (size_t)K * 8) : ((size_t)K * (tri + D + 1) * 8);
+  const size_t params = diag ? ((size_t)s.KS * D * 16 + (size_t)s.KS * 8) : ((size_t)K * (tri + D + 1) * 8);
   const size_t late = (size_t)T * 12;
   s.flags = s.late + fused_al16(params > late ? params : late);
   s.bc = fused_al16(s.flags + (size_t)T);           // 2 parities x 2 warps x 32 floats
@@ -183,8 +183,13 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
     // [d][k] and ck' = ck - sum Rs mu^2, so ll = ck' + sum_d (c2 x^2 + c1 x) (float64: the expansion
     // costs ~1e-12 absolute, two DFMA per term)
     if (a.diag) {
-      for (int i = tid; i < 2 * K * D; i += FUSED_NT) parS[i] = a.Rs[i];
-      for (int kk = tid; kk < K; kk += FUSED_NT) parS[2 * K * D + kk] = a.ck[kk];
+      for (int i = tid; i < KS * D; i += FUSED_NT) {      // [d][KS], zero-padded columns
+        const int d = i / KS, kk = i - d * KS;
+        const bool in = kk < K;
+        parS[2 * i] = in ? a.Rs[2 * (d * K + kk)] : 0.0;
+        parS[2 * i + 1] = in ? a.Rs[2 * (d * K + kk) + 1] : 0.0;
+      }
+      for (int kk = tid; kk < KS; kk += FUSED_NT) parS[2 * KS * D + kk] = kk < K ? a.ck[kk] : 0.0;
     } else {
       const int np = a.tri + D + 1;
       for (int i = tid; i < K * np; i += FUSED_NT) {
@@ -203,13 +208,19 @@ __global__ void __launch_bounds__(FUSED_NT, 2) k_estep_fused(const FusedArgs a) 
       double ll[KP];
       if (a.diag) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) ll[k] = k < K ? parS[2 * K * D + k] : -INFINITY;
-        for (int d = 0; d < D; ++d) {                   // KP independent accumulation chains per d
+        for (int k = 0; k < KP; ++k) ll[k] = k < KS ? parS[2 * KS * D + k] : 0.0;
+        for (int d = 0; d < D; ++d) {                   // independent accumulation chains, 4 loads in flight
           const double xd = x[d], xx = xd * xd;
-          const double2* pp = reinterpret_cast<const double2*>(parS) + (size_t)d * K;
+          const double2* pp = reinterpret_cast<const double2*>(parS) + (size_t)d * KS;
 #pragma unroll
-          for (int k = 0; k < KP; ++k) {
-            if (k < K) { const double2 c = pp[k]; ll[k] = fma(c.x, xx, fma(c.y, xd, ll[k])); }
+          for (int k0 = 0; k0 < KP; k0 += 4) {
+            if (k0 < KS) {
+              const double2 c0 = pp[k0], c1 = pp[k0 + 1], c2 = pp[k0 + 2], c3 = pp[k0 + 3];
+              ll[k0] = fma(c0.x, xx, fma(c0.y, xd, ll[k0]));
+              ll[k0 + 1] = fma(c1.x, xx, fma(c1.y, xd, ll[k0 + 1]));
+              ll[k0 + 2] = fma(c2.x, xx, fma(c2.y, xd, ll[k0 + 2]));
+              ll[k0 + 3] = fma(c3.x, xx, fma(c3.y, xd, ll[k0 + 3]));
+            }
           }
         }
       } else {
