@@ -127,6 +127,13 @@ int svihmm_global_update(svihmm_ctx* ctx, const double* stats, double lrate, dou
  * stats must come from svihmm_estep with B = 1, flags without WRAP / ADD_PRIOR. */
 int svihmm_batch_update(svihmm_ctx* ctx, const double* stats, void* stream);
 
+/* Batch natural-gradient step, hmmbatchsgd.py:202-259: var_init = prior_init + q0,
+ *   var_tran <- (1-lrate)(var_tran-1) + lrate*(prior_tran + A - 1) + 1,
+ *   eta_k    <- (1-lrate) eta_k + lrate * eta(conjugate posterior of state k)  [= eta_prior + e_k]
+ * stats must come from svihmm_estep with B = 1 and SVIHMM_ADD_PRIOR (| SVIHMM_MASK_LL as
+ * hmmbatchsgd.infer NaN-masks the observations, :148-149), no SVIHMM_WRAP. */
+int svihmm_batchsgd_update(svihmm_ctx* ctx, const double* stats, double lrate, void* stream);
+
 /* Local tables of the last svihmm_estep (valid until the next one; device -> dst at loc):
  *   lliks  B*T*K float64  expected log-likelihoods (self.lliks, hmmsgd_metaobs.py:508-509)
  *   alpha  B*T*K float32  normalised forward messages = softmax_k(self.lalpha[t])

@@ -332,3 +332,29 @@ def batch_cavi_step(obs, mask, var_init, var_tran, emit, prior_init, prior_tran,
     res.update(var_init_new=new_init, var_tran_new=new_tran, emit_new=new_emit,
                lZ=float(local_lower_bound(res['lalpha'])[0]))
     return res
+
+
+# --------------------------------------------------------------------------
+# batch natural gradient (hmmbatchsgd.py)
+# --------------------------------------------------------------------------
+def batch_sgd_step(obs, mask, var_init, var_tran, emit, prior_init, prior_tran, prior_emit, lrate):
+    """One iteration of hmmbatchsgd.VBHMM.infer (:160-168): base local_update (hmmbase.py:201-229) on
+    the NaN-masked observations (:148-149) then global_update (:202-259): the natural parameters move
+    a step `lrate` towards those of the conjugate full-batch update."""
+    xo = obs.copy()
+    if mask is not None:
+        xo[mask] = np.nan
+    res = local_update(xo[None], var_init, var_tran, emit)
+    q = res['var_x'][0]
+    new_init = prior_init + q[0]                                        # :216
+    tran_mf = prior_tran + tran_stat(q[None], wrap=False)[0]            # :222-225
+    new_tran = (1. - lrate) * (var_tran - 1.) + lrate * (tran_mf - 1.) + 1.
+    inds = np.logical_not(mask) if mask is not None else np.ones(len(obs), bool)
+    new_emit = []
+    for k in range(q.shape[1]):
+        post = niw_posterior(prior_emit[k], obs[inds], q[inds, k])      # util.NIW_meanfield
+        nt = niw_natural(post['mu'], post['sigma'], post['kappa'], post['nu'])
+        no = niw_natural(emit[k]['mu'], emit[k]['sigma'], emit[k]['kappa'], emit[k]['nu'])
+        new_emit.append(niw_moment(*[(1. - lrate) * o + lrate * t for o, t in zip(no, nt)]))
+    res.update(var_init_new=new_init, var_tran_new=new_tran, emit_new=new_emit)
+    return res

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsvihmm.so")
+LIB_PATH = os.environ.get("SVIHMM_LIB", os.path.join(HERE, "lib", "libsvihmm.so"))   # override: A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EMIT_NIW_FULL, EMIT_NIW_DIAG = 0, 1
@@ -31,6 +31,7 @@ SYMBOLS = {
     "svihmm_estep_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _vp]),
     "svihmm_global_update": (_i, [_vp, _vp, _d, _d, _d, _vp]),
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
+    "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_launch_count": (_i64, [_vp]),
     "svihmm_set_profiling": (_i, [_vp, _i]),

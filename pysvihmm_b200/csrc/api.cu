@@ -12,6 +12,7 @@
 #include "stats.cuh"
 #include "global.cuh"
 #include "fused.cuh"
+#include "fused_pipe.cuh"
 
 static thread_local std::string g_err;
 
@@ -337,6 +338,34 @@ static cudaError_t launch_fused(const FusedArgs& fa, size_t smem, cudaStream_t s
   return cudaGetLastError();
 }
 
+template <int KP>
+static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st, bool set_attr) {
+  if (set_attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_estep_pipe<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_estep_pipe<KP><<<fa.B, FP_NT, smem, st>>>(fa);
+  return cudaGetLastError();
+}
+
+// Pipelined single-kernel E-step (fused_pipe.cuh): same conditions as the phase-by-phase fused
+// kernel plus: every 4x4 statistics tile owned by one worker thread, barriers within the budget.
+static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
+  static const bool off = getenv("SVIHMM_NO_PIPE") != nullptr;
+  if (off || c->K > 32 || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+  const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
+  const PipeSmem L = pipe_smem_layout(T, c->K, c->D, tri, diag);
+  if (L.total > (size_t)c->max_smem_optin) return false;
+  const int nwk = c->K > 16 ? 128 : 192;
+  const int nbi = L.KS / 4, ncb = ((c->D + 1 + 3) & ~3) / 4;
+  if (nbi * nbi > nwk || nbi * ncb > nwk || (!diag && nbi * c->D * ncb > nwk)) return false;
+  const int npairs = (T + 1) / 2, nrounds = (npairs + nwk / 2 - 1) / (nwk / 2), ntiles = (T - T / 2 + FP_TB - 1) / FP_TB;
+  if (nrounds + ntiles > FP_MAXBAR || ntiles > 190) return false;
+  *smem_out = L.total;
+  return true;
+}
+
 // Single-kernel E-step (fused.cuh) when the window fits in shared memory: K <= 32, the three
 // T*K float tables + per-row scalars + emission constants <= the opt-in limit.
 static bool fused_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
@@ -351,7 +380,7 @@ static bool fused_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* s
 
 static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                        const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
-                       unsigned flags, size_t smem, cudaStream_t st) {
+                       unsigned flags, size_t smem, cudaStream_t st, bool pipe) {
   const int K = c->K, D = c->D;
   if ((size_t)B > c->cap_B) {
     if (c->seq_ws) CU(cudaFree(c->seq_ws));
@@ -374,27 +403,48 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
   fa.o_q0 = fa.o_sxx + (size_t)K * c->DD; fa.o_tail = fa.o_q0 + K;
   static const bool dbg_on = getenv("SVIHMM_FUSED_DBG") != nullptr;
   fa.dbg = nullptr;
-  if (dbg_on) CU(cudaMalloc((void**)&fa.dbg, sizeof(long long) * 8 * B));
+  if (dbg_on) CU(cudaMalloc((void**)&fa.dbg, sizeof(long long) * 16 * B));
   const bool set_attr = smem > 48 * 1024;
   cudaError_t e;
-  switch (c->KP) {
-    case 2:
-    case 4: e = launch_fused<4>(fa, smem, st, set_attr); break;
-    case 8: e = launch_fused<8>(fa, smem, st, set_attr); break;
-    case 16: e = launch_fused<16>(fa, smem, st, set_attr); break;
-    default: e = launch_fused<32>(fa, smem, st, set_attr); break;
+  if (pipe) {
+    switch (c->KP) {
+      case 2:
+      case 4: e = launch_pipe<4>(fa, smem, st, set_attr); break;
+      case 8: e = launch_pipe<8>(fa, smem, st, set_attr); break;
+      case 16: e = launch_pipe<16>(fa, smem, st, set_attr); break;
+      default: e = launch_pipe<32>(fa, smem, st, set_attr); break;
+    }
+  } else {
+    switch (c->KP) {
+      case 2:
+      case 4: e = launch_fused<4>(fa, smem, st, set_attr); break;
+      case 8: e = launch_fused<8>(fa, smem, st, set_attr); break;
+      case 16: e = launch_fused<16>(fa, smem, st, set_attr); break;
+      default: e = launch_fused<32>(fa, smem, st, set_attr); break;
+    }
   }
   if (e != cudaSuccess) return fail(SVIHMM_ECUDA, "fused E-step launch failed: %s", cudaGetErrorString(e));
-  if (dbg_on) {            // debug: mean clock cycles per phase over the CTAs of this launch
+  if (dbg_on && pipe) {
+    std::vector<long long> h((size_t)16 * B);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h.data(), fa.dbg, sizeof(long long) * 16 * B, cudaMemcpyDeviceToHost));
+    double m[6] = {0, 0, 0, 0, 0, 0}, q[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < B; ++b) for (int i = 1; i < 6; ++i) m[i] += (double)(h[16 * b + i] - h[16 * b]) / B;
+    for (int b = 0; b < B; ++b) for (int i = 0; i < 5; ++i) q[i] += (double)h[16 * b + 8 + i] / B;
+    fprintf(stderr, "[pipe dbg] worker 0 totals over tiles: wait=%.0f C1=%.0f bar=%.0f C2=%.0f C3+prefetch=%.0f\n", q[0], q[1], q[2], q[3], q[4]);
+    fprintf(stderr, "[pipe dbg] B=%d T=%d smem=%zu cycles since CTA start: chain start=%.0f chain end=%.0f (%.1f/step) | workers: phase A done=%.0f last tile done=%.0f | before final atomics=%.0f\n",
+            B, T, smem, m[1], m[2], (m[2] - m[1]) / (T > 1 ? T - 1 : 1), m[3], m[4], m[5]);
+  }
+  if (dbg_on && !pipe) {   // debug: mean clock cycles per phase over the CTAs of this launch
     std::vector<long long> h((size_t)8 * B);
     CU(cudaStreamSynchronize(st));
     CU(cudaMemcpy(h.data(), fa.dbg, sizeof(long long) * 8 * B, cudaMemcpyDeviceToHost));
-    CU(cudaFree(fa.dbg));
     double ph[5] = {0, 0, 0, 0, 0};
     for (int b = 0; b < B; ++b) for (int i = 0; i < 5; ++i) ph[i] += (double)(h[8 * b + i + 1] - h[8 * b + i]) / B;
     fprintf(stderr, "[fused dbg] B=%d T=%d smem=%zu cycles: A(emit)=%.0f B(chains)=%.0f C1(q,out,logZ)=%.0f C2(tran stat)=%.0f C3(emit stats)=%.0f\n",
             B, T, smem, ph[0], ph[1], ph[2], ph[3], ph[4]);
   }
+  if (dbg_on) CU(cudaFree(fa.dbg));
   c->launches++;
   c->last_B = B; c->last_T = T; c->last_fused = 1;
   return SVIHMM_OK;
@@ -406,8 +456,10 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   const int K = c->K, D = c->D;
   const bool xi = flags & SVIHMM_EXACT_XI;
   size_t fsmem = 0;
+  if (pipe_eligible(c, T, flags, &fsmem))
+    return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st, true);
   if (fused_eligible(c, T, flags, &fsmem))
-    return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st);
+    return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st, false);
   int rc = ensure_ws(c, B, T, xi);
   if (rc) return rc;
   const int64_t R = (int64_t)B * T;
@@ -641,6 +693,14 @@ extern "C" int svihmm_batch_update(svihmm_ctx* c, const double* stats, void* str
   CU(cudaSetDevice(c->device));
   c->user_init = 1;    // hmmbatchcd.py:179: var_init becomes an explicit Dirichlet parameter
   return run_global(c, GM_BATCH, stats, 0.0, 0.0, 0.0, (cudaStream_t)stream);
+}
+
+extern "C" int svihmm_batchsgd_update(svihmm_ctx* c, const double* stats, double lrate, void* stream) {
+  if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  CU(cudaSetDevice(c->device));
+  c->user_init = 1;    // hmmbatchsgd.py:216: var_init = prior_init + q[0]
+  return run_global(c, GM_BSGD, stats, lrate, 1.0, 1.0, (cudaStream_t)stream);
 }
 
 extern "C" int svihmm_get_locals(svihmm_ctx* c, double* lliks, float* alpha, double* mx, float* cs,

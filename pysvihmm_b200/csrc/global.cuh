@@ -12,7 +12,7 @@
 #pragma once
 #include "common.cuh"
 
-enum { GM_PREP = 0, GM_SVI = 1, GM_BATCH = 2 };
+enum { GM_PREP = 0, GM_SVI = 1, GM_BATCH = 2, GM_BSGD = 3 };   // BSGD: hmmbatchsgd.py:202-259 (SVI blend + explicit var_init)
 
 struct GlobalArgs {
   int K, D, DD, diag, mode, user_init;
@@ -106,9 +106,13 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   GSTAMP(0);
   const int KK = K * K;
   const GStats sv = gstats(a.stats, K, a.D, a.DD);
-  if (a.mode == GM_SVI) {
+  if (a.mode == GM_SVI || a.mode == GM_BSGD) {
 #pragma unroll 1
     for (int i = tid; i < KK; i += nth) a.W[i] = (1.0 - a.lrate) * (a.W[i] - 1.0) + a.lrate * a.bA * sv.A[i] + 1.0;
+    if (a.mode == GM_BSGD) {
+#pragma unroll 1
+      for (int i = tid; i < K; i += nth) a.vinit[K + i] = a.prior_init[i] + sv.q0[i];   // hmmbatchsgd.py:216
+    }
   } else if (a.mode == GM_BATCH) {
 #pragma unroll 1
     for (int i = tid; i < KK; i += nth) a.W[i] = a.prior_tran[i] + sv.A[i];
@@ -237,7 +241,7 @@ __device__ void global_emit_full_block(const GlobalArgs& a, const int k, double*
   double* p = a.emit + (size_t)k * a.plen;
   const double* pr = a.prior_emit + (size_t)k * a.plen;
   const size_t oS = D, oK = (size_t)D + (size_t)D * D, oN = oK + 1;
-  if (a.mode == GM_SVI) {
+  if (a.mode == GM_SVI || a.mode == GM_BSGD) {
     const double ka_o = p[oK], nu_o = p[oN], ka_p = pr[oK], nu_p = pr[oN], nk = sv.n[k];
     const double e2 = (1.0 - a.lrate) * ka_o + a.lrate * (ka_p + a.bE * nk);
     const double e4 = (1.0 - a.lrate) * (nu_o + 2.0 + D) + a.lrate * (nu_p + 2.0 + D + a.bE * nk);
@@ -352,7 +356,7 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
     const double* pr = a.prior_emit + (size_t)k * 4 * D;
     double mu = p[d], sg = p[D + d], ka = p[2 * D + d], nu = p[3 * D + d];
     const double mu0 = pr[d], sg0 = pr[D + d], ka0 = pr[2 * D + d], nu0 = pr[3 * D + d];
-    if (a.mode == GM_SVI) {
+    if (a.mode == GM_SVI || a.mode == GM_BSGD) {
       const double nk = sv.n[k];
       const double e1 = (1.0 - a.lrate) * ka * mu + a.lrate * (ka0 * mu0 + a.bE * sv.sx[e]);
       const double e2 = (1.0 - a.lrate) * ka + a.lrate * (ka0 + a.bE * nk);

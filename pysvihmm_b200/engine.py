@@ -183,6 +183,10 @@ class EStepEngine(object):
         """hmmbatchcd.py:172-189 on the device-resident globals."""
         L.check(self.lib.svihmm_batch_update(self._h, _ptr(stats), self._stream()))
 
+    def batchsgd_update(self, stats, lrate):
+        """hmmbatchsgd.py:202-259 on the device-resident globals."""
+        L.check(self.lib.svihmm_batchsgd_update(self._h, _ptr(stats), float(lrate), self._stream()))
+
     def get_locals(self, B, T, tables=True):
         """Per-window [logZ, Q4 bound]; with tables=True also lliks/alpha/mx/cs (needs the last
         estep to have run with keep_locals=True)."""

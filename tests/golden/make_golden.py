@@ -25,6 +25,7 @@ sys.path.insert(0, REF)
 
 import hmmsgd_metaobs as HSGD          # noqa: E402
 import hmmbatchcd as HCD               # noqa: E402
+import hmmbatchsgd as HBS              # noqa: E402
 import gen_synthetic as GS             # noqa: E402
 from pybasicbayes.distributions import Gaussian   # noqa: E402
 
@@ -176,6 +177,52 @@ def cavi_case(name, seed, T, maxit=3):
         name, T, len(rec['lZ']), float(np.mean(out["it_var_x"].max(-1) < 0.99))))
 
 
+def bsgd_case(name, seed, T, maxit=3):
+    """hmmbatchsgd.VBHMM (batch natural gradient, hmmbatchsgd.py:143-259) on overlapping
+    two-cluster data with a mask (rows NaN-ed inside infer, :148-149), explicit emission inits."""
+    K, D = 3, 2
+    rs = np.random.RandomState(seed)
+    sts = (np.arange(T) * K) // T
+    obs = rs.randn(T, D) + 1.2 * sts[:, None]
+    mask = np.zeros(T, bool)
+    mask[rs.choice(T, T // 8, replace=False)] = True
+    prior = dict(mu=np.zeros(D), sigma=0.75 * np.cov(obs.T), kappa=0.01, nu=4.)
+    init = [dict(mu=np.array([-0.3, 0.2]) + 1.1 * k, sigma=np.eye(D) * (1.5 + 0.2 * k), kappa=0.5 + 0.1 * k,
+                 nu=5. + k) for k in range(K)]
+    prior_emit = emit_objects(init, prior)
+    init_tran = 1. + 3. * rs.rand(K, K)
+    hmm = HBS.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7, mask=mask,
+                    init_tran=init_tran.copy(), maxit=maxit)
+    out = dict(obs=obs, sts=sts, mask=mask, prior_init=np.ones(K), prior_tran=np.ones((K, K)),
+               prior_mu=prior['mu'], prior_sigma=prior['sigma'], prior_kappa=prior['kappa'],
+               prior_nu=prior['nu'], init_var_init=hmm.var_init.copy(),
+               init_var_tran=hmm.var_tran.copy(), maxit=maxit, tau=1., kappa_lr=0.7)
+    pack_emit("init", hmm.var_emit, out)
+    rec = dict(var_x=[], var_init=[], var_tran=[], mu=[], sigma=[], kappa=[], nu=[], lrate=[])
+    gu = hmm.global_update
+
+    def rec_gu(batch=None):
+        gu(batch)
+        rec['var_x'].append(hmm.var_x.copy())
+        rec['var_init'].append(hmm.var_init.copy())
+        rec['var_tran'].append(hmm.var_tran.copy())
+        rec['mu'].append(np.array([g.mu_mf for g in hmm.var_emit]))
+        rec['sigma'].append(np.array([g.sigma_mf for g in hmm.var_emit]))
+        rec['kappa'].append(np.array([g.kappa_mf for g in hmm.var_emit], dtype=float))
+        rec['nu'].append(np.array([g.nu_mf for g in hmm.var_emit], dtype=float))
+        rec['lrate'].append(hmm.lrate)
+
+    hmm.global_update = rec_gu
+    hmm.lower_bound = lambda: 0.0           # get_vlb needs the absent pymattutil
+    hmm.pred_logprob = lambda: None
+    hmm.infer()
+    for k, v in rec.items():
+        out["it_" + k] = np.array(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s batch SGD T=%d iters=%d frac(max q<0.99)=%.2f" % (
+        name, T, len(rec['lrate']), float(np.mean(out["it_var_x"].max(-1) < 0.99))))
+
+
 def ell_1d_case(name, seed):
     """Gaussian(D=1).expected_log_likelihood values: pins the diagonal-Gaussian
     extension (product of 1-D NIW factors) to distributions.py:351-366."""
@@ -215,5 +262,6 @@ if __name__ == "__main__":
     svi_case("svi_k16_d8_l50", seed=13, K=16, D=8, T_full=1500, L=50, mb_sz=3, sep=0.4, maxit=1)
     svi_case("svi_k2_d2_l1", seed=14, K=2, D=2, T_full=60, L=1, mb_sz=5, sep=0.8, maxit=3)
     cavi_case("cavi_k2_d2_t200", seed=21, T=200)
+    bsgd_case("bsgd_k3_d2_t150", seed=22, T=150)
     ell_1d_case("ell_1d", seed=31)
     gen_case("gen_synthetic_k4", seed=8675309)

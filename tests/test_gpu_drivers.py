@@ -91,6 +91,24 @@ def test_batch_cavi_class_matches_reference_golden():
     assert np.max(np.abs(hmm.var_x - g["it_var_x"][-1])) < 1e-6
 
 
+def test_hmmbatchsgd_class_matches_reference_golden():
+    """hmmbatchsgd.VBHMM.infer (hmmbatchsgd.py:143-259): batch natural gradient on the device."""
+    from pysvihmm_b200 import hmmbatchsgd as HBS
+    g = load_golden("bsgd_k3_d2_t150")
+    K = 3
+    hmm = HBS.VBHMM(g["obs"].copy(), g["prior_init"], g["prior_tran"], _emit_objs(g, K), tau=1., kappa=0.7,
+                    mask=g["mask"], init_tran=g["init_var_tran"].copy(), maxit=int(g["maxit"]))
+    hmm.lower_bound = lambda: 0.0
+    hmm.infer()
+    assert _rel(hmm.var_tran, g["it_var_tran"][-1]) < 2e-5
+    assert _rel(hmm.var_init, g["it_var_init"][-1]) < 2e-5
+    assert _rel(np.array([e.mu_mf for e in hmm.var_emit]), g["it_mu"][-1]) < 2e-5
+    assert _rel(np.array([e.sigma_mf for e in hmm.var_emit]), g["it_sigma"][-1]) < 2e-5
+    assert _rel(np.array([e.kappa_mf for e in hmm.var_emit]), g["it_kappa"][-1]) < 2e-5
+    assert _rel(np.array([e.nu_mf for e in hmm.var_emit]), g["it_nu"][-1]) < 2e-5
+    assert np.max(np.abs(hmm.var_x - g["it_var_x"][-1])) < 2e-6
+
+
 def test_full_local_update_masks_likelihood():
     """hmmsgd_metaobs.py:1147-1205: masked rows carry no evidence."""
     from oracle import svihmm_oracle as O

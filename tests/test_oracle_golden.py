@@ -82,6 +82,29 @@ def test_batch_cavi_matches_reference():
         var_init, var_tran, emit = r["var_init_new"], r["var_tran_new"], r["emit_new"]
 
 
+def test_batch_sgd_matches_reference():
+    """hmmbatchsgd.VBHMM.infer iterations (hmmbatchsgd.py:143-259)."""
+    g = load_golden("bsgd_k3_d2_t150")
+    K = 3
+    var_init, var_tran = g["init_var_init"], g["init_var_tran"]
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    prior_emit = golden_prior_emit(g, K)
+    for it in range(int(g["maxit"])):
+        lrate = (it + float(g["tau"])) ** (-float(g["kappa_lr"]))
+        assert np.isclose(lrate, g["it_lrate"][it])
+        r = O.batch_sgd_step(g["obs"], g["mask"], var_init, var_tran, emit, g["prior_init"],
+                             g["prior_tran"], prior_emit, lrate)
+        np.testing.assert_allclose(r["var_x"][0], g["it_var_x"][it], rtol=1e-9, atol=AT)
+        np.testing.assert_allclose(r["var_init_new"], g["it_var_init"][it], rtol=RT)
+        np.testing.assert_allclose(r["var_tran_new"], g["it_var_tran"][it], rtol=RT)
+        for k in range(K):
+            np.testing.assert_allclose(r["emit_new"][k]["mu"], g["it_mu"][it][k], rtol=1e-9, atol=AT)
+            np.testing.assert_allclose(r["emit_new"][k]["sigma"], g["it_sigma"][it][k], rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(r["emit_new"][k]["kappa"], g["it_kappa"][it][k], rtol=RT)
+            np.testing.assert_allclose(r["emit_new"][k]["nu"], g["it_nu"][it][k], rtol=RT)
+        var_init, var_tran, emit = r["var_init_new"], r["var_tran_new"], r["emit_new"]
+
+
 def test_diag_extension_pinned_to_1d_reference():
     g = load_golden("ell_1d")
     for i in range(6):
