@@ -309,14 +309,21 @@ def run_ours(args, cfg):
     stats_pin = torch.empty(eng.slen, dtype=torch.float64).pin_memory()
 
     def step_host(i, it):
-        eng.estep_host(starts_h[i], T, flags=flags, stats_out=stats_h)      # H2D windows, D2H stats, sync
-        if world > 1:
-            stats_pin.copy_(torch.from_numpy(stats_h))
-            stats_d.copy_(stats_pin, non_blocking=True)
-            allreduce_stats(stats_d, dist)
+        # the call a user makes per global step, HOST buffers in and out: this step's windows come from
+        # the host series (H2D inside the timed region; the NEXT step's windows are announced so that
+        # their gather overlaps this step's compute), the minibatch statistics are read back (D2H)
+        nxt = starts_h[i + 1] if i + 1 < nst else None
+        if i + 2 < nst:
+            eng.prefetch_windows(starts_h[i + 2], T)        # two minibatches ahead: the host link never idles
+        lr = (it + 1.) ** -0.7
+        if world == 1:
+            eng.svi_step_host(starts_h[i], T, lr, bA, bE, next_starts=nxt, flags=flags, stats_out=stats_h)
         else:
-            stats_d.copy_(torch.from_numpy(stats_h), non_blocking=False)
-        eng.global_update(stats_d, (it + 1.) ** -0.7, bA, bE)
+            eng.estep_streamed(starts_h[i], T, next_starts=nxt, flags=flags, stats=stats_d)
+            allreduce_stats(stats_d, dist)
+            eng.global_update(stats_d, lr, bA, bE)
+            stats_pin.copy_(stats_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     for i in range(args.warmup):
         step_host(i, i)
@@ -327,6 +334,14 @@ def run_ours(args, cfg):
     e1.record()
     sync()
     ms2 = e0.elapsed_time(e1)
+    # untimed repeat with per-phase events: where the end-to-end step spends its device time
+    eng.set_profiling(True)
+    eng.phase_ms()
+    for i in range(args.warmup, min(nst, args.warmup + 20)):
+        step_host(i, i)
+    sync()
+    phases2 = eng.phase_ms()
+    eng.set_profiling(False)
     tmax = torch.tensor([ms2], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -357,7 +372,11 @@ def run_ours(args, cfg):
                          "whole_step_achieved": step_ach, "whole_step_frac": step_ach / peak,
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}},
             "e2e": {"value": e2e, "unit": "E-steps/s", "ms_per_step": ms2 / args.steps,
-                    "h2d_bytes_per_step": B * T * D * 4 + B * 8, "d2h_bytes_per_step": eng.slen * 8},
+                    "h2d_bytes_per_step": B * T * D * 4 + B * 8, "d2h_bytes_per_step": eng.slen * 8,
+                    "phases_ms_per_call": {k: v[0] / max(v[1], 1) for k, v in phases2.items()},
+                    "call": "svihmm_svi_step_host (one C-ABI call per global step: host windows in, statistics "
+                            "out; the next step's windows are gathered over PCIe while this step computes)"
+                            if world == 1 else "svihmm_estep_streamed + NCCL all-reduce + svihmm_global_update + D2H"},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu:

@@ -115,6 +115,33 @@ int svihmm_estep(svihmm_ctx* ctx, const int64_t* starts, int B, int T, float* va
 int svihmm_estep_host(svihmm_ctx* ctx, const int64_t* starts_host, int B, int T,
                       float* var_x_host, double* stats_host, unsigned flags, void* stream);
 
+/* Streamed step for training loops over a HOST-resident series (svihmm_set_series_streamed).
+ * The sampler does not depend on the global parameters (hmmsgd_metaobs.py:396, metaobs_unif
+ * :210-227), so upcoming minibatches can be drawn early and their windows moved host->device
+ * while the current minibatch is being processed:
+ *   svihmm_prefetch_windows  enqueues, on an internal copy stream, the gather of the windows
+ *                            obs[starts[b] : starts[b]+T] into one of SVIHMM ring slots (3); no-op
+ *                            if that minibatch is already staged.  Never blocks on compute.
+ *   svihmm_estep_streamed    enqueues (no synchronisation) the E-step of a minibatch on `stream`:
+ *                            from its staged copy if (starts, B, T) match a prefetched minibatch,
+ *                            else after gathering it on `stream`.  Statistics stay in the caller's
+ *                            DEVICE buffer so that an all-reduce and svihmm_global_update can follow
+ *                            on the same stream.  next_starts_host != NULL is a convenience for
+ *                            svihmm_prefetch_windows(next_starts_host, B, T) after the launch.
+ *   var_x_dev : B*T*K float32 (device) or NULL;  stats_dev : svihmm_stats_len() doubles (device). */
+int svihmm_prefetch_windows(svihmm_ctx* ctx, const int64_t* starts_host, int B, int T);
+int svihmm_estep_streamed(svihmm_ctx* ctx, const int64_t* starts_host, int B, int T,
+                          const int64_t* next_starts_host, float* var_x_dev, double* stats_dev,
+                          unsigned flags, void* stream);
+
+/* One whole global step of hmmsgd_metaobs.VBHMM.infer (:396-439) for one process, HOST buffers in
+ * and out: svihmm_estep_streamed + svihmm_global_update on the device-resident statistics, with the
+ * minibatch statistics (local_lower_bound terms included) copied to stats_host beside the update;
+ * synchronises `stream` before returning. */
+int svihmm_svi_step_host(svihmm_ctx* ctx, const int64_t* starts_host, int B, int T,
+                         const int64_t* next_starts_host, double* stats_host, unsigned flags,
+                         double lrate, double bfact_A, double bfact_E, void* stream);
+
 /* Stochastic natural-gradient step on the resident globals from (all-reduced) statistics:
  * hmmsgd_metaobs.py:1010-1069 with util.py:28-60.  stats on device.
  *   var_tran <- (1-lrate)(var_tran-1) + lrate*bfact_A*A + 1

@@ -29,6 +29,9 @@ SYMBOLS = {
     "svihmm_get_globals": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_estep": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _vp]),
     "svihmm_estep_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _vp]),
+    "svihmm_prefetch_windows": (_i, [_vp, _vp, _i, _i]),
+    "svihmm_estep_streamed": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _u, _vp]),
+    "svihmm_svi_step_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _d, _d, _d, _vp]),
     "svihmm_global_update": (_i, [_vp, _vp, _d, _d, _d, _vp]),
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
     "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),

@@ -85,7 +85,7 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   if (K < 1 || D < 1) return fail(SVIHMM_EINVAL, "K (%d) and D (%d) must be >= 1", K, D);
   if (kind != SVIHMM_EMIT_NIW_FULL && kind != SVIHMM_EMIT_NIW_DIAG)
     return fail(SVIHMM_EINVAL, "unknown emission kind %d", kind);
-  if (K > 232) return fail(SVIHMM_EUNSUPPORTED, "K = %d > 232 needs the dense tensor-core path (not built yet)", K);
+  if (K > 1024) return fail(SVIHMM_EUNSUPPORTED, "K = %d > 1024 (one thread per state in the wide recursion kernels)", K);
   if (kind == SVIHMM_EMIT_NIW_FULL && D > 96) return fail(SVIHMM_EUNSUPPORTED, "full-covariance D = %d > 96", D);
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -113,6 +113,8 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   return SVIHMM_OK;
 }
 
+static void sg_teardown(svihmm_ctx* c);
+
 static void free_streamed(svihmm_ctx* c) {
   if (c->h_reg_obs) cudaHostUnregister((void*)c->hobs);
   if (c->h_reg_mask) cudaHostUnregister((void*)c->hmask);
@@ -123,6 +125,7 @@ static void free_streamed(svihmm_ctx* c) {
 extern "C" int svihmm_destroy(svihmm_ctx* c) {
   if (!c) return SVIHMM_OK;
   cudaSetDevice(c->device);
+  sg_teardown(c);
   free_streamed(c);
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
                   c->pi0, c->lu, c->rowsum, c->ckc, c->par2, c->ckp, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
@@ -497,16 +500,18 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     }
   } else {
     const int KT = (K + 31) / 32 * 32;
-    const size_t smem = ((size_t)K * K + 2 * KT + 64) * sizeof(float);
+    size_t smem = ((size_t)K * K + 2 * KT + 64) * sizeof(float);
+    const int p_smem = smem <= (size_t)c->max_smem_optin;
+    if (!p_smem) smem = (2 * (size_t)KT + 64) * sizeof(float);
     if (smem > 48 * 1024) {
       CU(cudaFuncSetAttribute(k_forward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(cudaFuncSetAttribute(k_backward_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     { PhaseTimer pt(c, PH_FORWARD, st);
-      k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
+      k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs, p_smem);
       c->launches++; }
     { PhaseTimer pt(c, PH_BACKWARD, st);
-      k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r);
+      k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r, p_smem);
       c->launches++; }
   }
   CU(cudaGetLastError());
@@ -580,26 +585,52 @@ extern "C" int svihmm_estep(svihmm_ctx* c, const int64_t* starts, int B, int T, 
 }
 
 // gather B windows of T rows (row = rowbytes) from a mapped host (or device) series into a dense
-// [B][T] staging buffer, 16 bytes per thread when alignment allows; also the mask bytes.
+// [B][T] staging buffer; also the mask bytes.  A FEW long-lived CTAs with several 16-byte loads in
+// flight per thread: reads of mapped host memory take microseconds each, and a wide grid of
+// short CTAs would hold the SMs' thread slots for that long and lock a concurrently running
+// E-step kernel out (measured: fused E-step 65 -> 157 us beside a 1024-CTA gather).
+#define GATHER_CTAS 8
+#define GATHER_UNROLL 8
+static int gather_ctas() {
+  static const int n = getenv("SVIHMM_GATHER_CTAS") ? std::max(1, atoi(getenv("SVIHMM_GATHER_CTAS"))) : GATHER_CTAS;
+  return n;
+}
 __global__ void __launch_bounds__(256)
 k_gather_windows(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const uint8_t* __restrict__ msrc,
                  const int64_t* __restrict__ starts, uint8_t* __restrict__ dst, uint8_t* __restrict__ mdst,
                  int64_t* __restrict__ dense_starts, int vec16) {
-  const int b = blockIdx.y;
-  const int64_t s0 = starts[b];
   const size_t wbytes = (size_t)T * rowbytes;
-  const uint8_t* sp = src + (size_t)s0 * rowbytes;
-  uint8_t* dp = dst + (size_t)b * wbytes;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   if (vec16) {
-    const int4* s4 = (const int4*)sp; int4* d4 = (int4*)dp;
-    for (size_t i = tid; i < wbytes / 16; i += nth) d4[i] = s4[i];
+    const size_t upw = wbytes / 16, total = upw * B;               // 16-byte units per window / in all
+    for (size_t i0 = tid; i0 < total; i0 += nth * GATHER_UNROLL) {
+      int4 v[GATHER_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GATHER_UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * nth;
+        if (i < total) {
+          const size_t b = i / upw, k = i - b * upw;
+          v[u] = *((const int4*)(src + (size_t)starts[b] * rowbytes) + k);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < GATHER_UNROLL; ++u) {
+        const size_t i = i0 + (size_t)u * nth;
+        if (i < total) ((int4*)dst)[i] = v[u];
+      }
+    }
   } else {
-    const uint32_t* s1 = (const uint32_t*)sp; uint32_t* d1 = (uint32_t*)dp;
-    for (size_t i = tid; i < wbytes / 4; i += nth) d1[i] = s1[i];
+    const size_t upw = wbytes / 4, total = upw * B;
+    for (size_t i = tid; i < total; i += nth) {
+      const size_t b = i / upw, k = i - b * upw;
+      ((uint32_t*)dst)[i] = *((const uint32_t*)(src + (size_t)starts[b] * rowbytes) + k);
+    }
   }
-  if (msrc) for (size_t i = tid; i < (size_t)T; i += nth) mdst[(size_t)b * T + i] = msrc[s0 + i];
-  if (tid == 0) dense_starts[b] = (int64_t)b * T;
+  if (msrc) {
+    const size_t total = (size_t)B * T;
+    for (size_t i = tid; i < total; i += nth) { const size_t b = i / T; mdst[i] = msrc[starts[b] + (i - b * T)]; }
+  }
+  for (size_t b = tid; b < (size_t)B; b += nth) dense_starts[b] = (int64_t)b * T;
 }
 
 extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int B, int T,
@@ -634,10 +665,8 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
     // GPU-side gather straight out of the page-locked host series
     CU(cudaMemcpyAsync(c->stage_src, starts_host, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
     const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
-    const size_t units = (size_t)T * rowbytes / (vec16 ? 16 : 4);
-    dim3 grid((unsigned)((units + 255) / 256 > 64 ? 64 : (units + 255) / 256), B);
     PhaseTimer pt(c, PH_GATHER, st);
-    k_gather_windows<<<grid, 256, 0, st>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
+    k_gather_windows<<<gather_ctas(), 256, 0, st>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
                                            has_mask ? c->hmask_dev : nullptr, c->stage_src,
                                            (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, vec16);
     LAUNCHED(c);
@@ -676,6 +705,184 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
   if (var_x_host)
     CU(cudaMemcpyAsync(var_x_host, c->hostq_ws, sizeof(float) * rows * c->K, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+// ---- streamed step: double-buffered window staging ------------------------------------------
+static int sg_setup(svihmm_ctx* c) {
+  if (c->sg_init) return SVIHMM_OK;
+  CU(cudaStreamCreateWithFlags(&c->cstream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking));
+  for (int i = 0; i < SVIHMM_NSLOT; ++i) {
+    CU(cudaEventCreateWithFlags(&c->ev_gathered[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_read, cudaEventDisableTiming));
+  CU(cudaMallocHost((void**)&c->pin_stats, sizeof(double) * c->slen));
+  c->sg_init = 1;
+  return SVIHMM_OK;
+}
+
+static void sg_teardown(svihmm_ctx* c) {
+  if (!c->sg_init) return;
+  cudaStreamSynchronize(c->cstream); cudaStreamSynchronize(c->dstream);
+  for (int i = 0; i < SVIHMM_NSLOT; ++i) {
+    if (c->sg_obs[i]) cudaFree(c->sg_obs[i]);
+    if (c->sg_mask[i]) cudaFree(c->sg_mask[i]);
+    if (c->sg_src[i]) cudaFree(c->sg_src[i]);
+    if (c->sg_dense[i]) cudaFree(c->sg_dense[i]);
+    if (c->sg_pin_starts[i]) cudaFreeHost(c->sg_pin_starts[i]);
+    cudaEventDestroy(c->ev_gathered[i]); cudaEventDestroy(c->ev_consumed[i]);
+  }
+  cudaEventDestroy(c->ev_stats); cudaEventDestroy(c->ev_read);
+  cudaFreeHost(c->pin_stats);
+  cudaStreamDestroy(c->cstream); cudaStreamDestroy(c->dstream);
+  c->sg_init = 0;
+}
+
+static int sg_reserve(svihmm_ctx* c, int s, int B, int T) {
+  const size_t rows = (size_t)B * T;
+  if (rows > c->sg_rows[s]) {
+    if (c->sg_obs[s]) CU(cudaFree(c->sg_obs[s]));
+    if (c->sg_mask[s]) CU(cudaFree(c->sg_mask[s]));
+    c->sg_obs[s] = nullptr; c->sg_mask[s] = nullptr; c->sg_rows[s] = 0;
+    CU(cudaMalloc(&c->sg_obs[s], rows * c->D * 8));
+    CU(cudaMalloc((void**)&c->sg_mask[s], rows));
+    c->sg_rows[s] = rows;
+  }
+  if ((size_t)B > c->sg_B[s]) {
+    if (c->sg_src[s]) CU(cudaFree(c->sg_src[s]));
+    if (c->sg_dense[s]) CU(cudaFree(c->sg_dense[s]));
+    if (c->sg_pin_starts[s]) CU(cudaFreeHost(c->sg_pin_starts[s]));
+    c->sg_src[s] = nullptr; c->sg_dense[s] = nullptr; c->sg_pin_starts[s] = nullptr; c->sg_B[s] = 0;
+    CU(dalloc(&c->sg_src[s], (size_t)B)); CU(dalloc(&c->sg_dense[s], (size_t)B));
+    CU(cudaMallocHost((void**)&c->sg_pin_starts[s], sizeof(int64_t) * B));
+    c->sg_B[s] = B;
+  }
+  return SVIHMM_OK;
+}
+
+// enqueue on q: windows starts_host[0..B) of the page-locked host series -> staging slot s
+static int sg_gather(svihmm_ctx* c, int s, const int64_t* starts_host, int B, int T, cudaStream_t q) {
+  const size_t rowbytes = (size_t)c->D * esize(c->h_dtype);
+  const bool has_mask = c->hmask != nullptr;
+  memcpy(c->sg_pin_starts[s], starts_host, sizeof(int64_t) * B);
+  PhaseTimer pt(c, PH_GATHER, q);
+  // the GPU gathers the windows itself out of the mapped host series (one small persistent kernel)
+  CU(cudaMemcpyAsync(c->sg_src[s], c->sg_pin_starts[s], sizeof(int64_t) * B, cudaMemcpyHostToDevice, q));
+  const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
+  k_gather_windows<<<gather_ctas(), 256, 0, q>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
+                                               has_mask ? c->hmask_dev : nullptr, c->sg_src[s],
+                                               (uint8_t*)c->sg_obs[s], c->sg_mask[s], c->sg_dense[s], vec16);
+  LAUNCHED(c);
+  c->sg_valid[s] = 1; c->sg_T[s] = T; c->sg_nB[s] = B;
+  return SVIHMM_OK;
+}
+
+static int check_windows(svihmm_ctx* c, const int64_t* starts_host, int B, int T) {
+  for (int b = 0; b < B; ++b)
+    if (starts_host[b] < 0 || starts_host[b] + T > c->hT_full)
+      return fail(SVIHMM_EINVAL, "window %d = [%lld, +%d) outside the series of length %lld", b,
+                  (long long)starts_host[b], T, (long long)c->hT_full);
+  return SVIHMM_OK;
+}
+
+static int sg_find(const svihmm_ctx* c, const int64_t* starts_host, int B, int T) {
+  for (int i = 0; i < SVIHMM_NSLOT; ++i)
+    if (c->sg_valid[i] && c->sg_T[i] == T && c->sg_nB[i] == B &&
+        memcmp(c->sg_pin_starts[i], starts_host, sizeof(int64_t) * B) == 0) return i;
+  return -1;
+}
+
+// replacement: the oldest slot whose minibatch has already been consumed (or that is empty), else
+// the oldest staged-but-unused one; never `keep` (the slot of the E-step being enqueued, or -1)
+static int sg_victim(const svihmm_ctx* c, int keep) {
+  int v = -1;
+  for (int pass = 0; pass < 2 && v < 0; ++pass)
+    for (int i = 0; i < SVIHMM_NSLOT; ++i) {
+      if (i == keep || (pass == 0 && c->sg_pending[i])) continue;
+      if (v < 0 || c->sg_age[i] < c->sg_age[v]) v = i;
+    }
+  return v;
+}
+
+static int sg_checks(svihmm_ctx* c, const int64_t* starts_host, int B, int T) {
+  if (!c || !starts_host) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (B < 1 || T < 1) return fail(SVIHMM_EINVAL, "B (%d) and T (%d) must be >= 1", B, T);
+  if (!c->hobs) return fail(SVIHMM_ESTATE, "svihmm_set_series_streamed has not been called");
+  if (!c->hobs_dev) return fail(SVIHMM_EUNSUPPORTED, "the host series could not be page-locked: use svihmm_estep_host");
+  return check_windows(c, starts_host, B, T);
+}
+
+// gather into slot s on stream q, ordered after the last E-step that read the slot
+static int sg_fill(svihmm_ctx* c, int s, const int64_t* starts_host, int B, int T, cudaStream_t q) {
+  int rc;
+  CU(cudaEventSynchronize(c->ev_gathered[s]));                  // pinned starts of this slot are free again
+  c->sg_valid[s] = 0;
+  if ((rc = sg_reserve(c, s, B, T))) return rc;
+  CU(cudaStreamWaitEvent(q, c->ev_consumed[s], 0));
+  if ((rc = sg_gather(c, s, starts_host, B, T, q))) return rc;
+  CU(cudaEventRecord(c->ev_gathered[s], q));
+  c->sg_age[s] = ++c->sg_clock;
+  c->sg_pending[s] = 1;
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_prefetch_windows(svihmm_ctx* c, const int64_t* starts_host, int B, int T) {
+  int rc = sg_checks(c, starts_host, B, T);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  if ((rc = sg_setup(c))) return rc;
+  if (sg_find(c, starts_host, B, T) >= 0) return SVIHMM_OK;      // already staged (or on its way)
+  return sg_fill(c, sg_victim(c, -1), starts_host, B, T, c->cstream);
+}
+
+extern "C" int svihmm_estep_streamed(svihmm_ctx* c, const int64_t* starts_host, int B, int T,
+                                     const int64_t* next_starts_host, float* var_x_dev,
+                                     double* stats_dev, unsigned flags, void* stream) {
+  int rc = check_estep_args(c, starts_host, B, T, stats_dev, flags);
+  if (rc) return rc;
+  if ((rc = sg_checks(c, starts_host, B, T))) return rc;
+  if (next_starts_host && (rc = check_windows(c, next_starts_host, B, T))) return rc;
+  CU(cudaSetDevice(c->device));
+  if ((rc = sg_setup(c))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int s = sg_find(c, starts_host, B, T);
+  if (s >= 0) {
+    CU(cudaStreamWaitEvent(st, c->ev_gathered[s], 0));          // prefetched on cstream
+  } else {
+    s = sg_victim(c, -1);
+    CU(cudaStreamWaitEvent(st, c->ev_gathered[s], 0));          // a prefetch into this slot may be in flight
+    if ((rc = sg_fill(c, s, starts_host, B, T, st))) return rc;
+  }
+  c->sg_age[s] = ++c->sg_clock;
+  c->sg_pending[s] = 0;
+  rc = estep_impl(c, c->sg_obs[s], c->h_dtype, c->hmask ? c->sg_mask[s] : nullptr, c->sg_dense[s], B, T,
+                  var_x_dev, stats_dev, flags, st);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev_consumed[s], st));
+  if (next_starts_host && sg_find(c, next_starts_host, B, T) < 0)
+    if ((rc = sg_fill(c, sg_victim(c, s), next_starts_host, B, T, c->cstream))) return rc;
+  return SVIHMM_OK;
+}
+
+extern "C" int svihmm_svi_step_host(svihmm_ctx* c, const int64_t* starts_host, int B, int T,
+                                    const int64_t* next_starts_host, double* stats_host, unsigned flags,
+                                    double lrate, double bA, double bE, void* stream) {
+  if (!c || !stats_host) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  int rc = svihmm_estep_streamed(c, starts_host, B, T, next_starts_host, nullptr, c->stage_stats, flags, stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaEventRecord(c->ev_stats, st));
+  CU(cudaStreamWaitEvent(c->dstream, c->ev_stats, 0));          // read the result back beside the update
+  CU(cudaMemcpyAsync(c->pin_stats, c->stage_stats, sizeof(double) * c->slen, cudaMemcpyDeviceToHost, c->dstream));
+  CU(cudaEventRecord(c->ev_read, c->dstream));
+  if ((rc = run_global(c, GM_SVI, c->stage_stats, lrate, bA, bE, st))) return rc;
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventSynchronize(c->ev_read));
+  memcpy(stats_host, c->pin_stats, sizeof(double) * c->slen);
   return SVIHMM_OK;
 }
 

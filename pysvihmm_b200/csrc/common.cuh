@@ -9,6 +9,7 @@
 #include "../../include/svihmm.h"
 
 #define SVIHMM_EPS 1e-9      /* hmmbase.py:30 / hmmsgd_metaobs.py:26 */
+#define SVIHMM_NSLOT 3
 #define SVIHMM_WEPS 1e-12    /* pybasicbayes/distributions.py:22     */
 
 struct svihmm_ctx {
@@ -34,6 +35,18 @@ struct svihmm_ctx {
   void* stage_obs; uint8_t* stage_mask; int64_t* stage_src; int64_t* stage_starts;
   double* stage_stats; size_t stage_rows, stage_B;
   void* pin_obs; uint8_t* pin_mask; size_t pin_rows;
+  // ring of staging slots for the streamed step (svihmm_prefetch_windows / svihmm_estep_streamed):
+  // a slot holds the gathered windows of one minibatch; upcoming minibatches are gathered on
+  // `cstream` (back to back, so the host link stays busy) while the current one is processed
+  void* sg_obs[SVIHMM_NSLOT]; uint8_t* sg_mask[SVIHMM_NSLOT]; int64_t* sg_src[SVIHMM_NSLOT]; int64_t* sg_dense[SVIHMM_NSLOT];
+  size_t sg_rows[SVIHMM_NSLOT], sg_B[SVIHMM_NSLOT];
+  int64_t* sg_pin_starts[SVIHMM_NSLOT];               // pinned copies of the window starts
+  cudaStream_t cstream, dstream;                      // gather / result read-back streams
+  cudaEvent_t ev_gathered[SVIHMM_NSLOT], ev_consumed[SVIHMM_NSLOT], ev_stats, ev_read;
+  int sg_valid[SVIHMM_NSLOT], sg_T[SVIHMM_NSLOT], sg_nB[SVIHMM_NSLOT], sg_init, sg_ring;
+  int64_t sg_age[SVIHMM_NSLOT], sg_clock;             // last use of each slot (LRU replacement)
+  int sg_pending[SVIHMM_NSLOT];                       // staged, not consumed by an E-step yet
+  double* pin_stats;
   // workspaces
   size_t cap_rows, cap_B, cap_part;
   double *ll_ws, *mx_ws, *seq_ws;

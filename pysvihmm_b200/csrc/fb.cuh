@@ -148,14 +148,16 @@ __device__ __forceinline__ void block_sum2(float& v1, float& v2, float* red, int
   v1 = s1; v2 = s2;
 }
 
-// dynamic smem: (K*K + 2*KT + 64) floats
+// dynamic smem: (K*K + 2*KT + 64) floats; with p_smem == 0 (K*K floats do not fit: K > 232) the
+// transition matrix is read through L1/L2 instead and the K*K floats are not allocated
 __global__ void k_forward_wide(int B, int T, int K, const float* __restrict__ Pt,
                                const float* __restrict__ pi0, const float* __restrict__ b,
-                               float* __restrict__ alpha, float* __restrict__ cs) {
+                               float* __restrict__ alpha, float* __restrict__ cs, int p_smem) {
   extern __shared__ float smf[];
   const int KT = blockDim.x, nw = KT >> 5, j = threadIdx.x, s = blockIdx.x;
-  float* Ps = smf; float* ab = Ps + K * K; float* red = ab + 2 * KT;
-  for (int idx = j; idx < K * K; idx += KT) Ps[idx] = Pt[idx];
+  float* ab = smf + (p_smem ? K * K : 0); float* red = ab + 2 * KT;
+  const float* Ps = p_smem ? smf : Pt;
+  if (p_smem) for (int idx = j; idx < K * K; idx += KT) smf[idx] = Pt[idx];
   const bool act = j < K;
   const size_t base = (size_t)s * T * K + (act ? j : 0);
   const float* bp = b + base; float* ap = alpha + base;
@@ -192,14 +194,15 @@ __global__ void k_forward_wide(int B, int T, int K, const float* __restrict__ Pt
   }
 }
 
-// dynamic smem: (K*K + 2*KT + 64) floats; PtT is the transposed transition matrix
+// dynamic smem as k_forward_wide; PtT is the transposed transition matrix
 __global__ void k_backward_wide(int B, int T, int K, const float* __restrict__ PtT,
                                 const float* __restrict__ b, const float* __restrict__ alpha,
-                                float* __restrict__ q, float* __restrict__ r_out) {
+                                float* __restrict__ q, float* __restrict__ r_out, int p_smem) {
   extern __shared__ float smf[];
   const int KT = blockDim.x, nw = KT >> 5, i = threadIdx.x, s = blockIdx.x;
-  float* PsT = smf; float* ub = PsT + K * K; float* red = ub + 2 * KT;
-  for (int idx = i; idx < K * K; idx += KT) PsT[idx] = PtT[idx];
+  float* ub = smf + (p_smem ? K * K : 0); float* red = ub + 2 * KT;
+  const float* PsT = p_smem ? smf : PtT;
+  if (p_smem) for (int idx = i; idx < K * K; idx += KT) smf[idx] = PtT[idx];
   const bool act = i < K;
   const size_t base = (size_t)s * T * K + (act ? i : 0);
   const float* bp = b + base; const float* ap = alpha + base;

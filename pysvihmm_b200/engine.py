@@ -174,6 +174,43 @@ class EStepEngine(object):
                                            int(flags), self._stream()))
         return vx, stats
 
+    def prefetch_windows(self, starts, T):
+        """Announce an upcoming minibatch: its windows start moving host->device on the engine's
+        copy stream now (ring of 3 staging slots); estep_streamed / svi_step_host with the same
+        starts later use the staged copy."""
+        starts = np.ascontiguousarray(np.asarray(starts, dtype=np.int64))
+        L.check(self.lib.svihmm_prefetch_windows(self._h, _ptr(starts), int(starts.size), int(T)))
+
+    def estep_streamed(self, starts, T, next_starts=None, flags=0, stats=None, var_x=None):
+        """Enqueue-only E-step over windows of the HOST-resident series (set_series_streamed):
+        the windows are gathered host->device on the current stream, or taken from the staging
+        buffer if `starts` was announced as `next_starts` of the previous call, in which case the
+        gather overlapped the previous step.  Statistics stay on the device (all-reduce /
+        global_update follow on the same stream).  Returns the stats tensor."""
+        starts = np.ascontiguousarray(np.asarray(starts, dtype=np.int64))
+        nxt = None if next_starts is None else np.ascontiguousarray(np.asarray(next_starts, dtype=np.int64))
+        if nxt is not None and nxt.size != starts.size:
+            raise ValueError("next_starts must have as many windows as starts")
+        if stats is None:
+            stats = self.new_stats()
+        L.check(self.lib.svihmm_estep_streamed(self._h, _ptr(starts), int(starts.size), int(T), _ptr(nxt),
+                                               _ptr(var_x), _ptr(stats), int(flags), self._stream()))
+        return stats
+
+    def svi_step_host(self, starts, T, lrate, bfact_A, bfact_E, next_starts=None, flags=0, stats_out=None):
+        """One global step of hmmsgd_metaobs.VBHMM.infer (:396-439) with HOST buffers: windows in
+        (gathered from the streamed host series), minibatch statistics out (numpy float64), the
+        natural-gradient update applied to the device-resident globals.  Synchronises."""
+        starts = np.ascontiguousarray(np.asarray(starts, dtype=np.int64))
+        nxt = None if next_starts is None else np.ascontiguousarray(np.asarray(next_starts, dtype=np.int64))
+        if nxt is not None and nxt.size != starts.size:
+            raise ValueError("next_starts must have as many windows as starts")
+        stats = np.empty(self.slen) if stats_out is None else stats_out
+        L.check(self.lib.svihmm_svi_step_host(self._h, _ptr(starts), int(starts.size), int(T), _ptr(nxt),
+                                              _ptr(stats), int(flags), float(lrate), float(bfact_A),
+                                              float(bfact_E), self._stream()))
+        return stats
+
     def global_update(self, stats, lrate, bfact_A, bfact_E):
         """hmmsgd_metaobs.py:1010-1069 on the device-resident globals."""
         L.check(self.lib.svihmm_global_update(self._h, _ptr(stats), float(lrate), float(bfact_A),

@@ -171,6 +171,8 @@ ORACLE_CASES = [
     (33, 4, 64, 5, "niw_full"),        # first wide size
     (64, 32, 257, 4, "niw_full"),      # BASELINE config 3 shape (reduced B, T)
     (100, 3, 50, 3, "niw_diag"),
+    (256, 64, 256, 2, "niw_full"),     # BASELINE config 4 shape (reduced B; float32 recursions, not bf16)
+    (300, 4, 40, 2, "niw_diag"),       # K*K floats exceed shared memory: transition matrix read through L2
     (32, 4, 100, 3, "niw_diag"),       # fused path, one chain per warp (KP = 32)
     (20, 3, 300, 4, "niw_full"),       # fused path, K not a power of two
     (4, 12, 40, 3, "niw_diag"),        # fused path, D > K: observation staging in several tiles
@@ -309,6 +311,57 @@ def test_host_call_equals_device_call():
         # statistics are accumulated over windows with float64 atomics: order-dependent last bits
         np.testing.assert_allclose(stats.cpu().numpy(), sh, rtol=1e-12, atol=1e-12)
         eng.close()
+
+
+def test_streamed_step_equals_device_step():
+    """svihmm_estep_streamed / svihmm_svi_step_host (host series, double-buffered window gather with
+    the next minibatch announced one step ahead) follow the same trajectory as svihmm_estep +
+    svihmm_global_update on the HBM-resident series, with and without prefetch hits."""
+    from pysvihmm_b200 import _lib as L
+    K, D, T, B, n = 8, 4, 64, 21, 6
+    p = make_random_problem(seed=11, K=K, D=D, T_full=4000, kind="niw_full", miss=0.05)
+    obs = p["obs"].astype(np.float32)
+    rs = np.random.RandomState(3)
+    starts = rs.randint(0, 4000 - T + 1, (n, B))
+    flags = L.WRAP | L.ADD_PRIOR
+
+    def fresh():
+        eng = _engine(K, D, "niw_full")
+        eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        return eng
+    ref = fresh(); ref.set_series(obs, p["mask"])
+    ref_stats = []
+    for i in range(n):
+        _, st = ref.estep(starts[i], T, flags=flags, want_var_x=False)
+        ref_stats.append(st.cpu().numpy())
+        ref.global_update(st, (i + 1.) ** -0.7, 2.0, 1.5)
+    ref_glob = ref.get_globals()
+    ref.close()
+    # (a) single-call host step; announce the next minibatch except at i == 2 (cold gather at i == 3)
+    # and announce a WRONG one at i == 3 (prefetched windows must not be used at i == 4)
+    eng = fresh(); eng.set_series_streamed(obs, p["mask"])
+    for i in range(n):
+        nxt = starts[i + 1] if i + 1 < n and i != 2 else None
+        if i == 3:
+            nxt = starts[0]
+        sh = eng.svi_step_host(starts[i], T, (i + 1.) ** -0.7, 2.0, 1.5, next_starts=nxt, flags=flags)
+        np.testing.assert_allclose(sh, ref_stats[i], rtol=1e-9, atol=1e-9)
+    for a, b in zip(eng.get_globals(), ref_glob):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    eng.close()
+    # (b) enqueue-only variant with the statistics left on the device
+    eng = fresh(); eng.set_series_streamed(obs, p["mask"])
+    st = eng.new_stats()
+    for i in range(n):
+        if i + 2 < n:
+            eng.prefetch_windows(starts[i + 2], T)          # two minibatches ahead (ring of 3 slots)
+        eng.estep_streamed(starts[i], T, next_starts=starts[i + 1] if i + 1 < n else None, flags=flags, stats=st)
+        np.testing.assert_allclose(st.cpu().numpy(), ref_stats[i], rtol=1e-9, atol=1e-9)
+        eng.global_update(st, (i + 1.) ** -0.7, 2.0, 1.5)
+    for a, b in zip(eng.get_globals(), ref_glob):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    eng.close()
 
 
 def test_error_paths():
