@@ -13,6 +13,7 @@
 #include "global.cuh"
 #include "fused.cuh"
 #include "fused_pipe.cuh"
+#include "wide64.cuh"
 
 static thread_local std::string g_err;
 
@@ -129,7 +130,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   free_streamed(c);
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
                   c->pi0, c->lu, c->rowsum, c->ckc, c->par2, c->ckp, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
-                  c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws,
+                  c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
@@ -297,11 +298,13 @@ extern "C" int svihmm_get_globals(svihmm_ctx* c, double* var_tran, double* var_i
 static int ensure_ws(svihmm_ctx* c, int B, int T, bool need_r) {
   const size_t rows = (size_t)B * T, K = c->K;
   if (rows > c->cap_rows) {
-    void* olds[] = {c->ll_ws, c->mx_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws};
+    void* olds[] = {c->ll_ws, c->mx_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->lt_ws, c->e_ws};
     for (void* p : olds) if (p) CU(cudaFree(p));
     c->ll_ws = nullptr; c->mx_ws = nullptr; c->b_ws = nullptr; c->alpha_ws = nullptr; c->q_ws = nullptr; c->r_ws = nullptr;
+    c->lt_ws = nullptr; c->e_ws = nullptr;
     c->cap_rows = 0;
     CU(dalloc(&c->ll_ws, rows * K)); CU(dalloc(&c->mx_ws, 2 * rows));
+    CU(dalloc(&c->lt_ws, rows)); CU(dalloc(&c->e_ws, rows));
     CU(dalloc(&c->b_ws, rows * K)); CU(dalloc(&c->alpha_ws, rows * K)); CU(dalloc(&c->q_ws, rows * K));
     c->cap_rows = rows;
   }
@@ -469,6 +472,17 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   const int mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
   // K1: expected log-likelihoods (fp64) -> scaled likelihoods b (fp32) + row maxima
   { PhaseTimer pt(c, PH_EMIT, st);
+  if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {
+    // register-blocked float64 kernel with the row maximum and b = exp(ll - max) fused in
+    const unsigned grid = (unsigned)((R + 2 * ERB_NT - 1) / (2 * ERB_NT));
+#define ERB_LAUNCH(DV) do { \
+      const size_t smem = (size_t)ERB_KC * (erb_len(DV) + DV + (DV & 1)) * sizeof(double); \
+      k_emit_full_rb<DV><<<grid, ERB_NT, smem, st>>>(R, T, K, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, \
+                                                     c->ck, c->ll_ws, c->b_ws, c->mx_ws); } while (0)
+    if (D == 8) ERB_LAUNCH(8); else if (D == 16) ERB_LAUNCH(16); else ERB_LAUNCH(32);
+#undef ERB_LAUNCH
+    LAUNCHED(c);
+  } else {
   if (c->kind == SVIHMM_EMIT_NIW_FULL) {
     const size_t smem = ((size_t)EMIT_ROWS * D + (size_t)D * (D + 1) / 2 + D) * sizeof(double);
     if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the emission kernel", D);
@@ -486,10 +500,50 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
   LAUNCHED(c);
   }
+  }
   // K2/K3: forward, backward + marginals
   float* q = var_x_out ? var_x_out : c->q_ws;
   float* r = xi ? c->r_ws : nullptr;
   float* cs = (float*)(c->mx_ws + (size_t)B * T);
+  if (K > 32 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64) {
+    // warp-per-chain recursions, marginals, symmetric register-blocked statistics (wide64.cuh)
+    if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
+    { PhaseTimer pt(c, PH_FORWARD, st);
+      k_chain_wide<<<(2 * B + 3) / 4, 128, 0, st>>>(B, T, K, c->Pt, c->PtT, c->pi0, c->b_ws, c->alpha_ws, c->r_ws, c->e_ws);
+      LAUNCHED(c); }
+    { PhaseTimer pt(c, PH_BACKWARD, st);
+      k_marginals_wide<<<148 * 8, 256, 0, st>>>(R, K, c->alpha_ws, c->r_ws, c->e_ws, q, c->lt_ws);
+      LAUNCHED(c);
+      k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
+      LAUNCHED(c); }
+    PhaseTimer pt_stats(c, PH_STATS, st);
+    StatsSymArgs sa;
+    sa.B = B; sa.T = T; sa.K = K; sa.D = D; sa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+    sa.NF = K + 1 + D + (sa.diag ? D : D * (D + 1) / 2);
+    sa.wrap = (flags & SVIHMM_WRAP) ? 1 : 0; sa.dtype = dtype; sa.R = R;
+    sa.q = q; sa.obs = obs; sa.mask = mask; sa.starts = starts;
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((R + 1023) / 1024, 4096));
+    const int64_t rps = (((R + nsplit - 1) / nsplit) + SS_RC - 1) / SS_RC * SS_RC;
+    nsplit = (R + rps - 1) / rps;
+    sa.rows_per_split = rps;
+    const size_t need_part = (size_t)nsplit * K * sa.NF;
+    if (need_part > c->cap_part) {
+      if (c->part_ws) CU(cudaFree(c->part_ws));
+      c->part_ws = nullptr; c->cap_part = 0;
+      CU(dalloc(&c->part_ws, need_part));
+      c->cap_part = need_part;
+    }
+    sa.part = c->part_ws;
+    dim3 grid((sa.NF + SS_TN - 1) / SS_TN, (unsigned)nsplit);
+    k_stats_sym<<<grid, SS_NT, 0, st>>>(sa);
+    LAUNCHED(c);
+    k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+        B, T, K, D, c->DD, sa.NF, sa.diag, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
+        (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+    LAUNCHED(c);
+    c->last_B = B; c->last_T = T; c->last_fused = 1;     // no lliks/alpha/cs tables in the classic form
+    return SVIHMM_OK;
+  }
   if (K <= 32) {
     switch (c->KP) {
       case 2: launch_fb<2>(c, B, T, q, r, st); break;

@@ -49,7 +49,8 @@ struct svihmm_ctx {
   double* pin_stats;
   // workspaces
   size_t cap_rows, cap_B, cap_part;
-  double *ll_ws, *mx_ws, *seq_ws;
+  double *ll_ws, *mx_ws, *seq_ws, *lt_ws;
+  int* e_ws;
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
   size_t hostq_cap;
   int last_B, last_T, last_fused;
