@@ -28,11 +28,15 @@
  *     SVIHMM_EMIT_NIW_FULL : [ mu (D) | sigma (D*D) | kappa | nu ]        Gaussian mu_mf,
  *                            sigma_mf, kappa_mf, nu_mf (pybasicbayes/distributions.py:195-212)
  *     SVIHMM_EMIT_NIW_DIAG : [ mu (D) | sigma (D) | kappa (D) | nu (D) ]  D independent 1-D NIWs
+ *     SVIHMM_EMIT_CATEGORICAL : [ alpha_mf (D) ]  Dirichlet over D symbols (Categorical,
+ *                            pybasicbayes/distributions.py:1273-1418); the series then has ONE
+ *                            column holding the symbol index 0..D-1 (NaN / out of range = missing)
  *   sufficient statistics, `svihmm_stats_len()` doubles:
  *     [ A (K*K) | n (K) | sx (K*D) | sxx (K*D*D, or K*D for DIAG) | q0 (K) | tail (4) ]
  *     A    = sum_b sum_t outer(q[t-1], q[t])         (hmmsgd_metaobs.py:876-878)
  *            (+ B*(prior_tran-1) with SVIHMM_ADD_PRIOR, quirk Q5, :876,881)
  *     n,sx,sxx = sum over unmasked rows of q[t,k]*[1, x, x x^T]   (util.py:73-83)
+ *            CATEGORICAL: sx[k][c] = sum_t q[t,k] 1[x_t = c] (hmmsgd_metaobs.py:907-926), no sxx
  *     q0   = sum_b q[b,0,:]                           (hmmbatchcd.py:179)
  *     tail = [ sum_b logZ_b, sum_b Q4_b (hmmsgd_metaobs.py:257-271), B, 0 ]
  */
@@ -50,7 +54,7 @@ typedef struct svihmm_ctx svihmm_ctx;
 
 enum { SVIHMM_OK = 0, SVIHMM_EINVAL = -1, SVIHMM_ECUDA = -2, SVIHMM_ENOMEM = -3, SVIHMM_ESTATE = -4,
        SVIHMM_EUNSUPPORTED = -5 };
-enum { SVIHMM_EMIT_NIW_FULL = 0, SVIHMM_EMIT_NIW_DIAG = 1 };
+enum { SVIHMM_EMIT_NIW_FULL = 0, SVIHMM_EMIT_NIW_DIAG = 1, SVIHMM_EMIT_CATEGORICAL = 2 };
 enum { SVIHMM_F32 = 0, SVIHMM_F64 = 1 };
 enum { SVIHMM_LOC_DEVICE = 0, SVIHMM_LOC_HOST = 1 };
 

@@ -90,6 +90,33 @@ def categorical_ell(x, alpha_mf):
     return digamma(alpha_mf[x]) - digamma(alpha_mf.sum())
 
 
+def lliks_categorical(xw, emit):
+    """hmmsgd_metaobs.py:508-509 with Categorical emissions (distributions.py:1383-1386).
+    xw: (B,T) symbols as floats (NaN = missing -> ll = 0, np.nan_to_num semantics);
+    emit: list of K dicts(alpha=(C,)) -> (B,T,K)."""
+    bad = np.isnan(xw)
+    sym = np.where(bad, 0, xw).astype(int)
+    ll = np.stack([categorical_ell(sym, e['alpha']) for e in emit], axis=-1)
+    ll[bad] = 0.
+    return ll
+
+
+def cat_suffstats(xw, w, C):
+    """Intended statistic of the (non-running) Categorical branch hmmsgd_metaobs.py:907-926:
+    weighted counts sum_t w_t 1[x_t = c]."""
+    out = np.zeros(C)
+    np.add.at(out, xw.astype(int), w)
+    return out
+
+
+def cat_global_update(alpha, alpha_prior, counts, n_windows, lrate, bfact):
+    """hmmsgd_metaobs.py:1071-1084 with emit_inter[k] = sum over the minibatch of
+    (alphav_0 + counts_window - 1) (:925-926): the prior enters once per window and is scaled
+    by bfact like the data (quirk Q5 for emissions)."""
+    emit_inter = n_windows * (alpha_prior - 1.) + counts
+    return (1. - lrate) * (alpha - 1.) + lrate * bfact * emit_inter + 1.
+
+
 def lliks_gaussian(xw, emit):
     """hmmsgd_metaobs.py:508-509: per state expected_log_likelihood, then
     np.nan_to_num (a NaN row gives ll = 0 = 'missing').
@@ -273,6 +300,9 @@ def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_e
         xw = xw.copy()
         xw[mw] = np.nan
     var_init = stationary_init(var_tran)
+    if 'alpha' in emit[0]:
+        return _svi_minibatch_step_cat(xw[..., 0], mw, var_init, var_tran, emit, prior_tran, prior_emit,
+                                       lrate, L, S, T_full, wrap)
     res = local_update(xw, var_init, var_tran, emit)
     A_inter = np.zeros_like(var_tran)
     emit_inter = None
@@ -294,6 +324,33 @@ def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_e
     res.update(A_inter=A_inter, emit_inter=emit_inter, lb=lb, logZ=log_Z(res['lalpha']),
                var_tran_new=var_tran_new, emit_new=emit_new, var_init=var_init)
     return res
+
+
+def _svi_minibatch_step_cat(xw, mw, var_init, var_tran, emit, prior_tran, prior_emit, lrate, L, S,
+                            T_full, wrap):
+    """Categorical-emission variant of svi_minibatch_step (xw: (B,T) symbols, NaN = missing)."""
+    mod_init, mod_tran = mod_params(var_init, var_tran)
+    ll = lliks_categorical(xw, emit)
+    lalpha = forward_msgs(ll, mod_init, mod_tran)
+    lbeta = backward_msgs(ll, mod_tran)
+    q = marginals(lalpha, lbeta)
+    B, T, K = q.shape
+    C = len(emit[0]['alpha'])
+    A_inter = np.zeros_like(var_tran)
+    counts = np.zeros((K, C))
+    for b in range(B):
+        A_inter += prior_tran + tran_stat(q[b][None], wrap)[0] - 1.
+        inds = np.logical_not(mw[b]) & ~np.isnan(xw[b])
+        for k in range(K):
+            counts[k] += cat_suffstats(xw[b][inds], q[b][inds, k], C)
+    bA = (T_full - 2 * L - 1) / (2. * L * S)
+    bE = (T_full - 2 * L - 1) / ((2. * L + 1.) * S)
+    var_tran_new = (1. - lrate) * (var_tran - 1.) + lrate * bA * A_inter + 1.
+    emit_new = [dict(alpha=cat_global_update(emit[k]['alpha'], prior_emit[k]['alpha'], counts[k], B,
+                                             lrate, bE)) for k in range(K)]
+    return dict(ll=ll, lalpha=lalpha, lbeta=lbeta, var_x=q, mod_init=mod_init, mod_tran=mod_tran,
+                A_inter=A_inter, counts=counts, lb=float(np.sum(local_lower_bound(lalpha))),
+                logZ=log_Z(lalpha), var_tran_new=var_tran_new, emit_new=emit_new, var_init=var_init)
 
 
 def _intermediate_pars_diag(var_x, xw, maskw, prior_tran, wrap):

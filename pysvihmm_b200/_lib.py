@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVIHMM_LIB", os.path.join(HERE, "lib", "libsvihmm.so"))   # override: A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-EMIT_NIW_FULL, EMIT_NIW_DIAG = 0, 1
+EMIT_NIW_FULL, EMIT_NIW_DIAG, EMIT_CATEGORICAL = 0, 1, 2
 F32, F64 = 0, 1
 LOC_DEVICE, LOC_HOST = 0, 1
 WRAP, ADD_PRIOR, MASK_LL, EXACT_XI, KEEP_LOCALS = 1, 2, 4, 8, 16

@@ -84,7 +84,7 @@ template <typename Tp> static cudaError_t dalloc(Tp** p, size_t n) {
 extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kind) {
   if (!out) return fail(SVIHMM_EINVAL, "out is NULL");
   if (K < 1 || D < 1) return fail(SVIHMM_EINVAL, "K (%d) and D (%d) must be >= 1", K, D);
-  if (kind != SVIHMM_EMIT_NIW_FULL && kind != SVIHMM_EMIT_NIW_DIAG)
+  if (kind != SVIHMM_EMIT_NIW_FULL && kind != SVIHMM_EMIT_NIW_DIAG && kind != SVIHMM_EMIT_CATEGORICAL)
     return fail(SVIHMM_EINVAL, "unknown emission kind %d", kind);
   if (K > 1024) return fail(SVIHMM_EUNSUPPORTED, "K = %d > 1024 (one thread per state in the wide recursion kernels)", K);
   if (kind == SVIHMM_EMIT_NIW_FULL && D > 96) return fail(SVIHMM_EUNSUPPORTED, "full-covariance D = %d > 96", D);
@@ -97,8 +97,10 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
-  c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : D;
-  c->plen = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)D + (size_t)D * D + 2 : (size_t)4 * D;
+  c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : (kind == SVIHMM_EMIT_NIW_DIAG ? D : 0);
+  c->OD = kind == SVIHMM_EMIT_CATEGORICAL ? 1 : D;
+  c->plen = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)D + (size_t)D * D + 2
+          : (kind == SVIHMM_EMIT_NIW_DIAG ? (size_t)4 * D : (size_t)D);
   c->nfeat = K + 1 + D + c->DD;
   c->slen = (size_t)K * K + K + (size_t)K * D + (size_t)K * c->DD + K + 4;
   const size_t KK = (size_t)K * K;
@@ -159,7 +161,7 @@ extern "C" int svihmm_set_series(svihmm_ctx* c, const void* obs, int64_t T_full,
   if (loc == SVIHMM_LOC_DEVICE) {
     c->obs = obs; c->mask = mask;
   } else {
-    const size_t nb = (size_t)T_full * c->D * esize(dtype);
+    const size_t nb = (size_t)T_full * c->OD * esize(dtype);
     CU(cudaMalloc(&c->obs_own, nb));
     CU(cudaMemcpyAsync(c->obs_own, obs, nb, cudaMemcpyHostToDevice, st));
     c->obs = c->obs_own; c->mask = nullptr;
@@ -183,7 +185,7 @@ extern "C" int svihmm_set_series_streamed(svihmm_ctx* c, const void* obs_host, i
   c->hobs = obs_host; c->hmask = mask_host; c->h_dtype = dtype; c->hT_full = T_full;
   // Page-lock + map the caller's buffer so the GPU gathers each step's windows itself.  If the
   // registration is refused (e.g. read-only mapping) the CPU-gather + pinned-staging path is used.
-  const size_t nb = (size_t)T_full * c->D * esize(dtype);
+  const size_t nb = (size_t)T_full * c->OD * esize(dtype);
   if (cudaHostRegister((void*)obs_host, nb, cudaHostRegisterMapped) == cudaSuccess) {
     c->h_reg_obs = 1;
     void* dp = nullptr;
@@ -233,7 +235,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
                       cudaStream_t st) {
   const int K = c->K, D = c->D;
   GlobalArgs ga;
-  ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.mode = mode;
+  ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; ga.mode = mode;
   ga.user_init = c->user_init; ga.plen = c->plen;
   ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
   ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
@@ -241,9 +243,9 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
   ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
   ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck; ga.par2 = c->par2; ga.ckp = c->ckp;
-  const int nblk = ga.diag ? std::max(1, std::min(K, (K * D + 255) / 256)) : K;
+  const int nblk = ga.diag ? std::max(1, std::min(K, (K * D + 255) / 256)) : K;   // full / categorical: one block per state
   size_t smem = (2 * (size_t)K + 2) * sizeof(double);
-  if (!ga.diag) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
+  if (!ga.diag && !ga.cat) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool gdbg = getenv("SVIHMM_GLOBAL_DBG") != nullptr;
   ga.dbg = nullptr;
@@ -358,7 +360,7 @@ static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st
 // kernel plus: every 4x4 statistics tile owned by one worker thread, barriers within the budget.
 static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
   static const bool off = getenv("SVIHMM_NO_PIPE") != nullptr;
-  if (off || c->K > 32 || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  if (off || c->K > 32 || c->kind == SVIHMM_EMIT_CATEGORICAL || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
   const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
   const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
   const PipeSmem L = pipe_smem_layout(T, c->K, c->D, tri, diag);
@@ -375,7 +377,7 @@ static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* sm
 // Single-kernel E-step (fused.cuh) when the window fits in shared memory: K <= 32, the three
 // T*K float tables + per-row scalars + emission constants <= the opt-in limit.
 static bool fused_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
-  if (c->K > 32 || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  if (c->K > 32 || c->kind == SVIHMM_EMIT_CATEGORICAL || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
   const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
   const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
   const FusedSmem L = fused_smem_layout(T, c->K, c->D, tri, diag);
@@ -482,6 +484,12 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     if (D == 8) ERB_LAUNCH(8); else if (D == 16) ERB_LAUNCH(16); else ERB_LAUNCH(32);
 #undef ERB_LAUNCH
     LAUNCHED(c);
+  } else if (c->kind == SVIHMM_EMIT_CATEGORICAL) {
+    k_emit_cat<<<(unsigned)((R * K + 255) / 256), 256, 0, st>>>(B, T, K, D, obs, dtype, mask, starts, mask_ll,
+                                                             c->Rs, c->ll_ws);
+    LAUNCHED(c);
+    k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
+    LAUNCHED(c);
   } else {
   if (c->kind == SVIHMM_EMIT_NIW_FULL) {
     const size_t smem = ((size_t)EMIT_ROWS * D + (size_t)D * (D + 1) / 2 + D) * sizeof(double);
@@ -505,7 +513,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   float* q = var_x_out ? var_x_out : c->q_ws;
   float* r = xi ? c->r_ws : nullptr;
   float* cs = (float*)(c->mx_ws + (size_t)B * T);
-  if (K > 32 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64) {
+  if (K > 32 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64 && c->kind != SVIHMM_EMIT_CATEGORICAL) {
     // warp-per-chain recursions, marginals, symmetric register-blocked statistics (wide64.cuh)
     if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
     { PhaseTimer pt(c, PH_FORWARD, st);
@@ -575,7 +583,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   // K4: statistics
   StatsArgs a;
   a.B = B; a.T = T; a.K = K; a.D = D; a.DD = c->DD; a.N = c->nfeat;
-  a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.R = R;
+  a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; a.R = R;
   a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
   const int TM = K <= 16 ? 16 : (K <= 32 ? 32 : 64);
   const int tiles_m = (K + TM - 1) / TM;
@@ -698,12 +706,12 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
                   (long long)starts_host[b], T, (long long)c->hT_full);
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t rows = (size_t)B * T, es = esize(c->h_dtype), rowbytes = (size_t)c->D * es;
+  const size_t rows = (size_t)B * T, es = esize(c->h_dtype), rowbytes = (size_t)c->OD * es;
   if (rows > c->stage_rows) {
     if (c->stage_obs) CU(cudaFree(c->stage_obs));
     if (c->stage_mask) CU(cudaFree(c->stage_mask));
     c->stage_obs = nullptr; c->stage_mask = nullptr; c->stage_rows = 0;
-    CU(cudaMalloc(&c->stage_obs, rows * c->D * 8));
+    CU(cudaMalloc(&c->stage_obs, rows * c->OD * 8));
     CU(cudaMalloc((void**)&c->stage_mask, rows));
     c->stage_rows = rows;
   }
@@ -730,7 +738,7 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
       if (c->pin_obs) CU(cudaFreeHost(c->pin_obs));
       if (c->pin_mask) CU(cudaFreeHost(c->pin_mask));
       c->pin_obs = nullptr; c->pin_mask = nullptr; c->pin_rows = 0;
-      CU(cudaMallocHost(&c->pin_obs, rows * c->D * 8 + sizeof(int64_t) * B));
+      CU(cudaMallocHost(&c->pin_obs, rows * c->OD * 8 + sizeof(int64_t) * B));
       CU(cudaMallocHost((void**)&c->pin_mask, rows));
       c->pin_rows = rows;
     }
@@ -740,7 +748,7 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
              (const uint8_t*)c->hobs + (size_t)starts_host[b] * rowbytes, (size_t)T * rowbytes);
       if (has_mask) memcpy(c->pin_mask + (size_t)b * T, c->hmask + starts_host[b], (size_t)T);
     }
-    int64_t* ds = (int64_t*)((uint8_t*)c->pin_obs + rows * c->D * 8);
+    int64_t* ds = (int64_t*)((uint8_t*)c->pin_obs + rows * c->OD * 8);
     for (int b = 0; b < B; ++b) ds[b] = (int64_t)b * T;
     CU(cudaMemcpyAsync(c->stage_obs, c->pin_obs, rows * rowbytes, cudaMemcpyHostToDevice, st));
     if (has_mask) CU(cudaMemcpyAsync(c->stage_mask, c->pin_mask, rows, cudaMemcpyHostToDevice, st));
@@ -801,7 +809,7 @@ static int sg_reserve(svihmm_ctx* c, int s, int B, int T) {
     if (c->sg_obs[s]) CU(cudaFree(c->sg_obs[s]));
     if (c->sg_mask[s]) CU(cudaFree(c->sg_mask[s]));
     c->sg_obs[s] = nullptr; c->sg_mask[s] = nullptr; c->sg_rows[s] = 0;
-    CU(cudaMalloc(&c->sg_obs[s], rows * c->D * 8));
+    CU(cudaMalloc(&c->sg_obs[s], rows * c->OD * 8));
     CU(cudaMalloc((void**)&c->sg_mask[s], rows));
     c->sg_rows[s] = rows;
   }
@@ -819,7 +827,7 @@ static int sg_reserve(svihmm_ctx* c, int s, int B, int T) {
 
 // enqueue on q: windows starts_host[0..B) of the page-locked host series -> staging slot s
 static int sg_gather(svihmm_ctx* c, int s, const int64_t* starts_host, int B, int T, cudaStream_t q) {
-  const size_t rowbytes = (size_t)c->D * esize(c->h_dtype);
+  const size_t rowbytes = (size_t)c->OD * esize(c->h_dtype);
   const bool has_mask = c->hmask != nullptr;
   memcpy(c->sg_pin_starts[s], starts_host, sizeof(int64_t) * B);
   PhaseTimer pt(c, PH_GATHER, q);

@@ -14,6 +14,7 @@
 
 struct svihmm_ctx {
   int device, K, D, kind, KP;
+  int OD;         // columns of the observation series: D, or 1 for categorical symbols
   size_t plen;    // doubles per state in the packed emission parameters
   size_t slen;    // doubles in the packed statistics
   int nfeat;      // columns of the statistics contraction: K + 1 + D + DD

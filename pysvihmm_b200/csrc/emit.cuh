@@ -88,6 +88,24 @@ k_emit_diag(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
   ll[e] = dead ? 0.0 : ck[k] - acc;
 }
 
+// Categorical emissions (pybasicbayes/distributions.py:1383-1386): ll[r][k] = logp[k][x_r] with the
+// table logp[k][c] = psi(alpha_mf[k][c]) - psi(sum_c alpha_mf[k][c]) prepared by the global step.
+// One thread per (row, state).  A NaN, masked (with mask_ll) or out-of-range symbol gives ll = 0.
+__global__ void __launch_bounds__(256)
+k_emit_cat(int B, int T, int K, int C, const void* __restrict__ obs, int dtype,
+           const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+           const double* __restrict__ logp, double* __restrict__ ll) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t R = (int64_t)B * T;
+  if (e >= R * K) return;
+  const int64_t r = e / K; const int k = (int)(e - r * K);
+  const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+  const int64_t gi = starts[b] + t;
+  const double x = ld_obs(obs, dtype, gi);
+  const bool dead = (mask_ll && mask && mask[gi]) || isnan(x) || x < 0.0 || x >= (double)C;
+  ll[e] = dead ? 0.0 : logp[(size_t)k * C + (int)x];
+}
+
 // b[r][k] = exp(ll[r][k] - max_k ll[r][k]) (fp32), mx[r] = the max (fp64).
 // One warp per row, lanes stride over k.
 __global__ void __launch_bounds__(256)

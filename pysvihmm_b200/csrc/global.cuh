@@ -15,7 +15,7 @@
 enum { GM_PREP = 0, GM_SVI = 1, GM_BATCH = 2, GM_BSGD = 3 };   // BSGD: hmmbatchsgd.py:202-259 (SVI blend + explicit var_init)
 
 struct GlobalArgs {
-  int K, D, DD, diag, mode, user_init;
+  int K, D, DD, diag, cat, mode, user_init;
   size_t plen;
   double *W, *vinit, *emit;                 // vinit: [0,K) the vector in use, [K,2K) the user-given one
   const double *prior_tran, *prior_init, *prior_emit, *stats;
@@ -394,10 +394,49 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
   }
 }
 
+// categorical (Dirichlet over D symbols per state): one block per state.  sm: 1 double.
+//   SVI   hmmsgd_metaobs.py:1071-1084 with emit_inter = sum over the minibatch's windows of
+//         (alphav_0 + counts - 1) (:925-926): alpha <- (1-rho)(alpha-1) + rho bE (B (alpha0-1) + counts) + 1
+//   BATCH alpha = alphav_0 + counts (Categorical.meanfieldupdate, distributions.py:1366-1370)
+//   BSGD  alpha <- (1-rho)(alpha-1) + rho (alphav_0 + counts - 1) + 1 (hmmbatchsgd.py:202-259 pattern)
+// then logp[k][c] = psi(alpha[c]) - psi(sum_c alpha[c]) (distributions.py:1383-1386) into Rs.
+__device__ void global_emit_cat_block(const GlobalArgs& a, const int k, double* sm) {
+  const int K = a.K, C = a.D, tid = threadIdx.x, nth = blockDim.x;
+  const GStats sv = gstats(a.stats, K, C, 0);
+  double* p = a.emit + (size_t)k * C;
+  const double* pr = a.prior_emit + (size_t)k * C;
+  if (a.mode != GM_PREP) {
+    const double nwin = a.mode == GM_SVI ? sv.q0[K + 2] : 1.0;       // statistics tail [.., .., B, ..]
+#pragma unroll 1
+    for (int c = tid; c < C; c += nth) {
+      const double cnt = sv.sx[(size_t)k * C + c];
+      double v;
+      if (a.mode == GM_SVI) v = (1.0 - a.lrate) * (p[c] - 1.0) + a.lrate * a.bE * (nwin * (pr[c] - 1.0) + cnt) + 1.0;
+      else if (a.mode == GM_BSGD) v = (1.0 - a.lrate) * (p[c] - 1.0) + a.lrate * (pr[c] + cnt - 1.0) + 1.0;
+      else v = pr[c] + cnt;
+      p[c] = v;
+    }
+    __syncthreads();
+  }
+  if (tid < 32) {
+    double s = 0.0;
+#pragma unroll 1
+    for (int c = tid; c < C; c += 32) s += p[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (tid == 0) sm[0] = digamma_d(s);
+  }
+  __syncthreads();
+  const double dgs = sm[0];
+#pragma unroll 1
+  for (int c = tid; c < C; c += nth) a.Rs[(size_t)k * C + c] = digamma_d(p[c]) - dgs;
+}
+
 // grid: 1 + (diag ? nblk_diag : K) blocks.
 __global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a, const int nblk_emit) {
   extern __shared__ double gsm[];
   if (blockIdx.x == 0) global_tran_block(a, gsm);
+  else if (a.cat) global_emit_cat_block(a, blockIdx.x - 1, gsm);
   else if (a.diag) {
     if (a.dbg && threadIdx.x == 0) a.dbg[4] = clock64();
     global_emit_diag_block(a, blockIdx.x - 1, nblk_emit);

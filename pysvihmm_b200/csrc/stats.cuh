@@ -16,7 +16,7 @@
 #define ST_RC 32
 
 struct StatsArgs {
-  int B, T, K, D, DD, N, n_lo, n_hi, diag, wrap;
+  int B, T, K, D, DD, N, n_lo, n_hi, diag, wrap, cat;
   int64_t R, rows_per_split;
   const float* left; const float* next;
   const void* obs; int dtype; const uint8_t* mask; const int64_t* starts;
@@ -49,7 +49,17 @@ __global__ void __launch_bounds__(256) k_stats(const StatsArgs a) {
       const int64_t r = rc + rr;
       Ls[rr][m] = (r < rend && m0 + m < K) ? a.left[r * K + m0 + m] : 0.f;
     }
-    if (need_x) {
+    if (need_x && a.cat) {                     // one symbol per row
+      for (int rr = tid; rr < ST_RC; rr += 256) {
+        const int64_t r = rc + rr;
+        float v = 0.f;
+        if (r < rend) {
+          const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+          v = (float)ld_obs(a.obs, a.dtype, a.starts[b] + t);
+        }
+        xs[rr] = v;
+      }
+    } else if (need_x) {
       for (int idx = tid; idx < ST_RC * D; idx += 256) {
         const int rr = idx / D, d = idx - rr * D;
         const int64_t r = rc + rr;
@@ -68,7 +78,10 @@ __global__ void __launch_bounds__(256) k_stats(const StatsArgs a) {
       if (r < rend) {
         const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
         w = (a.mask && a.mask[a.starts[b] + t]) ? 0.f : 1.f;
-        if (need_x) {
+        if (need_x && a.cat) {
+          const float x = xs[tid];
+          if (isnan(x) || x < 0.f || x >= (float)D) { w = 0.f; xs[tid] = -1.f; }
+        } else if (need_x) {
           bool bad = false;
           for (int d = 0; d < D; ++d) bad |= isnan(xs[tid * D + d]);
           if (bad || w == 0.f) { w = 0.f; for (int d = 0; d < D; ++d) xs[tid * D + d] = 0.f; }
@@ -90,6 +103,8 @@ __global__ void __launch_bounds__(256) k_stats(const StatsArgs a) {
           if (valid) val = a.next[((int64_t)b * T + t) * K + n];
         } else if (n == K) {
           val = wv[rr];
+        } else if (a.cat) {
+          val = (wv[rr] != 0.f && (int)xs[rr] == n - K - 1) ? 1.f : 0.f;     // w * 1[x = c]
         } else if (n < K + 1 + D) {
           val = wv[rr] * xs[rr * D + (n - K - 1)];
         } else {

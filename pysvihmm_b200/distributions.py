@@ -130,6 +130,68 @@ class DiagonalGaussian(Gaussian):
         return tot
 
 
+class Categorical(object):
+    """Categorical over symbols 0..C-1 with a Dirichlet mean-field posterior
+    (pybasicbayes/distributions.py:1273-1418): the attribute surface the HMM drivers touch
+    (alphav_0, _alpha_mf, weights, num_parameters, expected_log_likelihood, meanfieldupdate, get_vlb).
+    Data are symbol indices, not indicator vectors (:1276-1283)."""
+    kind = "categorical"
+
+    def __init__(self, weights=None, alpha_0=None, K=None, alphav_0=None, alpha_mf=None):
+        self.K = K
+        self.alphav_0 = None if alphav_0 is None else np.asarray(alphav_0, dtype=np.float64)
+        if self.alphav_0 is None and alpha_0 is not None and K is not None:
+            self.alphav_0 = np.repeat(float(alpha_0) / K, K)              # :1308-1311
+        if self.alphav_0 is not None:
+            self.K = len(self.alphav_0)
+        self.alpha_0 = alpha_0
+        self._alpha_mf = np.asarray(alpha_mf, dtype=np.float64) if alpha_mf is not None else (
+            np.asarray(weights, dtype=np.float64) * self.K if weights is not None else None)   # :1298
+        self.weights = weights
+        if weights is None and self.alphav_0 is not None:
+            self.resample()                                               # :1302-1303
+
+    @property
+    def alpha_mf(self):
+        return self._alpha_mf
+
+    def num_parameters(self):
+        return self.K
+
+    def resample(self, data=[]):
+        """Initialise from the Dirichlet prior (:1335-1340, no data)."""
+        self.weights = np.random.dirichlet(self.alphav_0)
+        if self._alpha_mf is None:
+            self._alpha_mf = self.weights * self.alphav_0.sum()
+        return self
+
+    def rvs(self, size=None):
+        return np.random.choice(self.K, size=size, p=self.weights)
+
+    def expected_log_likelihood(self, x=None):
+        """distributions.py:1383-1386, evaluated by the CUDA emission kernel (no CPU path)."""
+        from .engine import EStepEngine
+        x = np.arange(self.K) if x is None else np.asarray(x)
+        xs = np.ascontiguousarray(x.reshape(-1, 1).astype(np.float64))
+        eng = EStepEngine(1, self.K, self.kind)
+        try:
+            eng.set_series(xs)
+            eng.set_globals(np.ones((1, 1)), self._alpha_mf[None])
+            eng.estep([0], xs.shape[0], want_var_x=False, keep_locals=True)
+            return eng.get_locals(1, xs.shape[0])["lliks"][0, :, 0].reshape(x.shape)
+        finally:
+            eng.close()
+
+    def get_vlb(self):
+        """distributions.py:1372-1381 (host: ELBO diagnostic)."""
+        logpitilde = special.digamma(self._alpha_mf) - special.digamma(self._alpha_mf.sum())
+        q_entropy = -1 * ((logpitilde * (self._alpha_mf - 1)).sum()
+                          + special.gammaln(self._alpha_mf.sum()) - special.gammaln(self._alpha_mf).sum())
+        p_avgengy = special.gammaln(self.alphav_0.sum()) - special.gammaln(self.alphav_0).sum() \
+            + ((self.alphav_0 - 1) * logpitilde).sum()
+        return p_avgengy + q_entropy
+
+
 def _iw_logpartition(sigma, nu):
     D = sigma.shape[0]
     chol = np.linalg.cholesky(sigma)

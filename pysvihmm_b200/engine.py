@@ -10,7 +10,7 @@ import torch
 
 from . import _lib as L
 
-_KINDS = {"niw_full": L.EMIT_NIW_FULL, "niw_diag": L.EMIT_NIW_DIAG}
+_KINDS = {"niw_full": L.EMIT_NIW_FULL, "niw_diag": L.EMIT_NIW_DIAG, "categorical": L.EMIT_CATEGORICAL}
 
 
 def _ptr(t):
@@ -32,6 +32,9 @@ def pack_emit_dicts(emit):
     (sigma 2-D = full NIW, 1-D = diagonal)."""
     rows = []
     for e in emit:
+        if "alpha" in e:                     # categorical: Dirichlet parameters
+            rows.append(np.asarray(e["alpha"], dtype=np.float64).ravel())
+            continue
         mu = np.asarray(e["mu"], dtype=np.float64).ravel()
         D = mu.size
         sg = np.asarray(e["sigma"], dtype=np.float64)
@@ -64,7 +67,8 @@ class EStepEngine(object):
         self._h = h
         self.plen = int(self.lib.svihmm_emit_param_len(h))
         self.slen = int(self.lib.svihmm_stats_len(h))
-        self.DD = self.D * self.D if emission == "niw_full" else self.D
+        self.DD = {"niw_full": self.D * self.D, "niw_diag": self.D, "categorical": 0}[emission]
+        self.OD = 1 if emission == "categorical" else self.D     # columns of the observation series
         self._keep = {}          # borrowed tensors / host arrays the C side points into
         self.T_full = None
 
@@ -94,8 +98,8 @@ class EStepEngine(object):
         if obs.dtype not in (torch.float32, torch.float64):
             obs = obs.to(torch.float64)
         obs = obs.to(self.device).contiguous().reshape(obs.shape[0], -1)
-        if obs.shape[1] != self.D:
-            raise ValueError("obs has D=%d, engine D=%d" % (obs.shape[1], self.D))
+        if obs.shape[1] != self.OD:
+            raise ValueError("obs has %d columns, engine expects %d" % (obs.shape[1], self.OD))
         m = None
         if mask is not None:
             m = torch.as_tensor(np.asarray(mask, dtype=np.uint8) if not isinstance(mask, torch.Tensor)
@@ -261,7 +265,7 @@ class EStepEngine(object):
         out["A"] = s[o:o + K * K].reshape(K, K); o += K * K
         out["n"] = s[o:o + K]; o += K
         out["sx"] = s[o:o + K * D].reshape(K, D); o += K * D
-        out["sxx"] = s[o:o + K * DD].reshape((K, D, D) if self.emission == "niw_full" else (K, D)); o += K * DD
+        out["sxx"] = s[o:o + K * DD].reshape({"niw_full": (K, D, D), "niw_diag": (K, D), "categorical": (K, 0)}[self.emission]); o += K * DD
         out["q0"] = s[o:o + K]; o += K
         out["logZ"], out["lb_q4"], out["B"] = float(s[o]), float(s[o + 1]), int(round(s[o + 2]))
         return out
@@ -269,6 +273,8 @@ class EStepEngine(object):
     def pack_emit(self, mu, sigma, kappa, nu):
         """(K,D), (K,D,D)|(K,D), (K,)|(K,D), (K,)|(K,D) -> (K, plen) float64."""
         K, D = self.K, self.D
+        if self.emission == "categorical":              # mu = alpha_mf (K, C); the rest is ignored
+            return _f64(mu).reshape(K, D).copy()
         out = np.empty((K, self.plen))
         mu = _f64(mu).reshape(K, D)
         if self.emission == "niw_full":
@@ -286,6 +292,8 @@ class EStepEngine(object):
     def unpack_emit(self, em):
         K, D = self.K, self.D
         em = np.asarray(em).reshape(K, self.plen)
+        if self.emission == "categorical":
+            return dict(alpha=em.copy())
         if self.emission == "niw_full":
             return dict(mu=em[:, :D].copy(), sigma=em[:, D:D + D * D].reshape(K, D, D).copy(),
                         kappa=em[:, D + D * D].copy(), nu=em[:, D + D * D + 1].copy())

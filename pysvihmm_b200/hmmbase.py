@@ -90,6 +90,14 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
 
     def _ensure_engine(self):
         from .engine import EStepEngine
+        cat = self.emission_kind == "categorical"
+        if self._engine is None and cat:
+            C = int(self.prior_emit[0].num_parameters())
+            self._engine = EStepEngine(self.K, C, "categorical", device=self._device)
+            self._engine.set_prior(self.prior_tran, np.array([np.asarray(g.alphav_0, dtype=float)
+                                                              for g in self.prior_emit]), self.prior_init)
+            self._series_dirty = True
+            self._globals_dirty = True
         if self._engine is None:
             self._engine = EStepEngine(self.K, self.D, self.emission_kind, device=self._device)
             pe = self.prior_emit
@@ -102,9 +110,13 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
             self._series_dirty = True
             self._globals_dirty = True
         if self._series_dirty:
-            obs = np.asarray(self.obs, dtype=np.float64).reshape(self.T, self.D)
+            obs = np.asarray(self.obs, dtype=np.float64).reshape(self.T, -1)
             self._engine.set_series(obs, self.mask, dtype=self.obs_dtype)
             self._series_dirty = False
+        if self._globals_dirty and cat:
+            em = np.array([np.asarray(g._alpha_mf, dtype=float) for g in self.var_emit])
+            self._engine.set_globals(self.var_tran, em, self.var_init if self._explicit_init else None)
+            self._globals_dirty = False
         if self._globals_dirty:
             ve = self.var_emit
             em = self._engine.pack_emit(
@@ -126,6 +138,12 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
         vt, vi, em = self._engine.get_globals()
         self.var_tran, self.var_init = vt, vi
         e = self._engine.unpack_emit(em)
+        if self.emission_kind == "categorical":
+            for k, G in enumerate(self.var_emit):                 # hmmsgd_metaobs.py:1083-1084
+                G._alpha_mf = e["alpha"][k]
+                G.weights = G._alpha_mf / G._alpha_mf.sum()
+            self._host_stale = False
+            return
         full = self.emission_kind == "niw_full"
         for k, G in enumerate(self.var_emit):
             G.mu_mf, G.sigma_mf = e["mu"][k], e["sigma"][k]

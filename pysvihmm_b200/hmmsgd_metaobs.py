@@ -215,6 +215,9 @@ class VBHMM(VariationalHMMBase):
     def intermediate_pars(self, metaobs=None):
         """hmmsgd_metaobs.py:857-928: (A_inter, emit_inter) of the last local_update."""
         s = self._last_stats_host
+        if self.emission_kind == "categorical":         # :907-926: alpha posterior - 1 per window
+            emit_inter = [np.asarray(self.prior_emit[k].alphav_0) + s["sx"][k] - 1. for k in range(self.K)]
+            return s["A"], emit_inter
         emit_inter = [[s["sx"][k], s["n"][k], s["sxx"][k], s["n"][k]] for k in range(self.K)]
         return s["A"], emit_inter
 

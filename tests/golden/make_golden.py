@@ -27,7 +27,7 @@ import hmmsgd_metaobs as HSGD          # noqa: E402
 import hmmbatchcd as HCD               # noqa: E402
 import hmmbatchsgd as HBS              # noqa: E402
 import gen_synthetic as GS             # noqa: E402
-from pybasicbayes.distributions import Gaussian   # noqa: E402
+from pybasicbayes.distributions import Categorical, Gaussian   # noqa: E402
 
 
 def make_problem(seed, K, D, T_full, sep, miss=0.0):
@@ -239,6 +239,35 @@ def ell_1d_case(name, seed):
     print("%-22s 1-D ELL table 6x50" % name)
 
 
+def cat_case(name, seed):
+    """Categorical.expected_log_likelihood (distributions.py:1383-1386) and the global
+    natural-gradient step of the Categorical branch (hmmsgd_metaobs.py:1071-1084, run
+    literally on reference objects).  The reference's Categorical branch of intermediate_pars
+    (:907-926) does not run (its fancy indexing raises), so the statistic itself is unpinned."""
+    rs = np.random.RandomState(seed)
+    K, C = 5, 7
+    alpha = 0.3 + 3 * rs.rand(K, C)
+    x = rs.randint(0, C, 80)
+    ell = np.empty((K, 80))
+    objs = []
+    for k in range(K):
+        g = Categorical(weights=np.ones(C) / C, alphav_0=np.ones(C) * 0.5, alpha_mf=alpha[k].copy())
+        g._alpha_mf = alpha[k].copy()
+        ell[k] = g.expected_log_likelihood(x)
+        objs.append(g)
+    emit_inter = rs.rand(K, C) * 20
+    lrate, bfact = 0.37, 2.5
+    new = np.empty((K, C))
+    for k in range(K):                      # hmmsgd_metaobs.py:1071-1084 verbatim
+        G = objs[k]
+        nats_old = G._alpha_mf - 1.
+        nats_new = (1. - lrate) * nats_old + lrate * bfact * emit_inter[k]
+        new[k] = nats_new + 1.
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), alpha=alpha, x=x, ell=ell,
+                        emit_inter=emit_inter, lrate=lrate, bfact=bfact, alpha_new=new)
+    print("%-22s categorical ELL table %dx80" % (name, K))
+
+
 def gen_case(name, seed):
     """gen_synthetic.generate_data (gen_synthetic.py:8-56) under the legacy global RNG."""
     K, D, T = 4, 3, 400
@@ -264,4 +293,5 @@ if __name__ == "__main__":
     cavi_case("cavi_k2_d2_t200", seed=21, T=200)
     bsgd_case("bsgd_k3_d2_t150", seed=22, T=150)
     ell_1d_case("ell_1d", seed=31)
+    cat_case("cat_ell", seed=32)
     gen_case("gen_synthetic_k4", seed=8675309)

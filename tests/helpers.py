@@ -32,6 +32,9 @@ def pack_emit_np(emit):
     """list of dict(mu, sigma, kappa, nu) -> (K, plen) float64 in the layout of include/svihmm.h."""
     rows = []
     for e in emit:
+        if "alpha" in e:
+            rows.append(np.asarray(e["alpha"], dtype=np.float64).ravel())
+            continue
         mu = np.asarray(e["mu"], dtype=np.float64).ravel()
         D = mu.size
         sg = np.asarray(e["sigma"], dtype=np.float64)
@@ -72,5 +75,26 @@ def make_random_problem(seed, K, D, T_full, kind="niw_full", miss=0.0, sep=0.4):
             emit.append(dict(mu=mu, sigma=(nu - 2) * (1. + 0.3 * rs.rand(D)), kappa=0.7 + rs.rand(D), nu=nu))
             prior_emit.append(dict(mu=np.zeros(D), sigma=0.75 * np.ones(D), kappa=0.01 * np.ones(D),
                                    nu=3. * np.ones(D)))
+    return dict(obs=obs, sts=sts, mask=mask, var_tran=1. + 5. * rs.rand(K, K), emit=emit,
+                prior_tran=np.ones((K, K)), prior_emit=prior_emit)
+
+
+def make_categorical_problem(seed, K, C, T_full, miss=0.0):
+    """Seeded categorical-emission problem with overlapping symbol distributions."""
+    rs = np.random.RandomState(seed)
+    tran = 0.9 * np.eye(K) + 0.1 / max(K - 1, 1) * (1 - np.eye(K))
+    pmf = rs.dirichlet(2. * np.ones(C), K)
+    sts = np.empty(T_full, dtype=np.int64)
+    st = 0
+    u = rs.rand(T_full)
+    cdf = np.cumsum(tran, axis=1)
+    for t in range(T_full):
+        sts[t] = st
+        st = min(int(np.searchsorted(cdf[st], u[t])), K - 1)
+    cum = np.cumsum(pmf, axis=1)
+    obs = np.minimum((rs.rand(T_full)[:, None] > cum[sts]).sum(1), C - 1).astype(np.float64)[:, None]
+    mask = rs.rand(T_full) < miss
+    emit = [dict(alpha=0.5 + 20. * pmf[k] + rs.rand(C)) for k in range(K)]
+    prior_emit = [dict(alpha=1. + 0.5 * rs.rand(C)) for _ in range(K)]
     return dict(obs=obs, sts=sts, mask=mask, var_tran=1. + 5. * rs.rand(K, K), emit=emit,
                 prior_tran=np.ones((K, K)), prior_emit=prior_emit)

@@ -143,3 +143,32 @@ def test_svihmm_surface_runs():
     assert list(next(hmm.allobs_batch())) == list(range(T))
     sts, obs = hmm.generate_obs(10)
     assert sts.shape == (10,) and obs.shape == (10, 2)
+
+
+def test_vbhmm_categorical_emissions_follow_oracle_trajectory():
+    """hmmsgd_metaobs.VBHMM with Categorical emission objects (the reference's Categorical branch,
+    hmmsgd_metaobs.py:907-926,1071-1084, does not run as shipped; the oracle restates its intent):
+    three natural-gradient steps with the reference's window sampler against the oracle."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    from pysvihmm_b200.distributions import Categorical
+    from tests.helpers import make_categorical_problem
+    K, C, Lh, S, maxit, seed = 4, 6, 10, 5, 3, 7
+    p = make_categorical_problem(seed=3, K=K, C=C, T_full=400, miss=0.1)
+    objs = [Categorical(weights=e["alpha"] / e["alpha"].sum(), alphav_0=pe["alpha"].copy(), alpha_mf=e["alpha"].copy())
+            for e, pe in zip(p["emit"], p["prior_emit"])]
+    hmm = H.VBHMM(p["obs"][:, 0].copy(), np.ones(K), p["prior_tran"], np.array(objs), tau=1., kappa=0.7,
+                  metaobs_half=Lh, mb_sz=S, mask=p["mask"], init_tran=p["var_tran"].copy(), maxit=maxit,
+                  seed=seed, track_elbo=False)
+    hmm.infer()
+    # the same windows from the legacy RNG stream (ctor draws, then infer reseeds: hmmsgd_metaobs.py:149,309)
+    np.random.seed(seed)
+    var_tran, emit = p["var_tran"], p["emit"]
+    for it in range(maxit):
+        c_vec = np.random.randint(Lh, 400 - 1 - Lh + 1, S)
+        r = O.svi_minibatch_step(p["obs"], p["mask"], c_vec - Lh, 2 * Lh + 1, var_tran, emit, p["prior_tran"],
+                                 p["prior_emit"], (it + 1.) ** -0.7, Lh, S)
+        var_tran, emit = r["var_tran_new"], r["emit_new"]
+    assert _rel(hmm.var_tran, var_tran) < 1e-4
+    assert _rel(np.array([g._alpha_mf for g in hmm.var_emit]), np.array([e["alpha"] for e in emit])) < 1e-4
+    assert abs(sum(hmm.var_emit[0].weights) - 1.) < 1e-12

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from tests.helpers import (SVI_CASES, emit_list, frac_soft, golden_prior_emit, load_golden,
-                           make_random_problem, pack_emit_np)
+                           make_categorical_problem, make_random_problem, pack_emit_np)
 
 pytestmark = pytest.mark.gpu
 
@@ -233,6 +233,58 @@ def test_estep_matches_oracle(K, D, T, B, kind, path):
         ref = np.array([np.broadcast_to(x[key], e[key][0].shape) for x in r["emit_new"]])
         assert_block(e[key], ref, S_RTOL, key)
     np.testing.assert_allclose(vi, O.stationary_init(r["var_tran_new"]), rtol=1e-5, atol=1e-9)
+    eng.close()
+
+
+@pytest.mark.parametrize("K,C,T,B", [(4, 6, 50, 5), (16, 20, 200, 7), (40, 9, 64, 3)])
+def test_categorical_emissions_match_oracle(K, C, T, B):
+    """SVIHMM_EMIT_CATEGORICAL (Categorical.expected_log_likelihood, distributions.py:1383-1386; count
+    statistics and Dirichlet natural-gradient step, hmmsgd_metaobs.py:907-926,1071-1084) against the
+    oracle; the expected log-likelihood table also against the reference's own values (cat_ell)."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    p = make_categorical_problem(seed=K + C, K=K, C=C, T_full=max(4 * T, 300), miss=0.1)
+    obs = p["obs"].copy()
+    obs[np.random.RandomState(2).rand(len(obs)) < 0.03] = np.nan        # NaN symbols = missing
+    starts = np.random.RandomState(5).randint(0, obs.shape[0] - T + 1, B)
+    eng = _engine(K, C, "categorical")
+    eng.set_series(obs, p["mask"], dtype="f64")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR, keep_locals=True)
+    Lh, Tf = max(T // 2, 1), obs.shape[0]
+    r = O.svi_minibatch_step(obs, p["mask"], starts, T, p["var_tran"], p["emit"], p["prior_tran"],
+                             p["prior_emit"], 0.37, Lh, wrap=True)
+    assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+    loc = eng.get_locals(B, T)
+    np.testing.assert_allclose(loc["lliks"], r["ll"], rtol=1e-11, atol=1e-12)
+    assert_q(vx.cpu().numpy(), r["var_x"])
+    s = eng.unpack_stats(stats)
+    assert_block(s["A"], r["A_inter"], S_RTOL, "A")
+    assert_block(s["sx"], r["counts"], S_RTOL, "counts")
+    assert_block(s["n"], r["counts"].sum(1), S_RTOL, "n")
+    np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=3e-6)
+    eng.global_update(stats, 0.37, (Tf - 2 * Lh - 1) / (2. * Lh * B), (Tf - 2 * Lh - 1) / ((2. * Lh + 1.) * B))
+    vt, vi, em = eng.get_globals()
+    assert_block(vt, r["var_tran_new"], S_RTOL, "var_tran")
+    assert_block(em, np.array([e["alpha"] for e in r["emit_new"]]), S_RTOL, "alpha")
+    # second E-step on the updated globals exercises the refreshed log-probability table
+    vx2, _ = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+    r2 = O.svi_minibatch_step(obs, p["mask"], starts, T, r["var_tran_new"], r["emit_new"], p["prior_tran"],
+                              p["prior_emit"], 0.37, Lh, wrap=True)
+    assert_q(vx2.cpu().numpy(), r2["var_x"])
+    eng.close()
+
+
+def test_categorical_ell_table_matches_reference_golden():
+    g = load_golden("cat_ell")
+    K, C = g["alpha"].shape
+    eng = _engine(K, C, "categorical")
+    eng.set_series(g["x"].astype(np.float64)[:, None])
+    eng.set_globals(np.ones((K, K)), g["alpha"])
+    eng.estep([0], len(g["x"]), want_var_x=False, keep_locals=True)
+    ll = eng.get_locals(1, len(g["x"]))["lliks"][0]
+    np.testing.assert_allclose(ll.T, g["ell"], rtol=1e-12, atol=1e-13)
     eng.close()
 
 

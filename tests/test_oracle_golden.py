@@ -121,3 +121,22 @@ def test_logZ_identities():
     assert np.allclose(g["w_var_x"][0].sum(-1), 1.0, atol=1e-12)
     assert np.allclose(O.local_lower_bound(la), g["w_lb"][0], rtol=1e-12)
     assert np.all(O.log_Z(la) < 0)
+
+
+def test_categorical_ell_and_update_match_reference():
+    """Categorical.expected_log_likelihood (distributions.py:1383-1386) and the Categorical branch of
+    global_update (hmmsgd_metaobs.py:1071-1084) as run on reference objects."""
+    g = load_golden("cat_ell")
+    K = g["alpha"].shape[0]
+    emit = [dict(alpha=g["alpha"][k]) for k in range(K)]
+    ll = O.lliks_categorical(g["x"][None].astype(float), emit)[0]
+    np.testing.assert_allclose(ll.T, g["ell"], rtol=RT, atol=AT)
+    xs = g["x"].astype(float)[None].copy()
+    xs[0, 3] = np.nan
+    assert np.all(O.lliks_categorical(xs, emit)[0, 3] == 0.)
+    # emit_inter = n_windows*(prior-1) + counts: feed the fixture's emit_inter through counts with
+    # a prior of ones (prior - 1 = 0)
+    for k in range(K):
+        new = O.cat_global_update(g["alpha"][k], np.ones_like(g["alpha"][k]), g["emit_inter"][k], 3,
+                                  float(g["lrate"]), float(g["bfact"]))
+        np.testing.assert_allclose(new, g["alpha_new"][k], rtol=RT, atol=AT)
