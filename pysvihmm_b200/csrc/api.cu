@@ -346,28 +346,28 @@ static cudaError_t launch_fused(const FusedArgs& fa, size_t smem, cudaStream_t s
   return cudaGetLastError();
 }
 
-template <int KP>
+template <int KP, int NTE>
 static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st, bool set_attr) {
   if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_estep_pipe<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_estep_pipe<KP, NTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k_estep_pipe<KP><<<fa.B, FP_NT, smem, st>>>(fa);
+  k_estep_pipe<KP, NTE><<<fa.B, FP_NT, smem, st>>>(fa);
   return cudaGetLastError();
 }
 
-// Pipelined single-kernel E-step (fused_pipe.cuh): same conditions as the phase-by-phase fused
-// kernel plus: every 4x4 statistics tile owned by one worker thread, barriers within the budget.
+// Pipelined single-kernel E-step (fused_pipe.cuh): the diagonal model with K <= 32 whose window
+// fits in shared memory and whose emission features [x | x^2 | w] fit the tensor-core statistics
+// tiles instantiated below (D <= 16, or D <= 8 for 16 < K <= 32); barriers within the budget.
+static int pipe_nte(const svihmm_ctx* c) { return 2 * ((c->D + 7) / 8) + 1; }
 static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
   static const bool off = getenv("SVIHMM_NO_PIPE") != nullptr;
-  if (off || c->K > 32 || c->kind == SVIHMM_EMIT_CATEGORICAL || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
-  const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
-  const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
-  const PipeSmem L = pipe_smem_layout(T, c->K, c->D, tri, diag);
+  if (off || c->K > 32 || c->kind != SVIHMM_EMIT_NIW_DIAG || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  const int nte = pipe_nte(c);
+  if (nte > 5 || (c->K > 16 && nte > 3)) return false;
+  const PipeSmem L = pipe_smem_layout(T, c->K, c->D, c->D, 1);
   if (L.total > (size_t)c->max_smem_optin) return false;
   const int nwk = c->K > 16 ? 128 : 192;
-  const int nbi = L.KS / 4, ncb = ((c->D + 1 + 3) & ~3) / 4;
-  if (nbi * nbi > nwk || nbi * ncb > nwk || (!diag && nbi * c->D * ncb > nwk)) return false;
   const int npairs = (T + 1) / 2, nrounds = (npairs + nwk / 2 - 1) / (nwk / 2), ntiles = (T - T / 2 + FP_TB - 1) / FP_TB;
   if (nrounds + ntiles > FP_MAXBAR || ntiles > 190) return false;
   *smem_out = L.total;
@@ -415,12 +415,13 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
   const bool set_attr = smem > 48 * 1024;
   cudaError_t e;
   if (pipe) {
+    const bool wide = pipe_nte(c) > 3;                  // 8 < D <= 16
     switch (c->KP) {
       case 2:
-      case 4: e = launch_pipe<4>(fa, smem, st, set_attr); break;
-      case 8: e = launch_pipe<8>(fa, smem, st, set_attr); break;
-      case 16: e = launch_pipe<16>(fa, smem, st, set_attr); break;
-      default: e = launch_pipe<32>(fa, smem, st, set_attr); break;
+      case 4: e = wide ? launch_pipe<4, 5>(fa, smem, st, set_attr) : launch_pipe<4, 3>(fa, smem, st, set_attr); break;
+      case 8: e = wide ? launch_pipe<8, 5>(fa, smem, st, set_attr) : launch_pipe<8, 3>(fa, smem, st, set_attr); break;
+      case 16: e = wide ? launch_pipe<16, 5>(fa, smem, st, set_attr) : launch_pipe<16, 3>(fa, smem, st, set_attr); break;
+      default: e = launch_pipe<32, 3>(fa, smem, st, set_attr); break;
     }
   } else {
     switch (c->KP) {
@@ -439,6 +440,10 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
     double m[6] = {0, 0, 0, 0, 0, 0}, q[5] = {0, 0, 0, 0, 0};
     for (int b = 0; b < B; ++b) for (int i = 1; i < 6; ++i) m[i] += (double)(h[16 * b + i] - h[16 * b]) / B;
     for (int b = 0; b < B; ++b) for (int i = 0; i < 5; ++i) q[i] += (double)h[16 * b + 8 + i] / B;
+    long long gmin = h[13], gmaxs = h[13], gmaxe = h[14];
+    for (int b = 0; b < B; ++b) { gmin = std::min(gmin, h[16 * b + 13]); gmaxs = std::max(gmaxs, h[16 * b + 13]); gmaxe = std::max(gmaxe, h[16 * b + 14]); }
+    fprintf(stderr, "[pipe dbg] globaltimer: last CTA start - first CTA start = %.2f us, last CTA end - first CTA start = %.2f us\n",
+            (gmaxs - gmin) * 1e-3, (gmaxe - gmin) * 1e-3);
     fprintf(stderr, "[pipe dbg] worker 0 totals over tiles: wait=%.0f C1=%.0f bar=%.0f C2=%.0f C3+prefetch=%.0f\n", q[0], q[1], q[2], q[3], q[4]);
     fprintf(stderr, "[pipe dbg] B=%d T=%d smem=%zu cycles since CTA start: chain start=%.0f chain end=%.0f (%.1f/step) | workers: phase A done=%.0f last tile done=%.0f | before final atomics=%.0f\n",
             B, T, smem, m[1], m[2], (m[2] - m[1]) / (T > 1 ? T - 1 : 1), m[3], m[4], m[5]);

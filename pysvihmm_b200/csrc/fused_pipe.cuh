@@ -1,21 +1,26 @@
-// Pipelined single-kernel E-step for K <= 32 (supersedes the phase-by-phase k_estep_fused): the
-// same arithmetic, but the three phases of a window overlap inside its CTA.
+// Pipelined single-kernel E-step for the diagonal model with K <= 32 (other models: k_estep_fused,
+// the phase-by-phase version of the same arithmetic): the three phases of a window overlap inside
+// its CTA.
 //
-//   warps 1..7 (224 "workers")   phase A: expected log-likelihoods -> b table, rows taken OUTSIDE-IN
-//                                (row p and row T-1-p per pair index p) straight from global memory,
-//                                one mbarrier arrival per round of 112 pairs
+//   worker warps {1,2,3,5,6,7}   phase A: expected log-likelihoods -> b table, rows taken OUTSIDE-IN
+//   (the warps that do not       (row p and row T-1-p per pair index p) straight from global memory,
+//   share the chain's            one mbarrier arrival per round of 96 pairs
+//   scheduler)
 //   warp 0 (the "chain" warp)    phase B: forward chain in lanes 0..15, backward chain in lanes 16..31
 //                                (fused.cuh: smem broadcast + packed FFMA2 + power-of-two rescaling);
 //                                starts as soon as round 0 of phase A has landed and signals an
 //                                mbarrier every FP_TB steps once the two chains have crossed
-//   warps 1..7 again             phase C: rows between the two chain heads are final; for every
+//   worker warps again           phase C: rows between the two chain heads are final; for every
 //                                signalled tile the workers form the marginals INSIDE-OUT, write them
-//                                out, and accumulate the transition / emission statistics in
-//                                registers (4x4 tiles); only the cross-thread reduction and the
-//                                float64 atomics remain after the chain has finished.
+//                                out, and accumulate the transition / emission statistics on the
+//                                TENSOR CORES (mma.m16n8k8, 3xTF32, float32 accumulators in
+//                                registers); only the cross-warp reduction and the float64 atomics
+//                                remain after the chain has finished.
 // The kernel time is therefore ~ (first phase-A round) + chain + (last tile + reduction) instead of
-// A + B + C.  No observation staging in shared memory: phase A and C read the window rows from
-// global memory (HBM once, then L2), so HBM traffic stays at the algorithmic T*D + T*K.
+// A + B + C (measured at c2: chain ends at 75.6k cycles, CTA done at 86k; the scalar phase C of the
+// first version finished at 103k).  No observation staging in shared memory: phase A and C read the
+// window rows from global memory (HBM once, then L2), so HBM traffic stays at the algorithmic
+// T*D + T*K.
 #pragma once
 #include "fused.cuh"
 
@@ -64,6 +69,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
 }
+// waiting for a hand-off that is microseconds away: back off between polls so that the spinning
+// warps do not take issue slots and shared-memory bandwidth from the chain warp (ncu: 30 % of all
+// executed instructions of the kernel were try_wait polls)
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long* bar, int parity) {
+  unsigned ok;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void bar_workers(const int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
 // one float4 of the phase-C feature row of window row t: columns [c0, c0+4) of [x_0..x_{D-1} | w | 0..]
@@ -87,7 +104,21 @@ __device__ __forceinline__ float4 pipe_xrow4(const FusedArgs& a, const int64_t s
   return make_float4(e[0], e[1], e[2], e[3]);
 }
 
-template <int KP>
+// 3xTF32 helpers: v = hi + lo with hi, lo representable in TF32 (10-bit mantissa)
+__device__ __forceinline__ void split_tf32(const float v, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float r = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// KP: lane group of a chain (power of two >= K); NTE: 8-column tiles of the emission features
+// [x | x^2 | w] = 2*ceil(D/8) + 1 (diagonal model only; other models use k_estep_fused)
+template <int KP, int NTE>
 __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int T = a.T, K = a.K, D = a.D;
@@ -109,6 +140,7 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
   const int64_t s0 = a.starts[w];
 #define PIPE_STAMP(i, who) do { if (a.dbg && tid == (who)) a.dbg[(size_t)w * 16 + (i)] = clock64(); } while (0)
   PIPE_STAMP(0, 0);
+  if (a.dbg && tid == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[(size_t)w * 16 + 13] = (long long)gt; }
   constexpr int NCW = KP == 32 ? 2 : 1;                        // chain warps (K > 16: one warp per direction)
   // Workers are the warps that do NOT share a scheduler (warp id mod 4) with a chain warp: the chain
   // issues ~40 dependent instructions per step, and a busy warp on the same scheduler delays each of
@@ -335,52 +367,51 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
 
     PIPE_STAMP(3, 32 * (NCW == 1 ? 1 : 2));
     // ---------------------------------------------------------------- phase C, inside-out
-    const int nbi = KS / 4;
-    const int DS = (D + 1 + 3) & ~3, ncb = DS / 4;
-    const int nbA = nbi * nbi, slotsA = max(1, NWK / nbA);
-    const int nbE = nbi * ncb, slotsE = max(1, NWK / nbE);
-    const int nb2 = a.diag ? nbE : nbi * D * ncb, slots2 = max(1, NWK / nb2);
-    const bool roleA = wt < nbA * slotsA, roleE = wt < nbE * slotsE, role2 = !a.diag && wt < nb2 * slots2;
-    const int blkA = wt % nbA, slotA = wt / nbA, i0 = (blkA / nbi) * 4, j0 = (blkA % nbi) * 4;
-    const int blkE = wt % nbE, slotE = wt / nbE, k0E = (blkE / ncb) * 4, c0E = (blkE % ncb) * 4;
-    const int blk2 = wt % nb2, slot2 = wt / nb2;
-    const int k02 = (blk2 / (D * ncb)) * 4, d2 = (blk2 / ncb) % D, e02 = (blk2 % ncb) * 4;
-    const bool vecx = a.dtype == SVIHMM_F32 && (D & 3) == 0 && ((((uintptr_t)a.obs) & 15) == 0);
-    float accA[16], accE[16], acc2[16];
+    // Statistics on the tensor cores: per group of 8 rows one warp forms, with mma.m16n8k8 (TF32
+    // inputs split hi/lo = "3xTF32", float32 accumulate),
+    //     accT[mt][j] += Q[prev rows]^T (16 states x 8) . Q[next rows] (8 x 8 states)      transitions
+    //     accE[mt][j] += Q[rows]^T . F[rows],  F = [ x (ND8 tiles) | x^2 (ND8 tiles) | w ]    emissions
+    // (ncu on the scalar version: 37k of the CTA's 118k executed warp instructions were phase C
+    // index arithmetic around 16-FMA register tiles and the worker schedulers were ~80 % busy; one
+    // group of 8 rows is now ~110 warp instructions instead of ~580).
+    constexpr int MT = KP > 16 ? 2 : 1;                 // 16-state tiles
+    constexpr int NTT = KP > 8 ? KP / 8 : 1;            // 8-state tiles of the "next" side
+    const int g = lane >> 2, tig = lane & 3;
+    const int ND8 = (D + 7) >> 3;
+    float accT[MT][NTT][4], accE[MT][NTE][4];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) { accA[u] = 0.f; accE[u] = 0.f; acc2[u] = 0.f; }
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int j = 0; j < NTT; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) accT[m][j][c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NTE; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) accE[m][j][c] = 0.f;
+    }
     double ltsum = 0.0;
     constexpr int LPR = KP / 4, RPW = 32 / LPR;
     const int sub = lane % LPR, rsub = lane / LPR;
     int lo = 0, hi = -1;
     bool first = true;
-    // the window rows a tile needs do not depend on the chain: each emission thread fetches its (up to
-    // four) rows of the NEXT tile while it waits for the chain to hand that tile over
-    float4 xpre[4];
     auto tile_rows = [&](int tile_, int lo_, int hi_, bool first_, int& nlo_, int& nhi_, int& plo_, int& phi_) {
       int e_ = h - 1 + FP_TB * (tile_ + 1); if (e_ > T - 1) e_ = T - 1;
       nlo_ = T - 1 - e_; nhi_ = e_;
       if (first_) { plo_ = (nlo_ + nhi_ + 1) / 2; phi_ = plo_ - 1; } else { plo_ = lo_; phi_ = hi_; }
     };
-    auto prefetch_tile = [&](int tile_, int lo_, int hi_, bool first_) {
-      int nlo_, nhi_, plo_, phi_;
-      tile_rows(tile_, lo_, hi_, first_, nlo_, nhi_, plo_, phi_);
-      const int nl_ = plo_ - nlo_, nnew_ = nl_ + (nhi_ - phi_);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int n = slotE + i * slotsE;
-        xpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (roleE && n < nnew_) {
-          const int row = n < nl_ ? nlo_ + n : phi_ + 1 + (n - nl_);
-          xpre[i] = pipe_xrow4(a, s0, row, c0E, false, vecx);
-        }
-      }
+    // q entries of one A fragment (states 16*mt + {g, g+8}) of table rows r0 / r1 (ok0/ok1: row exists)
+    auto load_a = [&](const int mt, const int r0, const int r1, const bool ok0, const bool ok1, float (&av)[4]) {
+      const int c0 = 16 * mt + g, c1 = c0 + 8;
+      av[0] = (ok0 && c0 < KS) ? aS[(size_t)r0 * KS + c0] : 0.f;
+      av[1] = (ok0 && c1 < KS) ? aS[(size_t)r0 * KS + c1] : 0.f;
+      av[2] = (ok1 && c0 < KS) ? aS[(size_t)r1 * KS + c0] : 0.f;
+      av[3] = (ok1 && c1 < KS) ? aS[(size_t)r1 * KS + c1] : 0.f;
     };
-    prefetch_tile(0, 0, -1, true);
     long long tw = 0, t1c = 0, tbar = 0, t2c = 0, t3c = 0;
     for (int tile = 0; tile < ntiles; ++tile) {
       long long c0 = clock64();
-      mbar_wait(barB + tile, 0);
+      mbar_wait_relaxed(barB + tile, 0);
       long long c1 = clock64(); tw += c1 - c0;
       int nlo, nhi, plo, phi;
       tile_rows(tile, lo, hi, first, nlo, nhi, plo, phi);
@@ -427,80 +458,96 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
       long long c2 = clock64(); t1c += c2 - c1;
       bar_workers(NWK);
       long long c3 = clock64(); tbar += c3 - c2;
-      // ---- C2: transition pairs (u-1, u) that became available
-      if (roleA) {
+      // ---- C2: transition pairs (u-1, u) that became available, 8 pairs per warp per pass
+      {
         const int npl = nl;                                       // u in [nlo+1, lo]
         const int ru0 = max(hi + 1, lo + 1), npr = nhi - ru0 + 1; // u in [ru0, nhi]
         const int np_ = npl + (npr > 0 ? npr : 0);
-        for (int n = slotA; n < np_; n += slotsA) {
-          const int u = n < npl ? nlo + 1 + n : ru0 + (n - npl);
-          const float4 pv = *reinterpret_cast<const float4*>(aS + (size_t)(u - 1) * KS + i0);
-          const float4 cv = *reinterpret_cast<const float4*>(aS + (size_t)u * KS + j0);
-          const float pa[4] = {pv.x, pv.y, pv.z, pv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+        for (int g0 = wwp * 8; g0 < np_; g0 += NWW * 8) {
+          const int n0 = g0 + tig, n1 = n0 + 4;
+          const bool ok0 = n0 < np_, ok1 = n1 < np_;
+          const int u0 = n0 < npl ? nlo + 1 + n0 : ru0 + (n0 - npl);
+          const int u1 = n1 < npl ? nlo + 1 + n1 : ru0 + (n1 - npl);
+          unsigned bh[NTT][2], bl[NTT][2];
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
+          for (int j = 0; j < NTT; ++j) {
+            const int cn = 8 * j + g;
+            const float b0 = (ok0 && cn < KS) ? aS[(size_t)u0 * KS + cn] : 0.f;
+            const float b1 = (ok1 && cn < KS) ? aS[(size_t)u1 * KS + cn] : 0.f;
+            split_tf32(b0, bh[j][0], bl[j][0]); split_tf32(b1, bh[j][1], bl[j][1]);
+          }
 #pragma unroll
-            for (int y = 0; y < 4; ++y) accA[x * 4 + y] = fmaf(pa[x], ca[y], accA[x * 4 + y]);
-        }
-      }
-      long long c4 = clock64(); t2c += c4 - c3;
-      // ---- C3: emission statistics of the new rows
-      if (roleE) {
-        int ix = 0;
-        for (int n = slotE; n < nnew; n += slotsE, ++ix) {
-          const int row = n < nl ? nlo + n : hi + 1 + (n - nl);
-          const bool drop = fl[row] & 1;
-          const float4 qv = *reinterpret_cast<const float4*>(aS + (size_t)row * KS + k0E);
-          float4 xv;
-          if (ix < 4) {
-            xv = ix == 0 ? xpre[0] : (ix == 1 ? xpre[1] : (ix == 2 ? xpre[2] : xpre[3]));
-            if (drop) xv = make_float4(0.f, 0.f, 0.f, 0.f);
-          } else xv = pipe_xrow4(a, s0, row, c0E, drop, vecx);
-          const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, xa4[4] = {xv.x, xv.y, xv.z, xv.w};
+          for (int mt = 0; mt < MT; ++mt) {
+            float av[4];
+            load_a(mt, u0 - 1, u1 - 1, ok0, ok1, av);
+            unsigned ah[4], al_[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
+            for (int c = 0; c < 4; ++c) split_tf32(av[c], ah[c], al_[c]);
 #pragma unroll
-            for (int y = 0; y < 4; ++y) accE[x * 4 + y] = fmaf(qa[x], xa4[y], accE[x * 4 + y]);
-          if (a.diag) {
-            const float x2[4] = {xv.x * xv.x, xv.y * xv.y, xv.z * xv.z, xv.w * xv.w};
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-              for (int y = 0; y < 4; ++y) acc2[x * 4 + y] = fmaf(qa[x], x2[y], acc2[x * 4 + y]);
+            for (int j = 0; j < NTT; ++j) {
+              mma_tf32(accT[mt][j], al_, bh[j]); mma_tf32(accT[mt][j], ah, bl[j]); mma_tf32(accT[mt][j], ah, bh[j]);
+            }
           }
         }
       }
-      if (role2) {
-        for (int n = slot2; n < nnew; n += slots2) {
-          const int row = n < nl ? nlo + n : hi + 1 + (n - nl);
-          const bool drop = fl[row] & 1;
-          const float4 qv = *reinterpret_cast<const float4*>(aS + (size_t)row * KS + k02);
-          float4 xv = pipe_xrow4(a, s0, row, e02, drop, vecx);
-          const float xd = drop ? 0.f : (float)ld_obs(a.obs, a.dtype, (s0 + row) * D + d2);
-          xv.x *= xd; xv.y *= xd; xv.z *= xd; xv.w *= xd;
-          const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, xa4[4] = {xv.x, xv.y, xv.z, xv.w};
+      long long c4 = clock64(); t2c += c4 - c3;
+      // ---- C3: emission statistics of the new rows (masked / NaN rows dropped: w = 0)
+      for (int g0 = wwp * 8; g0 < nnew; g0 += NWW * 8) {
+        const int n0 = g0 + tig, n1 = n0 + 4;
+        const bool ok0 = n0 < nnew, ok1 = n1 < nnew;
+        const int r0 = n0 < nl ? nlo + n0 : hi + 1 + (n0 - nl);
+        const int r1 = n1 < nl ? nlo + n1 : hi + 1 + (n1 - nl);
+        const bool w0 = ok0 && !(fl[r0] & 1), w1 = ok1 && !(fl[r1] & 1);
+        unsigned bh[NTE][2], bl[NTE][2];
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
+        for (int j = 0; j < NTE; ++j) { bh[j][0] = bh[j][1] = bl[j][0] = bl[j][1] = 0u; }
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc2[x * 4 + y] = fmaf(qa[x], xa4[y], acc2[x * 4 + y]);
+        for (int j = 0; j < (NTE - 1) / 2; ++j) {
+          if (j < ND8) {
+            const int d = 8 * j + g;
+            const float x0 = (w0 && d < D) ? (float)ld_obs(a.obs, a.dtype, (s0 + r0) * D + d) : 0.f;
+            const float x1 = (w1 && d < D) ? (float)ld_obs(a.obs, a.dtype, (s0 + r1) * D + d) : 0.f;
+            split_tf32(x0, bh[j][0], bl[j][0]); split_tf32(x1, bh[j][1], bl[j][1]);
+            split_tf32(x0 * x0, bh[(NTE - 1) / 2 + j][0], bl[(NTE - 1) / 2 + j][0]);
+            split_tf32(x1 * x1, bh[(NTE - 1) / 2 + j][1], bl[(NTE - 1) / 2 + j][1]);
+          }
+        }
+        bh[NTE - 1][0] = (w0 && g == 0) ? 0x3f800000u : 0u;      // the count column: w = 1.0 (exact in TF32)
+        bh[NTE - 1][1] = (w1 && g == 0) ? 0x3f800000u : 0u;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          float av[4];
+          load_a(mt, r0, r1, ok0, ok1, av);
+          unsigned ah[4], al_[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_tf32(av[c], ah[c], al_[c]);
+#pragma unroll
+          for (int j = 0; j < NTE - 1; ++j) {
+            mma_tf32(accE[mt][j], al_, bh[j]); mma_tf32(accE[mt][j], ah, bl[j]); mma_tf32(accE[mt][j], ah, bh[j]);
+          }
+          mma_tf32(accE[mt][NTE - 1], al_, bh[NTE - 1]); mma_tf32(accE[mt][NTE - 1], ah, bh[NTE - 1]);
         }
       }
       lo = nlo; hi = nhi; first = false;
-      if (tile + 1 < ntiles) prefetch_tile(tile + 1, lo, hi, false);
       t3c += clock64() - c4;
     }
     if (a.dbg && wt == 0) { long long* dq = a.dbg + (size_t)w * 16; dq[8] = tw; dq[9] = t1c; dq[10] = tbar; dq[11] = t2c; dq[12] = t3c; }
     PIPE_STAMP(4, 32 * (NCW == 1 ? 1 : 2));
-    // partial results of this thread -> shared memory (the tables under `red` are dead: the chain has
-    // finished (last tile signalled) and every worker is past its last read of b / beta)
+    // accumulator fragments of this warp -> shared memory (the tables under `red` are dead: the chain
+    // has finished (last tile signalled) and every worker is past its last read of b / beta)
     bar_workers(NWK);
     {
-      float* rp = red + (size_t)wt * 48;
+      float* rp = red + (size_t)wwp * (MT * (NTT + NTE) * 4) * 32 + lane;
 #pragma unroll
-      for (int u = 0; u < 16; u += 4) {
-        *reinterpret_cast<float4*>(rp + u) = make_float4(accA[u], accA[u + 1], accA[u + 2], accA[u + 3]);
-        *reinterpret_cast<float4*>(rp + 16 + u) = make_float4(accE[u], accE[u + 1], accE[u + 2], accE[u + 3]);
-        *reinterpret_cast<float4*>(rp + 32 + u) = make_float4(acc2[u], acc2[u + 1], acc2[u + 2], acc2[u + 3]);
+      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int j = 0; j < NTT; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rp[(((mt * (NTT + NTE)) + j) * 4 + c) * 32] = accT[mt][j][c];
+#pragma unroll
+        for (int j = 0; j < NTE; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rp[(((mt * (NTT + NTE)) + NTT + j) * 4 + c) * 32] = accE[mt][j][c];
       }
     }
     // log-normaliser pieces: reduce (sum mx, sum (T-t) mx, sum lt) over the workers
@@ -516,50 +563,37 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
 
   // ---------------------------------------------------------------- reduction + float64 atomics
   {
-    const int nbi = KS / 4;
-    const int DS = (D + 1 + 3) & ~3, ncb = DS / 4;
-    const int nbA = nbi * nbi, slotsA = max(1, NWK / nbA);
-    const int nbE = nbi * ncb, slotsE = max(1, NWK / nbE);
-    const int nb2 = a.diag ? nbE : nbi * D * ncb, slots2 = max(1, NWK / nb2);
-    for (int e = tid; e < nbA * 16; e += FP_NT) {
-      const int blk = e / 16, u = e - blk * 16;
-      const int i = (blk / nbi) * 4 + u / 4, jq = (blk % nbi) * 4 + (u & 3);
-      if (i < K && jq < K) {
-        double tot = 0.0;
-        for (int c = 0; c < slotsA; ++c) tot += (double)red[((size_t)c * nbA + blk) * 48 + u];
-        if (a.wrap) tot += (double)(aS[(size_t)(T - 1) * KS + i] * aS[jq]);      // pair (T-1, 0), quirk Q2
-        if (a.add_prior) tot += a.prior_tran[i * K + jq] - 1.0;
-        atomicAdd(a.stats_out + i * K + jq, tot);
-      }
+    constexpr int MT = KP > 16 ? 2 : 1, NTT = KP > 8 ? KP / 8 : 1, NJ = NTT + NTE;
+    const int ND8 = (D + 7) >> 3;
+    // element (state m, tile j, column n of the tile) sits in fragment register c of lane 4*(m%8)+n/2
+    auto frag_sum = [&](const int m, const int j, const int n) {
+      const int mt = m >> 4, mm = m & 15, c = 2 * (mm >> 3) + (n & 1), ln = 4 * (mm & 7) + (n >> 1);
+      double tot = 0.0;
+      for (int wv_ = 0; wv_ < NWW; ++wv_)
+        tot += (double)red[((size_t)wv_ * (MT * NJ * 4) + ((mt * NJ + j) * 4 + c)) * 32 + ln];
+      return tot;
+    };
+    {
+    for (int e = tid; e < K * K; e += FP_NT) {
+      const int i = e / K, jq = e - i * K;
+      double tot = frag_sum(i, jq >> 3, jq & 7);
+      if (a.wrap) tot += (double)(aS[(size_t)(T - 1) * KS + i] * aS[jq]);      // pair (T-1, 0), quirk Q2
+      if (a.add_prior) tot += a.prior_tran[e] - 1.0;
+      atomicAdd(a.stats_out + e, tot);
     }
-    for (int e = tid; e < nbE * 16; e += FP_NT) {
-      const int blk = e / 16, u = e - blk * 16;
-      const int kq = (blk / ncb) * 4 + u / 4, cc = (blk % ncb) * 4 + (u & 3);
-      if (kq < K && cc <= D) {
-        double tot = 0.0, tot2 = 0.0;
-        for (int c = 0; c < slotsE; ++c) {
-          tot += (double)red[((size_t)c * nbE + blk) * 48 + 16 + u];
-          tot2 += (double)red[((size_t)c * nbE + blk) * 48 + 32 + u];
-        }
-        if (cc < D) {
-          atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + cc, tot);
-          if (a.diag) atomicAdd(a.stats_out + a.o_sxx + (size_t)kq * D + cc, tot2);
-        } else atomicAdd(a.stats_out + a.o_n + kq, tot);
-      }
-    }
-    if (!a.diag) {
-      for (int e = tid; e < nb2 * 16; e += FP_NT) {
-        const int blk = e / 16, u = e - blk * 16;
-        const int kq = (blk / (D * ncb)) * 4 + u / 4, dd = (blk / ncb) % D, cc = (blk % ncb) * 4 + (u & 3);
-        if (kq < K && cc < D) {
-          double tot = 0.0;
-          for (int c = 0; c < slots2; ++c) tot += (double)red[((size_t)c * nb2 + blk) * 48 + 32 + u];
-          atomicAdd(a.stats_out + a.o_sxx + ((size_t)kq * D + dd) * D + cc, tot);
-        }
-      }
+    for (int e = tid; e < K * (2 * D + 1); e += FP_NT) {
+      const int kq = e / (2 * D + 1), f = e - kq * (2 * D + 1);
+      if (f < D) atomicAdd(a.stats_out + a.o_sx + (size_t)kq * D + f, frag_sum(kq, NTT + (f >> 3), f & 7));
+      else if (f < 2 * D) {
+        const int d = f - D;
+        atomicAdd(a.stats_out + a.o_sxx + (size_t)kq * D + d, frag_sum(kq, NTT + (NTE - 1) / 2 + (d >> 3), d & 7));
+      } else atomicAdd(a.stats_out + a.o_n + kq, frag_sum(kq, NTT + NTE - 1, 0));
     }
     if (tid < K) atomicAdd(a.stats_out + a.o_q0 + tid, (double)aS[tid]);
+    }
+    (void)ND8;
     PIPE_STAMP(5, 32);
+    if (a.dbg && tid == 32) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); a.dbg[(size_t)w * 16 + 14] = (long long)gt; }
     if (tid == 32) {
       // logZ = lt[T-1] + sum_t mx[t];  Q4 = sum_t (lt[t] + sum_{s<=t} mx[s]) = sum lt + sum (T - t) mx[t]
       const double lz = misc[0] + misc[1], q4 = misc[3] + misc[2];

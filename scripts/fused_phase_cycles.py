@@ -5,7 +5,7 @@ import bench
 from pysvihmm_b200 import _lib as L
 from pysvihmm_b200.engine import EStepEngine, pack_emit_dicts
 cfg = bench.CONFIGS["c2"]
-K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], cfg["B"], cfg["kind"]
+K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], int(os.environ.get("DBG_B", cfg["B"])), cfg["kind"]
 obs, mus = bench.synthetic_series(K, D, 1 << 20, 1)
 vt, em, pr = bench.globals_for(K, D, kind, mus, 1)
 eng = EStepEngine(K, D, kind)
