@@ -76,6 +76,21 @@ int svihmm_destroy(svihmm_ctx* ctx);
 size_t svihmm_emit_param_len(const svihmm_ctx* ctx); /* doubles per state */
 size_t svihmm_stats_len(const svihmm_ctx* ctx);      /* doubles           */
 
+/* EXTENSION (BASELINE config 5, no mean-field counterpart in the reference: MixtureDistribution,
+ * pybasicbayes/models.py:256-300, is Gibbs/EM only): every state emits from a mixture of C NIW
+ * components (kind = SVIHMM_EMIT_NIW_FULL or _DIAG) with Dirichlet weights.  Component arrays
+ * (svihmm_set_prior / svihmm_set_globals `emit`) then hold K*C rows of svihmm_emit_param_len()
+ * doubles, row k*C + c = component c of state k; the statistics are
+ *   [ A (K*K) | n (K*C) | sx (K*C*D) | sxx (K*C*DD) | q0 (K) | tail (4) ]
+ * with component weights q[t,k] * r[t,k,c], r = softmax_c(E[ln pi_kc] + E[ln N_kc(x_t)])
+ * (pybasicbayes/internals/labels.py:52-65), and ll[t,k] = logsumexp_c of the same terms.
+ * svihmm_set_mix_weights must be called (with the prior) before the first E-step; omega, omega_prior:
+ * K*C Dirichlet parameters.  Only the SVI update (svihmm_global_update) is defined for mixtures. */
+int svihmm_create_mix(svihmm_ctx** out, int device, int K, int D, int emission_kind, int C);
+int svihmm_set_mix_weights(svihmm_ctx* ctx, const double* omega, const double* omega_prior, int loc,
+                           void* stream);
+int svihmm_get_mix_weights(svihmm_ctx* ctx, double* omega, int loc, void* stream);
+
 /* Observation series obs (T_full x D, dtype f32/f64) and optional mask (T_full bytes, 1 = missing,
  * hmmbase.py:60-65).  Replaces set_data (hmmbase.py:138-143).
  * loc = DEVICE: pointers are borrowed (caller keeps them alive).  loc = HOST: copied into HBM. */

@@ -117,6 +117,87 @@ def cat_global_update(alpha, alpha_prior, counts, n_windows, lrate, bfact):
     return (1. - lrate) * (alpha - 1.) + lrate * bfact * emit_inter + 1.
 
 
+def lliks_gmm(xw, emit):
+    """EXTENSION (BASELINE config 5; the reference's MixtureDistribution, pybasicbayes/models.py:
+    256-300, has no mean-field path).  State k emits from C NIW components with Dirichlet(omega_k)
+    weights.  Following the variational mixture update pybasicbayes/internals/labels.py:52-65
+    (logr = E[ln pi] + component expected log-likelihoods, r = softmax):
+        ll[t,k]  = logsumexp_c( psi(omega_kc) - psi(sum_c omega_kc) + ELL_kc(x_t) )
+        r[t,k,c] = exp(that term - ll[t,k])
+    with distributions.py:351-366 per component and :1383-1386 for the weights; NaN rows give
+    ll = 0 (hmmsgd_metaobs.py:508-509).  emit: list of K dicts(omega=(C,), comps=[C dicts]).
+    Returns ll (B,T,K), r (B,T,K,C).  End-to-end parity unpinned (C = 1 reduces to the pinned
+    Gaussian path)."""
+    B, T, D = xw.shape
+    K, C = len(emit), len(emit[0]['comps'])
+    bad = np.isnan(xw).any(-1)
+    ll = np.empty((B, T, K)); r = np.empty((B, T, K, C))
+    with np.errstate(invalid='ignore'):
+        for k, e in enumerate(emit):
+            lw = digamma(e['omega']) - digamma(np.sum(e['omega']))
+            sc = np.stack([lw[c] + (gaussian_ell(xw, g['mu'], g['sigma'], g['kappa'], g['nu'])
+                                    if np.ndim(g['sigma']) == 2 else
+                                    diag_gaussian_ell(xw, g['mu'], g['sigma'], g['kappa'], g['nu']))
+                           for c, g in enumerate(e['comps'])], axis=-1)
+            m = np.max(sc, axis=-1, keepdims=True)
+            ll[:, :, k] = (m + np.log(np.sum(np.exp(sc - m), axis=-1, keepdims=True)))[..., 0]
+            r[:, :, k] = np.exp(sc - ll[:, :, k][..., None])
+    ll[bad] = 0.
+    r[bad] = 0.
+    return ll, r
+
+
+def gmm_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_emit, lrate, L, S=None,
+                       wrap=True):
+    """svi_minibatch_step with GMM emissions (EXTENSION, see lliks_gmm).  Component (k,c) collects
+    the NIW statistics (util.py:73-83) weighted by q[t,k] r[t,k,c]; its natural-gradient step is
+    hmmsgd_metaobs.py:1048-1069 verbatim; the Dirichlet weights move like the transition rows
+    (:1029-1045): omega <- (1-rho)(omega-1) + rho (omega0 - 1 + bE n_kc) + 1."""
+    T_full = obs.shape[0]
+    K, C = len(emit), len(emit[0]['comps'])
+    S = len(starts) if S is None else S
+    idx = np.asarray(starts)[:, None] + np.arange(T)[None]
+    xw = obs[idx]
+    mw = mask[idx] if mask is not None else np.zeros(idx.shape, bool)
+    var_init = stationary_init(var_tran)
+    mod_init, mod_tran = mod_params(var_init, var_tran)
+    ll, r = lliks_gmm(xw, emit)
+    lalpha = forward_msgs(ll, mod_init, mod_tran)
+    lbeta = backward_msgs(ll, mod_tran)
+    q = marginals(lalpha, lbeta)
+    A_inter = np.zeros_like(var_tran)
+    full = np.ndim(emit[0]['comps'][0]['sigma']) == 2
+    stats = [[None] * C for _ in range(K)]
+    for b in range(len(starts)):
+        A_inter += prior_tran + tran_stat(q[b][None], wrap)[0] - 1.
+        inds = np.logical_not(mw[b]) & ~np.isnan(xw[b]).any(-1)
+        xb = xw[b][inds]
+        for k in range(K):
+            for c in range(C):
+                w = q[b][inds, k] * r[b][inds, k, c]
+                e = niw_suffstats(xb, w) if full else diag_suffstats(xb, w)
+                stats[k][c] = e if stats[k][c] is None else [u + v for u, v in zip(stats[k][c], e)]
+    bA = (T_full - 2 * L - 1) / (2. * L * S)
+    bE = (T_full - 2 * L - 1) / ((2. * L + 1.) * S)
+    var_tran_new = (1. - lrate) * (var_tran - 1.) + lrate * bA * A_inter + 1.
+    nat, mom = (niw_natural, niw_moment) if full else (diag_natural, diag_moment)
+    emit_new = []
+    for k in range(K):
+        comps, om = [], np.empty(C)
+        for c in range(C):
+            g, p = emit[k]['comps'][c], prior_emit[k]['comps'][c]
+            old = nat(g['mu'], g['sigma'], g['kappa'], g['nu'])
+            pri = nat(p['mu'], p['sigma'], p['kappa'], p['nu'])
+            comps.append(mom(*[(1. - lrate) * o + lrate * (pp + bE * e)
+                               for o, pp, e in zip(old, pri, stats[k][c])]))
+            om[c] = (1. - lrate) * (emit[k]['omega'][c] - 1.) + lrate * (
+                prior_emit[k]['omega'][c] - 1. + bE * stats[k][c][1]) + 1.
+        emit_new.append(dict(omega=om, comps=comps))
+    return dict(ll=ll, resp=r, lalpha=lalpha, lbeta=lbeta, var_x=q, A_inter=A_inter, stats=stats,
+                lb=float(np.sum(local_lower_bound(lalpha))), logZ=log_Z(lalpha),
+                var_tran_new=var_tran_new, emit_new=emit_new, var_init=var_init)
+
+
 def lliks_gaussian(xw, emit):
     """hmmsgd_metaobs.py:508-509: per state expected_log_likelihood, then
     np.nan_to_num (a NaN row gives ll = 0 = 'missing').

@@ -19,6 +19,9 @@ SYMBOLS = {
     "svihmm_last_error": (C.c_char_p, []),
     "svihmm_version": (_i, []),
     "svihmm_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "svihmm_create_mix": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "svihmm_set_mix_weights": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "svihmm_get_mix_weights": (_i, [_vp, _vp, _i, _vp]),
     "svihmm_destroy": (_i, [_vp]),
     "svihmm_emit_param_len": (C.c_size_t, [_vp]),
     "svihmm_stats_len": (C.c_size_t, [_vp]),

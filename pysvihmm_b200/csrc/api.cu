@@ -81,8 +81,10 @@ template <typename Tp> static cudaError_t dalloc(Tp** p, size_t n) {
   return cudaMalloc((void**)p, (n ? n : 1) * sizeof(Tp));
 }
 
-extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kind) {
+static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int C) {
   if (!out) return fail(SVIHMM_EINVAL, "out is NULL");
+  if (C < 1 || C > 64) return fail(SVIHMM_EINVAL, "mixture components C = %d must be in 1..64", C);
+  if (C > 1 && kind == SVIHMM_EMIT_CATEGORICAL) return fail(SVIHMM_EUNSUPPORTED, "mixtures of categorical emissions");
   if (K < 1 || D < 1) return fail(SVIHMM_EINVAL, "K (%d) and D (%d) must be >= 1", K, D);
   if (kind != SVIHMM_EMIT_NIW_FULL && kind != SVIHMM_EMIT_NIW_DIAG && kind != SVIHMM_EMIT_CATEGORICAL)
     return fail(SVIHMM_EINVAL, "unknown emission kind %d", kind);
@@ -97,23 +99,34 @@ extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kin
   CU(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
+  c->C = C; c->KE = K * C;
+  const size_t KE = (size_t)c->KE;
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : (kind == SVIHMM_EMIT_NIW_DIAG ? D : 0);
   c->OD = kind == SVIHMM_EMIT_CATEGORICAL ? 1 : D;
   c->plen = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)D + (size_t)D * D + 2
           : (kind == SVIHMM_EMIT_NIW_DIAG ? (size_t)4 * D : (size_t)D);
   c->nfeat = K + 1 + D + c->DD;
-  c->slen = (size_t)K * K + K + (size_t)K * D + (size_t)K * c->DD + K + 4;
+  c->slen = (size_t)K * K + KE + KE * D + KE * c->DD + K + 4;
   const size_t KK = (size_t)K * K;
-  const size_t rs = kind == SVIHMM_EMIT_NIW_FULL ? (size_t)K * D * (D + 1) / 2 : (size_t)K * D;
-  CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, K * c->plen));
-  CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, K * c->plen));
+  const size_t rs = kind == SVIHMM_EMIT_NIW_FULL ? KE * D * (D + 1) / 2 : KE * D;
+  CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, KE * c->plen));
+  CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, KE * c->plen));
+  CU(dalloc(&c->omega, KE)); CU(dalloc(&c->omega_prior, KE)); CU(dalloc(&c->lw, KE));
   CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
-  CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * (size_t)K * D));
-  CU(dalloc(&c->par2, 2 * (size_t)K * D)); CU(dalloc(&c->ckp, (size_t)K));
-  CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, (size_t)K * D)); CU(dalloc(&c->ck, (size_t)K));
+  CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * KE * D));
+  CU(dalloc(&c->par2, 2 * KE * D)); CU(dalloc(&c->ckp, KE));
+  CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, KE * D)); CU(dalloc(&c->ck, KE));
   CU(dalloc(&c->stage_stats, c->slen));
   *out = c;
   return SVIHMM_OK;
+}
+
+extern "C" int svihmm_create(svihmm_ctx** out, int device, int K, int D, int kind) {
+  return create_impl(out, device, K, D, kind, 1);
+}
+
+extern "C" int svihmm_create_mix(svihmm_ctx** out, int device, int K, int D, int kind, int C) {
+  return create_impl(out, device, K, D, kind, C);
 }
 
 static void sg_teardown(svihmm_ctx* c);
@@ -133,7 +146,8 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
   void* ptrs[] = {c->W, c->vinit, c->emit, c->prior_tran, c->prior_init, c->prior_emit, c->Pt, c->PtT,
                   c->pi0, c->lu, c->rowsum, c->ckc, c->par2, c->ckp, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
-                  c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws};
+                  c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
+                  c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -217,7 +231,7 @@ extern "C" int svihmm_set_prior(svihmm_ctx* c, const double* prior_tran, const d
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if ((rc = copy_in(c->prior_tran, prior_tran, sizeof(double) * c->K * c->K, loc, st))) return rc;
-  if ((rc = copy_in(c->prior_emit, prior_emit, sizeof(double) * c->K * c->plen, loc, st))) return rc;
+  if ((rc = copy_in(c->prior_emit, prior_emit, sizeof(double) * c->KE * c->plen, loc, st))) return rc;
   if (prior_init) { if ((rc = copy_in(c->prior_init, prior_init, sizeof(double) * c->K, loc, st))) return rc; }
   else {
     double* ones = (double*)malloc(sizeof(double) * c->K);
@@ -237,13 +251,17 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   GlobalArgs ga;
   ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; ga.mode = mode;
   ga.user_init = c->user_init; ga.plen = c->plen;
+  ga.KE = c->KE; ga.C = c->C; ga.omega = c->omega; ga.omega_prior = c->omega_prior; ga.lw = c->lw;
   ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
   ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
   ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
   ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
   ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck; ga.par2 = c->par2; ga.ckp = c->ckp;
-  const int nblk = ga.diag ? std::max(1, std::min(K, (K * D + 255) / 256)) : K;   // full / categorical: one block per state
+  const int KE = c->KE;
+  if (c->C > 1 && mode != GM_PREP && mode != GM_SVI) return fail(SVIHMM_EUNSUPPORTED, "mixture emissions support the SVI update only");
+  if (c->C > 1 && !c->have_mix) return fail(SVIHMM_ESTATE, "svihmm_set_mix_weights has not been called");
+  const int nblk = ga.diag ? std::max(1, std::min(KE, (KE * D + 255) / 256)) : KE;   // full / categorical: one block per component
   size_t smem = (2 * (size_t)K + 2) * sizeof(double);
   if (!ga.diag && !ga.cat) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -254,7 +272,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
     PhaseTimer pt(c, PH_UPDATE, st);
     // K*K digamma threads + one warp for the stationary vector
     const int nthr = std::min(512, ((K * K + 31) / 32) * 32 + 32);
-    k_global_step<<<1 + nblk, std::max(nthr, 128), smem, st>>>(ga, nblk);
+    k_global_step<<<1 + nblk + (c->C > 1 ? 1 : 0), std::max(nthr, 128), smem, st>>>(ga, nblk);
     LAUNCHED(c);
   }
   if (gdbg) {
@@ -276,11 +294,37 @@ extern "C" int svihmm_set_globals(svihmm_ctx* c, const double* var_tran, const d
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if ((rc = copy_in(c->W, var_tran, sizeof(double) * c->K * c->K, loc, st))) return rc;
-  if ((rc = copy_in(c->emit, emit, sizeof(double) * c->K * c->plen, loc, st))) return rc;
+  if ((rc = copy_in(c->emit, emit, sizeof(double) * c->KE * c->plen, loc, st))) return rc;
   c->user_init = var_init != nullptr;
   if (var_init && (rc = copy_in(c->vinit + c->K, var_init, sizeof(double) * c->K, loc, st))) return rc;
   c->have_globals = 1;
+  if (c->C > 1 && !c->have_mix) return SVIHMM_OK;      // constants are derived once the mixture weights arrive
   return run_global(c, GM_PREP, nullptr, 0.0, 0.0, 0.0, st);
+}
+
+extern "C" int svihmm_set_mix_weights(svihmm_ctx* c, const double* omega, const double* omega_prior,
+                                      int loc, void* stream) {
+  if (!c || !omega) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (c->C < 2) return fail(SVIHMM_ESTATE, "the context was not created with svihmm_create_mix (C >= 2)");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = copy_in(c->omega, omega, sizeof(double) * c->KE, loc, st))) return rc;
+  if (omega_prior && (rc = copy_in(c->omega_prior, omega_prior, sizeof(double) * c->KE, loc, st))) return rc;
+  if (!omega_prior && !c->have_mix) return fail(SVIHMM_EINVAL, "omega_prior is required on the first call");
+  c->have_mix = 1;
+  return c->have_globals ? run_global(c, GM_PREP, nullptr, 0.0, 0.0, 0.0, st) : SVIHMM_OK;
+}
+
+extern "C" int svihmm_get_mix_weights(svihmm_ctx* c, double* omega, int loc, void* stream) {
+  if (!c || !omega) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (c->C < 2 || !c->have_mix) return fail(SVIHMM_ESTATE, "no mixture weights set");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(omega, c->omega, sizeof(double) * c->KE,
+                     loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
 }
 
 extern "C" int svihmm_get_globals(svihmm_ctx* c, double* var_tran, double* var_init, double* emit,
@@ -292,7 +336,7 @@ extern "C" int svihmm_get_globals(svihmm_ctx* c, double* var_tran, double* var_i
   const cudaMemcpyKind kd = loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (var_tran) CU(cudaMemcpyAsync(var_tran, c->W, sizeof(double) * c->K * c->K, kd, st));
   if (var_init) CU(cudaMemcpyAsync(var_init, c->vinit, sizeof(double) * c->K, kd, st));
-  if (emit) CU(cudaMemcpyAsync(emit, c->emit, sizeof(double) * c->K * c->plen, kd, st));
+  if (emit) CU(cudaMemcpyAsync(emit, c->emit, sizeof(double) * c->KE * c->plen, kd, st));
   if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
   return SVIHMM_OK;
 }
@@ -362,7 +406,7 @@ static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st
 static int pipe_nte(const svihmm_ctx* c) { return 2 * ((c->D + 7) / 8) + 1; }
 static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
   static const bool off = getenv("SVIHMM_NO_PIPE") != nullptr;
-  if (off || c->K > 32 || c->kind != SVIHMM_EMIT_NIW_DIAG || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  if (off || c->K > 32 || c->C > 1 || c->kind != SVIHMM_EMIT_NIW_DIAG || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
   const int nte = pipe_nte(c);
   if (nte > 5 || (c->K > 16 && nte > 3)) return false;
   const PipeSmem L = pipe_smem_layout(T, c->K, c->D, c->D, 1);
@@ -377,7 +421,7 @@ static bool pipe_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* sm
 // Single-kernel E-step (fused.cuh) when the window fits in shared memory: K <= 32, the three
 // T*K float tables + per-row scalars + emission constants <= the opt-in limit.
 static bool fused_eligible(const svihmm_ctx* c, int T, unsigned flags, size_t* smem_out) {
-  if (c->K > 32 || c->kind == SVIHMM_EMIT_CATEGORICAL || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
+  if (c->K > 32 || c->C > 1 || c->kind == SVIHMM_EMIT_CATEGORICAL || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS))) return false;
   const int diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
   const int tri = diag ? c->D : c->D * (c->D + 1) / 2;
   const FusedSmem L = fused_smem_layout(T, c->K, c->D, tri, diag);
@@ -463,6 +507,60 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
   return SVIHMM_OK;
 }
 
+// launch k_stats for one column range with row splits sized for ~4 CTAs per SM; returns nsplit
+static int launch_kstats(svihmm_ctx* c, StatsArgs a, int Kleft, int n_lo, int n_hi, float** part, size_t* cap,
+                         int64_t* nsplit_out, cudaStream_t st) {
+  const int TM = Kleft <= 16 ? 16 : (Kleft <= 32 ? 32 : 64);
+  const int tiles_m = (Kleft + TM - 1) / TM, tiles_n = (n_hi - n_lo + ST_TN - 1) / ST_TN;
+  const int64_t chunks = (a.R + ST_RC - 1) / ST_RC;
+  int64_t nsplit = (4 * 148 + (int64_t)tiles_m * tiles_n - 1) / ((int64_t)tiles_m * tiles_n);
+  if (nsplit > chunks) nsplit = chunks;
+  if (nsplit < 1) nsplit = 1;
+  const int64_t rps = ((chunks + nsplit - 1) / nsplit) * ST_RC;
+  nsplit = (a.R + rps - 1) / rps;
+  a.rows_per_split = rps; a.n_lo = n_lo; a.n_hi = n_hi;
+  const size_t need = (size_t)nsplit * Kleft * a.N;
+  if (need > *cap) {
+    if (*part) CU(cudaFree(*part));
+    *part = nullptr; *cap = 0;
+    CU(dalloc(part, need));
+    *cap = need;
+  }
+  a.part = *part;
+  dim3 grid(tiles_n, tiles_m, (unsigned)nsplit);
+  const size_t xsm = (size_t)ST_RC * a.D * sizeof(float);
+  if (TM == 16) k_stats<16><<<grid, 256, xsm, st>>>(a);
+  else if (TM == 32) k_stats<32><<<grid, 256, xsm, st>>>(a);
+  else k_stats<64><<<grid, 256, xsm, st>>>(a);
+  LAUNCHED(c);
+  *nsplit_out = nsplit;
+  return SVIHMM_OK;
+}
+
+// Mixture statistics: transitions from q, NIW statistics of the K*C components weighted by
+// q[t,k] * resp[t,k,c] (util.py:73-83 with the responsibilities of labels.py:52-65).
+static int stats_mix(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask, const int64_t* starts,
+                     int B, int T, const float* q, double* stats_out, unsigned flags, cudaStream_t st) {
+  const int K = c->K, KE = c->KE, D = c->D;
+  const int64_t R = (int64_t)B * T;
+  k_mix_weights<<<(unsigned)((R * KE + 255) / 256), 256, 0, st>>>(R * KE, c->C, q, c->resp_ws, c->wq_ws);
+  LAUNCHED(c);
+  StatsArgs a;
+  a.B = B; a.T = T; a.D = D; a.DD = c->DD; a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.cat = 0; a.R = R;
+  a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
+  int64_t nsT = 0, nsE = 0;
+  int rc;
+  a.K = K; a.N = K; a.left = q; a.next = q; a.wrap = (flags & SVIHMM_WRAP) ? 1 : 0;
+  if ((rc = launch_kstats(c, a, K, 0, K, &c->part_ws, &c->cap_part, &nsT, st))) return rc;
+  a.K = KE; a.N = KE + 1 + D + c->DD; a.left = c->wq_ws; a.next = c->wq_ws; a.wrap = 0;
+  if ((rc = launch_kstats(c, a, KE, KE, a.N, &c->part2_ws, &c->cap_part2, &nsE, st))) return rc;
+  k_stats_finalize_mix<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+      B, T, K, KE, D, c->DD, (int)nsT, (int)nsE, c->part_ws, c->part2_ws, q, c->seq_ws, c->prior_tran,
+      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
 static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                       const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
                       unsigned flags, cudaStream_t st) {
@@ -477,15 +575,31 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   if (rc) return rc;
   const int64_t R = (int64_t)B * T;
   const int mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
-  // K1: expected log-likelihoods (fp64) -> scaled likelihoods b (fp32) + row maxima
+  // K1: expected log-likelihoods (fp64) -> scaled likelihoods b (fp32) + row maxima.  Mixtures:
+  // the K*C component log-likelihoods first, then the per-state logsumexp + responsibilities.
+  const bool mix = c->C > 1;
+  if (mix && xi) return fail(SVIHMM_EUNSUPPORTED, "SVIHMM_EXACT_XI with mixture emissions");
+  if (mix) {
+    const size_t rows = (size_t)B * T;
+    if (rows > c->cap_rows_mix) {
+      void* olds[] = {c->ell_ws, c->resp_ws, c->wq_ws};
+      for (void* p : olds) if (p) CU(cudaFree(p));
+      c->ell_ws = nullptr; c->resp_ws = nullptr; c->wq_ws = nullptr; c->cap_rows_mix = 0;
+      CU(dalloc(&c->ell_ws, rows * c->KE)); CU(dalloc(&c->resp_ws, rows * c->KE)); CU(dalloc(&c->wq_ws, rows * c->KE));
+      c->cap_rows_mix = rows;
+    }
+  }
   { PhaseTimer pt(c, PH_EMIT, st);
+  const int Ke = c->KE;                                   // emission components (= K without mixtures)
+  double* ll_out = mix ? c->ell_ws : c->ll_ws;
+  float* b_out = mix ? nullptr : c->b_ws;
   if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {
     // register-blocked float64 kernel with the row maximum and b = exp(ll - max) fused in
     const unsigned grid = (unsigned)((R + 2 * ERB_NT - 1) / (2 * ERB_NT));
 #define ERB_LAUNCH(DV) do { \
       const size_t smem = (size_t)ERB_KC * (erb_len(DV) + DV + (DV & 1)) * sizeof(double); \
-      k_emit_full_rb<DV><<<grid, ERB_NT, smem, st>>>(R, T, K, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, \
-                                                     c->ck, c->ll_ws, c->b_ws, c->mx_ws); } while (0)
+      k_emit_full_rb<DV><<<grid, ERB_NT, smem, st>>>(R, T, Ke, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, \
+                                                     c->ck, ll_out, b_out, c->mx_ws); } while (0)
     if (D == 8) ERB_LAUNCH(8); else if (D == 16) ERB_LAUNCH(16); else ERB_LAUNCH(32);
 #undef ERB_LAUNCH
     LAUNCHED(c);
@@ -501,17 +615,26 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the emission kernel", D);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_emit_full<<<(unsigned)((R + EMIT_ROWS - 1) / EMIT_ROWS), EMIT_ROWS, smem, st>>>(
-        B, T, K, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, c->ll_ws);
+        B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
   } else {
-    const size_t smem = 2 * (size_t)K * D * sizeof(double);
-    if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "K*D = %d too large for the diagonal emission kernel", K * D);
+    const size_t smem = 2 * (size_t)Ke * D * sizeof(double);
+    if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "K*D = %d too large for the diagonal emission kernel", Ke * D);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_emit_diag<<<(unsigned)((R * K + 255) / 256), 256, smem, st>>>(
-        B, T, K, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, c->ll_ws);
+    k_emit_diag<<<(unsigned)((R * Ke + 255) / 256), 256, smem, st>>>(
+        B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
   }
   LAUNCHED(c);
-  k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
-  LAUNCHED(c);
+  if (!mix) {
+    k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
+    LAUNCHED(c);
+  }
+  }
+  if (mix) {
+    k_mix_combine<<<(unsigned)((R * K + 255) / 256), 256, 0, st>>>(B, T, K, c->C, D, obs, dtype, mask, starts, mask_ll,
+                                                                c->lw, c->ell_ws, c->ll_ws, c->resp_ws);
+    LAUNCHED(c);
+    k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
+    LAUNCHED(c);
   }
   }
   // K2/K3: forward, backward + marginals
@@ -530,6 +653,10 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
       LAUNCHED(c); }
     PhaseTimer pt_stats(c, PH_STATS, st);
+    if (mix) {
+      c->last_B = B; c->last_T = T; c->last_fused = 1;
+      return stats_mix(c, obs, dtype, mask, starts, B, T, q, stats_out, flags, st);
+    }
     StatsSymArgs sa;
     sa.B = B; sa.T = T; sa.K = K; sa.D = D; sa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
     sa.NF = K + 1 + D + (sa.diag ? D : D * (D + 1) / 2);
@@ -585,6 +712,10 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   PhaseTimer pt_stats(c, PH_STATS, st);
   k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
   LAUNCHED(c);
+  if (mix) {
+    c->last_B = B; c->last_T = T; c->last_fused = 0;
+    return stats_mix(c, obs, dtype, mask, starts, B, T, q, stats_out, flags, st);
+  }
   // K4: statistics
   StatsArgs a;
   a.B = B; a.T = T; a.K = K; a.D = D; a.DD = c->DD; a.N = c->nfeat;

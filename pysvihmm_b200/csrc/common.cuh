@@ -15,12 +15,15 @@
 struct svihmm_ctx {
   int device, K, D, kind, KP;
   int OD;         // columns of the observation series: D, or 1 for categorical symbols
+  int C, KE;      // mixture components per state (1 = plain emissions) and emission components K*C
   size_t plen;    // doubles per state in the packed emission parameters
   size_t slen;    // doubles in the packed statistics
   int nfeat;      // columns of the statistics contraction: K + 1 + D + DD
   int DD;         // D*D (full) or D (diag)
   // master copies of the global variational parameters and priors (device, f64)
   double *W, *vinit, *emit, *prior_tran, *prior_init, *prior_emit;
+  double *omega, *omega_prior, *lw;   // mixtures: Dirichlet weights (KE), their prior, E[ln pi] (KE)
+  int have_mix;
   int user_init, have_globals, have_prior;
   // derived per-global-step constants
   float *Pt, *PtT, *pi0;          // exp(E[log A]) row-major, its transpose, exp(E[log pi])
@@ -51,6 +54,7 @@ struct svihmm_ctx {
   // workspaces
   size_t cap_rows, cap_B, cap_part;
   double *ll_ws, *mx_ws, *seq_ws, *lt_ws;
+  double* ell_ws; float *resp_ws, *wq_ws, *part2_ws; size_t cap_rows_mix, cap_part2;   // mixture workspaces
   int* e_ws;
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
   size_t hostq_cap;

@@ -106,6 +106,51 @@ k_emit_cat(int B, int T, int K, int C, const void* __restrict__ obs, int dtype,
   ll[e] = dead ? 0.0 : logp[(size_t)k * C + (int)x];
 }
 
+// Mixture emissions (EXTENSION, BASELINE config 5): state k emits from C components with expected
+// log-weights lw[k*C + c] = E[ln pi_kc].  From the component expected log-likelihoods ell[r][k*C+c]
+// (distributions.py:351-366, computed by the kernels above with K*C "states"):
+//     ll[r][k]    = logsumexp_c( lw[kc] + ell[r][kc] )          (labels.py:52-65: logr, then softmax)
+//     resp[r][kc] = exp( lw[kc] + ell[r][kc] - ll[r][k] )
+// A row without evidence (NaN, or masked with mask_ll) has ell = 0 for every component and gets
+// ll = 0 (np.nan_to_num, hmmsgd_metaobs.py:508-509).  One thread per (row, state).
+__global__ void __launch_bounds__(256)
+k_mix_combine(int B, int T, int K, int C, int D, const void* __restrict__ obs, int dtype,
+              const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+              const double* __restrict__ lw, const double* __restrict__ ell, double* __restrict__ ll,
+              float* __restrict__ resp) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t R = (int64_t)B * T;
+  if (e >= R * K) return;
+  const int64_t r = e / K; const int k = (int)(e - r * K);
+  const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+  const int64_t gi = starts[b] + t;
+  bool dead = mask_ll && mask && mask[gi];
+  for (int d = 0; d < D; ++d) dead |= isnan(ld_obs(obs, dtype, gi * D + d));
+  const double* ep = ell + (r * K + k) * C;
+  const double* lp = lw + (size_t)k * C;
+  float* rp = resp + (r * K + k) * C;
+  if (dead) {
+    ll[e] = 0.0;
+    for (int c = 0; c < C; ++c) rp[c] = 0.f;
+    return;
+  }
+  double m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmax(m, lp[c] + ep[c]);
+  double s = 0.0;
+  for (int c = 0; c < C; ++c) s += exp(lp[c] + ep[c] - m);
+  const double l = m + log(s);
+  ll[e] = l;
+  for (int c = 0; c < C; ++c) rp[c] = (float)exp(lp[c] + ep[c] - l);
+}
+
+// statistics weights of the components: wq[r][kc] = q[r][k] * resp[r][kc]
+__global__ void __launch_bounds__(256)
+k_mix_weights(int64_t n, int C, const float* __restrict__ q, const float* __restrict__ resp,
+              float* __restrict__ wq) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) wq[e] = q[e / C] * resp[e];
+}
+
 // b[r][k] = exp(ll[r][k] - max_k ll[r][k]) (fp32), mx[r] = the max (fp64).
 // One warp per row, lanes stride over k.
 __global__ void __launch_bounds__(256)

@@ -16,6 +16,8 @@ enum { GM_PREP = 0, GM_SVI = 1, GM_BATCH = 2, GM_BSGD = 3 };   // BSGD: hmmbatch
 
 struct GlobalArgs {
   int K, D, DD, diag, cat, mode, user_init;
+  int KE, C;                                // emission components K*C, components per state
+  double *omega, *omega_prior, *lw;         // mixtures only
   size_t plen;
   double *W, *vinit, *emit;                 // vinit: [0,K) the vector in use, [K,2K) the user-given one
   const double *prior_tran, *prior_init, *prior_emit, *stats;
@@ -48,9 +50,9 @@ __device__ __noinline__ double digamma_fast(double x) {
 }
 
 struct GStats { const double *A, *n, *sx, *sxx, *q0; };
-__device__ inline GStats gstats(const double* s, int K, int D, int DD) {
+__device__ inline GStats gstats(const double* s, int K, int KE, int D, int DD) {
   GStats v;
-  v.A = s; v.n = s + (size_t)K * K; v.sx = v.n + K; v.sxx = v.sx + (size_t)K * D; v.q0 = v.sxx + (size_t)K * DD;
+  v.A = s; v.n = s + (size_t)K * K; v.sx = v.n + KE; v.sxx = v.sx + (size_t)KE * D; v.q0 = v.sxx + (size_t)KE * DD;
   return v;
 }
 
@@ -105,7 +107,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
 #define GSTAMP(i) do { if (a.dbg && tid == 0) a.dbg[i] = clock64(); } while (0)
   GSTAMP(0);
   const int KK = K * K;
-  const GStats sv = gstats(a.stats, K, a.D, a.DD);
+  const GStats sv = gstats(a.stats, K, a.KE, a.D, a.DD);
   if (a.mode == GM_SVI || a.mode == GM_BSGD) {
 #pragma unroll 1
     for (int i = tid; i < KK; i += nth) a.W[i] = (1.0 - a.lrate) * (a.W[i] - 1.0) + a.lrate * a.bA * sv.A[i] + 1.0;
@@ -237,7 +239,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
 __device__ void global_emit_full_block(const GlobalArgs& a, const int k, double* sm) {
   const int K = a.K, D = a.D, tid = threadIdx.x, nth = blockDim.x;
   double* L = sm; double* Ri = sm + D * D; double* mu_o = Ri + D * D; double* mu_p = mu_o + D; double* mu_n = mu_p + D;
-  const GStats sv = gstats(a.stats, K, D, a.DD);
+  const GStats sv = gstats(a.stats, K, a.KE, D, a.DD);
   double* p = a.emit + (size_t)k * a.plen;
   const double* pr = a.prior_emit + (size_t)k * a.plen;
   const size_t oS = D, oK = (size_t)D + (size_t)D * D, oN = oK + 1;
@@ -346,9 +348,10 @@ __device__ void global_emit_full_block(const GlobalArgs& a, const int k, double*
 // diagonal (D independent 1-D NIWs per state): one thread per (k, d), all states in one block sweep
 __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const int nblk) {
   const int K = a.K, D = a.D, tid = threadIdx.x, nth = blockDim.x;
-  const GStats sv = gstats(a.stats, K, D, a.DD);
+  const GStats sv = gstats(a.stats, K, a.KE, D, a.DD);
   // block b owns states [k0, k1): whole states per block so that ck can be summed locally
-  const int per = (K + nblk - 1) / nblk, k0 = blk * per, k1 = min(K, k0 + per);
+  const int KE = a.KE;
+  const int per = (KE + nblk - 1) / nblk, k0 = blk * per, k1 = min(KE, k0 + per);
 #pragma unroll 1
   for (int e = k0 * D + tid; e < k1 * D; e += nth) {
     const int k = e / D, d = e - k * D;
@@ -378,8 +381,8 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
     const double rs = nu / (2.0 * sg);
     a.Rs[e] = rs;
     a.gk[e] = mu;
-    a.par2[2 * ((size_t)d * K + k)] = -rs;
-    a.par2[2 * ((size_t)d * K + k) + 1] = 2.0 * rs * mu;
+    a.par2[2 * ((size_t)d * KE + k)] = -rs;
+    a.par2[2 * ((size_t)d * KE + k) + 1] = 2.0 * rs * mu;
     a.ckc[2 * (size_t)e] = 0.5 * (digamma_fast(0.5 * nu) + M_LN2 - dlog_ni(sg)) - 1.0 / (2.0 * ka) - 0.5 * 1.8378770664093453;
     a.ckc[2 * (size_t)e + 1] = rs * mu * mu;
   }
@@ -402,7 +405,7 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
 // then logp[k][c] = psi(alpha[c]) - psi(sum_c alpha[c]) (distributions.py:1383-1386) into Rs.
 __device__ void global_emit_cat_block(const GlobalArgs& a, const int k, double* sm) {
   const int K = a.K, C = a.D, tid = threadIdx.x, nth = blockDim.x;
-  const GStats sv = gstats(a.stats, K, C, 0);
+  const GStats sv = gstats(a.stats, K, K, C, 0);
   double* p = a.emit + (size_t)k * C;
   const double* pr = a.prior_emit + (size_t)k * C;
   if (a.mode != GM_PREP) {
@@ -432,10 +435,36 @@ __device__ void global_emit_cat_block(const GlobalArgs& a, const int k, double* 
   for (int c = tid; c < C; c += nth) a.Rs[(size_t)k * C + c] = digamma_d(p[c]) - dgs;
 }
 
+// mixture weights (EXTENSION, BASELINE config 5): Dirichlet(omega_k) over the C components of state k.
+//   SVI  omega <- (1-rho)(omega-1) + rho (omega0 - 1 + bE n_kc) + 1   (the transition-row rule
+//        hmmsgd_metaobs.py:1029-1045 applied to the component counts)
+// then lw[kc] = psi(omega_kc) - psi(sum_c omega_kc) (pybasicbayes/internals/labels.py:59,
+// distributions.py:1383-1386).
+__device__ void global_mix_block(const GlobalArgs& a) {
+  const int K = a.K, C = a.C, KE = a.KE, tid = threadIdx.x, nth = blockDim.x;
+  const GStats sv = gstats(a.stats, K, KE, a.D, a.DD);
+  if (a.mode == GM_SVI) {
+#pragma unroll 1
+    for (int e = tid; e < KE; e += nth)
+      a.omega[e] = (1.0 - a.lrate) * (a.omega[e] - 1.0) + a.lrate * (a.omega_prior[e] - 1.0 + a.bE * sv.n[e]) + 1.0;
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (int k = tid; k < K; k += nth) {
+    double s = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) s += a.omega[k * C + c];
+    const double dgs = digamma_d(s);
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) a.lw[k * C + c] = digamma_d(a.omega[k * C + c]) - dgs;
+  }
+}
+
 // grid: 1 + (diag ? nblk_diag : K) blocks.
 __global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a, const int nblk_emit) {
   extern __shared__ double gsm[];
   if (blockIdx.x == 0) global_tran_block(a, gsm);
+  else if ((int)blockIdx.x == 1 + nblk_emit) global_mix_block(a);
   else if (a.cat) global_emit_cat_block(a, blockIdx.x - 1, gsm);
   else if (a.diag) {
     if (a.dbg && threadIdx.x == 0) a.dbg[4] = clock64();

@@ -171,3 +171,37 @@ k_stats_finalize(int B, int T, int K, int D, int DD, int N, int nsplit, const fl
   }
   out[idx] = v;
 }
+
+// Mixture layout: transition partials partT [nsplitT][K][K] and component partials
+// partE [nsplitE][KE][NE] (NE = KE + 1 + D + DD, columns < KE unused) ->
+// [ A (K*K) | n (KE) | sx (KE*D) | sxx (KE*DD) | q0 (K) | tail ].
+__global__ void __launch_bounds__(256)
+k_stats_finalize_mix(int B, int T, int K, int KE, int D, int DD, int nsplitT, int nsplitE,
+                     const float* __restrict__ partT, const float* __restrict__ partE,
+                     const float* __restrict__ q, const double* __restrict__ seq,
+                     const double* __restrict__ prior_tran, int add_prior, double* __restrict__ out, size_t slen) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= slen) return;
+  const int NE = KE + 1 + D + DD;
+  const size_t o_n = (size_t)K * K, o_sx = o_n + KE, o_sxx = o_sx + (size_t)KE * D,
+               o_q0 = o_sxx + (size_t)KE * DD, o_tail = o_q0 + K;
+  double v = 0.0;
+  if (idx < o_n) {
+    for (int z = 0; z < nsplitT; ++z) v += (double)partT[(size_t)z * K * K + idx];
+    if (add_prior) v += (double)B * (prior_tran[idx] - 1.0);
+  } else if (idx < o_q0) {
+    int m, n;
+    if (idx < o_sx) { m = (int)(idx - o_n); n = KE; }
+    else if (idx < o_sxx) { const size_t e = idx - o_sx; m = (int)(e / D); n = KE + 1 + (int)(e % D); }
+    else { const size_t e = idx - o_sxx; m = (int)(e / DD); n = KE + 1 + D + (int)(e % DD); }
+    for (int z = 0; z < nsplitE; ++z) v += (double)partE[((size_t)z * KE + m) * NE + n];
+  } else if (idx < o_tail) {
+    const int k = (int)(idx - o_q0);
+    for (int b = 0; b < B; ++b) v += (double)q[(size_t)b * T * K + k];
+  } else {
+    const int tt = (int)(idx - o_tail);
+    if (tt < 2) for (int b = 0; b < B; ++b) v += seq[2 * b + tt];
+    else if (tt == 2) v = (double)B;
+  }
+  out[idx] = v;
+}

@@ -131,6 +131,7 @@ k_emit_full_rb(int64_t R, int T, int K, const void* __restrict__ obs, int dtype,
       }
     }
   }
+  if (!bout) return;                              // mixtures: only the component log-likelihoods are wanted
   // b = exp(ll - max): this thread re-reads the rows it has just written (L1/L2 hits)
   const int64_t rr[2] = {r0, r1};
   const double mm[2] = {m0, m1};

@@ -192,6 +192,24 @@ class Categorical(object):
         return p_avgengy + q_entropy
 
 
+class MixtureDistribution(object):
+    """EXTENSION (BASELINE config 5): a mixture of NIW Gaussians used as the emission of one HMM
+    state, with the attribute surface of pybasicbayes.models.MixtureDistribution (models.py:256-300:
+    `components`, `weights` = a Categorical).  The reference class has Gibbs/EM methods only; the
+    mean-field E-step / statistics / natural-gradient step run in the engine (svihmm_create_mix)."""
+
+    def __init__(self, components, weights=None, alpha_0=None):
+        self.components = list(components)
+        C = len(self.components)
+        self.weights = weights if weights is not None else Categorical(
+            weights=np.ones(C) / C, alphav_0=np.ones(C) * (1. if alpha_0 is None else float(alpha_0) / C),
+            alpha_mf=np.ones(C))
+        self.kind = self.components[0].kind
+
+    def get_vlb(self):
+        return self.weights.get_vlb() + sum(c.get_vlb() for c in self.components)
+
+
 def _iw_logpartition(sigma, nu):
     D = sigma.shape[0]
     chol = np.linalg.cholesky(sigma)

@@ -54,7 +54,7 @@ class EStepEngine(object):
     (hmmbatchcd.py:172-189).
     """
 
-    def __init__(self, K, D, emission="niw_full", device=None):
+    def __init__(self, K, D, emission="niw_full", device=None, components=1):
         if not torch.cuda.is_available():
             raise L.SvihmmError("pysvihmm_b200 needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -63,7 +63,13 @@ class EStepEngine(object):
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
             if not isinstance(device, torch.device) else device
         h = C.c_void_p()
-        L.check(self.lib.svihmm_create(C.byref(h), self.device.index, self.K, self.D, _KINDS[emission]))
+        self.C = int(components)                 # mixture components per state (EXTENSION, config 5)
+        self.KE = self.K * self.C                # emission components: rows of the emission arrays
+        if self.C > 1:
+            L.check(self.lib.svihmm_create_mix(C.byref(h), self.device.index, self.K, self.D, _KINDS[emission],
+                                               self.C))
+        else:
+            L.check(self.lib.svihmm_create(C.byref(h), self.device.index, self.K, self.D, _KINDS[emission]))
         self._h = h
         self.plen = int(self.lib.svihmm_emit_param_len(h))
         self.slen = int(self.lib.svihmm_stats_len(h))
@@ -127,20 +133,33 @@ class EStepEngine(object):
     # ------------------------------------------------------------------ parameters
     def set_prior(self, prior_tran, prior_emit, prior_init=None):
         pt, pe = _f64(prior_tran), _f64(prior_emit)
-        assert pt.shape == (self.K, self.K) and pe.size == self.K * self.plen
+        assert pt.shape == (self.K, self.K) and pe.size == self.KE * self.plen
         pi = None if prior_init is None else _f64(prior_init)
         L.check(self.lib.svihmm_set_prior(self._h, _ptr(pt), _ptr(pi), _ptr(pe), L.LOC_HOST, self._stream()))
 
     def set_globals(self, var_tran, emit, var_init=None):
         vt, em = _f64(var_tran), _f64(emit)
-        assert vt.shape == (self.K, self.K) and em.size == self.K * self.plen
+        assert vt.shape == (self.K, self.K) and em.size == self.KE * self.plen
         vi = None if var_init is None else _f64(var_init)
         L.check(self.lib.svihmm_set_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
 
     def get_globals(self):
-        vt = np.empty((self.K, self.K)); vi = np.empty(self.K); em = np.empty((self.K, self.plen))
+        vt = np.empty((self.K, self.K)); vi = np.empty(self.K); em = np.empty((self.KE, self.plen))
         L.check(self.lib.svihmm_get_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
         return vt, vi, em
+
+    def set_mix_weights(self, omega, omega_prior=None):
+        """Dirichlet parameters (K, C) of the mixture weights and, on the first call, their prior.
+        Call before set_globals."""
+        om = _f64(omega)
+        assert om.size == self.KE
+        op = None if omega_prior is None else _f64(omega_prior)
+        L.check(self.lib.svihmm_set_mix_weights(self._h, _ptr(om), _ptr(op), L.LOC_HOST, self._stream()))
+
+    def get_mix_weights(self):
+        om = np.empty((self.K, self.C))
+        L.check(self.lib.svihmm_get_mix_weights(self._h, _ptr(om), L.LOC_HOST, self._stream()))
+        return om
 
     # ------------------------------------------------------------------ the hot path
     def new_stats(self):
@@ -259,20 +278,20 @@ class EStepEngine(object):
     # ------------------------------------------------------------------ packing helpers
     def unpack_stats(self, stats):
         s = stats.detach().cpu().numpy() if isinstance(stats, torch.Tensor) else np.asarray(stats)
-        K, D, DD = self.K, self.D, self.DD
+        K, D, DD, KE = self.K, self.D, self.DD, self.KE
         o = 0
         out = {}
         out["A"] = s[o:o + K * K].reshape(K, K); o += K * K
-        out["n"] = s[o:o + K]; o += K
-        out["sx"] = s[o:o + K * D].reshape(K, D); o += K * D
-        out["sxx"] = s[o:o + K * DD].reshape({"niw_full": (K, D, D), "niw_diag": (K, D), "categorical": (K, 0)}[self.emission]); o += K * DD
+        out["n"] = s[o:o + KE]; o += KE
+        out["sx"] = s[o:o + KE * D].reshape(KE, D); o += KE * D
+        out["sxx"] = s[o:o + KE * DD].reshape({"niw_full": (KE, D, D), "niw_diag": (KE, D), "categorical": (KE, 0)}[self.emission]); o += KE * DD
         out["q0"] = s[o:o + K]; o += K
         out["logZ"], out["lb_q4"], out["B"] = float(s[o]), float(s[o + 1]), int(round(s[o + 2]))
         return out
 
     def pack_emit(self, mu, sigma, kappa, nu):
         """(K,D), (K,D,D)|(K,D), (K,)|(K,D), (K,)|(K,D) -> (K, plen) float64."""
-        K, D = self.K, self.D
+        K, D = self.KE, self.D
         if self.emission == "categorical":              # mu = alpha_mf (K, C); the rest is ignored
             return _f64(mu).reshape(K, D).copy()
         out = np.empty((K, self.plen))
@@ -290,7 +309,7 @@ class EStepEngine(object):
         return out
 
     def unpack_emit(self, em):
-        K, D = self.K, self.D
+        K, D = self.KE, self.D
         em = np.asarray(em).reshape(K, self.plen)
         if self.emission == "categorical":
             return dict(alpha=em.copy())

@@ -91,6 +91,9 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
     def _ensure_engine(self):
         from .engine import EStepEngine
         cat = self.emission_kind == "categorical"
+        comps = getattr(self.var_emit[0], "components", None)
+        if comps is not None:
+            return self._ensure_engine_mix()
         if self._engine is None and cat:
             C = int(self.prior_emit[0].num_parameters())
             self._engine = EStepEngine(self.K, C, "categorical", device=self._device)
@@ -128,6 +131,40 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
             self._globals_dirty = False
         return self._engine
 
+    def _flat(self, emit):
+        return [g for m in emit for g in m.components]
+
+    def _ensure_engine_mix(self):
+        """Mixture emissions: K*C component rows + Dirichlet weights (svihmm_create_mix)."""
+        from .engine import EStepEngine
+        C = len(self.var_emit[0].components)
+        kshape = () if self.emission_kind == "niw_full" else (self.D,)
+        bc = lambda v: np.broadcast_to(np.asarray(v, dtype=float), kshape)
+        if self._engine is None:
+            self._engine = EStepEngine(self.K, self.D, self.emission_kind, device=self._device, components=C)
+            pe = self._flat(self.prior_emit)
+            self._engine.set_prior(self.prior_tran, self._engine.pack_emit(
+                np.array([np.asarray(g.mu_0, dtype=float) for g in pe]),
+                np.array([np.asarray(g.sigma_0, dtype=float) for g in pe]),
+                np.array([bc(g.kappa_0) for g in pe]), np.array([bc(g.nu_0) for g in pe])), self.prior_init)
+            self._series_dirty = True
+            self._globals_dirty = True
+        if self._series_dirty:
+            obs = np.asarray(self.obs, dtype=np.float64).reshape(self.T, -1)
+            self._engine.set_series(obs, self.mask, dtype=self.obs_dtype)
+            self._series_dirty = False
+        if self._globals_dirty:
+            ve = self._flat(self.var_emit)
+            self._engine.set_mix_weights(np.array([m.weights._alpha_mf for m in self.var_emit]),
+                                         np.array([m.weights.alphav_0 for m in self.prior_emit]))
+            self._engine.set_globals(self.var_tran, self._engine.pack_emit(
+                np.array([np.asarray(g.mu_mf, dtype=float) for g in ve]),
+                np.array([np.asarray(g.sigma_mf, dtype=float) for g in ve]),
+                np.array([bc(g.kappa_mf) for g in ve]), np.array([bc(g.nu_mf) for g in ve])),
+                self.var_init if self._explicit_init else None)
+            self._globals_dirty = False
+        return self._engine
+
     def _kn_shape(self):
         return () if self.emission_kind == "niw_full" else (self.D,)
 
@@ -138,6 +175,12 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
         vt, vi, em = self._engine.get_globals()
         self.var_tran, self.var_init = vt, vi
         e = self._engine.unpack_emit(em)
+        mixed = getattr(self.var_emit[0], "components", None) is not None
+        if mixed:
+            om = self._engine.get_mix_weights()
+            for k, M in enumerate(self.var_emit):
+                M.weights._alpha_mf = om[k]
+                M.weights.weights = om[k] / om[k].sum()
         if self.emission_kind == "categorical":
             for k, G in enumerate(self.var_emit):                 # hmmsgd_metaobs.py:1083-1084
                 G._alpha_mf = e["alpha"][k]
@@ -145,7 +188,7 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
             self._host_stale = False
             return
         full = self.emission_kind == "niw_full"
-        for k, G in enumerate(self.var_emit):
+        for k, G in enumerate(self._flat(self.var_emit) if mixed else self.var_emit):
             G.mu_mf, G.sigma_mf = e["mu"][k], e["sigma"][k]
             G.kappa_mf = float(e["kappa"][k]) if full else e["kappa"][k]
             G.nu_mf = float(e["nu"][k]) if full else e["nu"][k]

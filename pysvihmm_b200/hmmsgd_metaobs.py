@@ -218,8 +218,8 @@ class VBHMM(VariationalHMMBase):
         if self.emission_kind == "categorical":         # :907-926: alpha posterior - 1 per window
             emit_inter = [np.asarray(self.prior_emit[k].alphav_0) + s["sx"][k] - 1. for k in range(self.K)]
             return s["A"], emit_inter
-        emit_inter = [[s["sx"][k], s["n"][k], s["sxx"][k], s["n"][k]] for k in range(self.K)]
-        return s["A"], emit_inter
+        emit_inter = [[s["sx"][k], s["n"][k], s["sxx"][k], s["n"][k]] for k in range(len(s["n"]))]
+        return s["A"], emit_inter      # mixtures: one entry per component, row k*C + c
 
     def global_update(self, A_inter, emit_inter=None):
         """hmmsgd_metaobs.py:1010-1069.  Accepts the packed device statistics (engine path) or the

@@ -172,3 +172,41 @@ def test_vbhmm_categorical_emissions_follow_oracle_trajectory():
     assert _rel(hmm.var_tran, var_tran) < 1e-4
     assert _rel(np.array([g._alpha_mf for g in hmm.var_emit]), np.array([e["alpha"] for e in emit])) < 1e-4
     assert abs(sum(hmm.var_emit[0].weights) - 1.) < 1e-12
+
+
+def test_vbhmm_gmm_emissions_follow_oracle_trajectory():
+    """hmmsgd_metaobs.VBHMM with MixtureDistribution emission objects (EXTENSION, BASELINE config 5):
+    two natural-gradient steps against the oracle."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    from pysvihmm_b200.distributions import Categorical, Gaussian, MixtureDistribution
+    from tests.helpers import make_random_problem
+    K, C, D, Lh, S, maxit, seed = 3, 2, 2, 8, 4, 2, 5
+    p = make_random_problem(seed=4, K=K * C, D=D, T_full=300, kind="niw_full", miss=0.1, sep=0.8)
+    rs = np.random.RandomState(1)
+    om, om0 = 1. + 3. * rs.rand(K, C), 0.5 + rs.rand(K, C)
+    objs = []
+    for k in range(K):
+        comps = [Gaussian(mu=e["mu"].copy(), sigma=e["sigma"].copy(), mu_0=pe["mu"], sigma_0=pe["sigma"],
+                          kappa_0=pe["kappa"], nu_0=pe["nu"], kappa_mf=e["kappa"], nu_mf=e["nu"])
+                 for e, pe in zip(p["emit"][k * C:(k + 1) * C], p["prior_emit"][k * C:(k + 1) * C])]
+        objs.append(MixtureDistribution(comps, Categorical(weights=np.ones(C) / C, alphav_0=om0[k].copy(),
+                                                           alpha_mf=om[k].copy())))
+    var_tran = 1. + 5. * rs.rand(K, K)
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), np.array(objs, dtype=object), tau=1., kappa=0.7,
+                  metaobs_half=Lh, mb_sz=S, mask=p["mask"], init_tran=var_tran.copy(), maxit=maxit, seed=seed,
+                  track_elbo=False)
+    hmm.infer()
+    np.random.seed(seed)
+    emit = [dict(omega=om[k], comps=p["emit"][k * C:(k + 1) * C]) for k in range(K)]
+    prior = [dict(omega=om0[k], comps=p["prior_emit"][k * C:(k + 1) * C]) for k in range(K)]
+    vt = var_tran
+    for it in range(maxit):
+        c_vec = np.random.randint(Lh, 300 - 1 - Lh + 1, S)
+        r = O.gmm_minibatch_step(p["obs"], p["mask"], c_vec - Lh, 2 * Lh + 1, vt, emit, np.ones((K, K)), prior,
+                                 (it + 1.) ** -0.7, Lh, S)
+        vt, emit = r["var_tran_new"], r["emit_new"]
+    assert _rel(hmm.var_tran, vt) < 1e-4
+    assert _rel(np.array([m.weights._alpha_mf for m in hmm.var_emit]), np.array([e["omega"] for e in emit])) < 1e-4
+    assert _rel(np.array([g.mu_mf for m in hmm.var_emit for g in m.components]),
+                np.array([g["mu"] for e in emit for g in e["comps"]])) < 1e-4

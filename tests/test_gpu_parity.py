@@ -170,6 +170,7 @@ ORACLE_CASES = [
     (32, 16, 129, 5, "niw_full"),
     (33, 4, 64, 5, "niw_full"),        # first wide size
     (64, 32, 257, 4, "niw_full"),      # BASELINE config 3 shape (reduced B, T)
+    (64, 32, 1024, 2, "niw_full"),     # BASELINE config 3 window (full T, reduced B)
     (100, 3, 50, 3, "niw_diag"),
     (256, 64, 256, 2, "niw_full"),     # BASELINE config 4 shape (reduced B; float32 recursions, not bf16)
     (300, 4, 40, 2, "niw_diag"),       # K*K floats exceed shared memory: transition matrix read through L2
@@ -285,6 +286,55 @@ def test_categorical_ell_table_matches_reference_golden():
     eng.estep([0], len(g["x"]), want_var_x=False, keep_locals=True)
     ll = eng.get_locals(1, len(g["x"]))["lliks"][0]
     np.testing.assert_allclose(ll.T, g["ell"], rtol=1e-12, atol=1e-13)
+    eng.close()
+
+
+@pytest.mark.parametrize("K,C,D,T,B,kind", [(3, 2, 2, 40, 4, "niw_full"), (8, 4, 16, 128, 3, "niw_diag"),
+                                             (32, 4, 16, 96, 2, "niw_full"), (40, 3, 5, 64, 3, "niw_full")])
+def test_gmm_emissions_match_oracle(K, C, D, T, B, kind):
+    """EXTENSION (BASELINE config 5): mixture-of-NIW emissions per state.  No reference mean-field
+    code exists (parity unpinned); the oracle restates labels.py:52-65 + distributions.py:351-366 and
+    reduces to the pinned Gaussian path at C = 1 (test_oracle_golden)."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    p = make_random_problem(seed=K * 100 + C, K=K * C, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1, sep=0.8)
+    rs = np.random.RandomState(K + C)
+    emit = [dict(omega=1. + 3. * rs.rand(C), comps=p["emit"][k * C:(k + 1) * C]) for k in range(K)]
+    prior = [dict(omega=0.5 + rs.rand(C), comps=p["prior_emit"][k * C:(k + 1) * C]) for k in range(K)]
+    var_tran, prior_tran = 1. + 5. * rs.rand(K, K), np.ones((K, K))
+    obs = p["obs"].copy()
+    obs[rs.rand(len(obs)) < 0.03, 0] = np.nan
+    starts = rs.randint(0, obs.shape[0] - T + 1, B)
+    eng = __import__("pysvihmm_b200.engine", fromlist=["EStepEngine"]).EStepEngine(K, D, kind, components=C)
+    eng.set_series(obs, p["mask"], dtype="f64")
+    eng.set_prior(prior_tran, pack_emit_np(p["prior_emit"]))
+    eng.set_mix_weights(np.array([e["omega"] for e in emit]), np.array([e["omega"] for e in prior]))
+    eng.set_globals(var_tran, pack_emit_np(p["emit"]))
+    Lh, Tf = max(T // 2, 1), obs.shape[0]
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+    r = O.gmm_minibatch_step(obs, p["mask"], starts, T, var_tran, emit, prior_tran, prior, 0.37, Lh)
+    assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+    assert_q(vx.cpu().numpy(), r["var_x"])
+    s = eng.unpack_stats(stats)
+    assert_block(s["A"], r["A_inter"], S_RTOL, "A")
+    flat = [r["stats"][k][c] for k in range(K) for c in range(C)]
+    assert_block(s["n"], np.array([e[1] for e in flat]), S_RTOL, "n")
+    assert_block(s["sx"], np.array([e[0] for e in flat]), S_RTOL, "sx")
+    assert_block(s["sxx"], np.array([e[2] for e in flat]), S_RTOL, "sxx")
+    np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=3e-6)
+    eng.global_update(stats, 0.37, (Tf - 2 * Lh - 1) / (2. * Lh * B), (Tf - 2 * Lh - 1) / ((2. * Lh + 1.) * B))
+    vt, vi, em = eng.get_globals()
+    e = eng.unpack_emit(em)
+    assert_block(vt, r["var_tran_new"], S_RTOL, "var_tran")
+    newc = [g for k in range(K) for g in r["emit_new"][k]["comps"]]
+    for key in ("mu", "sigma", "kappa", "nu"):
+        ref = np.array([np.broadcast_to(x[key], e[key][0].shape) for x in newc])
+        assert_block(e[key], ref, S_RTOL, key)
+    assert_block(eng.get_mix_weights(), np.array([x["omega"] for x in r["emit_new"]]), S_RTOL, "omega")
+    # second E-step: refreshed component constants and expected log-weights
+    vx2, _ = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+    r2 = O.gmm_minibatch_step(obs, p["mask"], starts, T, r["var_tran_new"], r["emit_new"], prior_tran, prior, 0.37, Lh)
+    assert_q(vx2.cpu().numpy(), r2["var_x"])
     eng.close()
 
 
