@@ -128,6 +128,21 @@ int svihmm_get_globals(svihmm_ctx* ctx, double* var_tran, double* var_init, doub
 int svihmm_estep(svihmm_ctx* ctx, const int64_t* starts, int B, int T, float* var_x_out,
                  double* stats_out, unsigned flags, void* stream);
 
+/* Buffered meta-observations (growBuffer: select_buffer hmmsgd_metaobs.py:579-661 +
+ * intermediate_pars_buffer :932-1008): the E-step runs on windows of T = 2*bufferL+1 rows, but only
+ * the inner T - 2*trim rows (trim = bufferL - L) feed the statistics, with the wrap-around pair
+ * taken inside the inner slice exactly as :957-958 does on var_x[bufferL-L : bufferL+L+1].
+ * var_x_out holds the marginals of the whole buffered windows; the log-normaliser tail is that of
+ * the whole windows (local_lower_bound reads the full lalpha).  trim = 0 is svihmm_estep. */
+int svihmm_estep_buffered(svihmm_ctx* ctx, const int64_t* starts, int B, int T, int trim,
+                          float* var_x_out, double* stats_out, unsigned flags, void* stream);
+
+/* Replace the initial-state Dirichlet parameter in use (var_init != NULL), or go back to the
+ * stationary vector of the current transition parameters (NULL), and refresh the per-step
+ * constants.  select_L / select_buffer / get_local_messages (hmmsgd_metaobs.py:521-700) run with
+ * whatever self.var_init holds at that moment, which is the vector of the PREVIOUS minibatch. */
+int svihmm_set_var_init(svihmm_ctx* ctx, const double* var_init, int loc, void* stream);
+
 /* Same with HOST buffers (the reference-facing call): windows are gathered from the streamed host
  * series (svihmm_set_series_streamed) host->device, the E-step runs, stats (and var_x if not
  * NULL) are copied device->host, and the stream is synchronised. */

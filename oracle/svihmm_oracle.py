@@ -496,3 +496,77 @@ def batch_sgd_step(obs, mask, var_init, var_tran, emit, prior_init, prior_tran, 
         new_emit.append(niw_moment(*[(1. - lrate) * o + lrate * t for o, t in zip(no, nt)]))
     res.update(var_init_new=new_init, var_tran_new=new_tran, emit_new=new_emit)
     return res
+
+
+# --------------------------------------------------------------------------
+# adaptive window machinery
+# --------------------------------------------------------------------------
+def get_local_messages(obs, ind, halflength, var_init, var_tran, emit):
+    """hmmsgd_metaobs.py:663-700: marginals of the window [ind-halflength, ind+halflength] with
+    the GIVEN var_init (whatever self.var_init holds, not recomputed)."""
+    xw = obs[ind - halflength: ind + halflength + 1][None]
+    return local_update(xw, var_init, var_tran, emit)['var_x'][0]
+
+
+def select_L(obs, indices, var_init, var_tran, emit, epsilon=1e-5, minHalfL=1, Lincrement=1, Lcutoff=1000):
+    """hmmsgd_metaobs.py:521-545 (non-averaged branch) for given centre indices."""
+    T = obs.shape[0]
+    maxL = -1
+    for ind in indices:
+        q_diff = np.finfo(np.float64).max
+        L = minHalfL
+        q_old = get_local_messages(obs, ind, minHalfL, var_init, var_tran, emit)[minHalfL]
+        while True:
+            if ind - L < 1 + Lincrement or ind + L + Lincrement + 1 > T or L > Lcutoff:
+                break
+            if q_diff < epsilon:
+                break
+            L += Lincrement
+            q_new = get_local_messages(obs, ind, L, var_init, var_tran, emit)[L]
+            q_diff = np.sum(np.abs(q_new - q_old))
+            q_old = q_new
+        maxL = max(maxL, L)
+    return maxL
+
+
+def select_buffer(obs, indices, var_init, var_tran, emit, epsilon=1e-5, halfL=10, Lincrement=1, Lcutoff=1000):
+    """hmmsgd_metaobs.py:579-625 (non-averaged branch) for given centre indices."""
+    T = obs.shape[0]
+    maxL = -1
+    for ind in indices:
+        dl = dr = np.finfo(np.float64).max
+        bufferL = halfL
+        v = get_local_messages(obs, ind, halfL, var_init, var_tran, emit)
+        ql, qr = v[bufferL - halfL], v[bufferL + halfL]
+        while True:
+            if ind - bufferL < 1 + Lincrement or ind + bufferL + Lincrement + 1 > T or bufferL > Lcutoff:
+                break
+            if dl < epsilon and dr < epsilon:
+                break
+            bufferL += Lincrement
+            v = get_local_messages(obs, ind, bufferL, var_init, var_tran, emit)
+            nl, nr = v[bufferL - halfL], v[bufferL + halfL]
+            dl, dr = np.sum(np.abs(nl - ql)), np.sum(np.abs(nr - qr))
+            ql, qr = nl, nr
+        maxL = max(maxL, bufferL)
+    return maxL
+
+
+def buffered_stats(obs, mask, starts, bufferL, L, var_tran, emit, prior_tran):
+    """local_update on the buffered windows [start, start+2*bufferL] then intermediate_pars_buffer
+    (hmmsgd_metaobs.py:932-1008): statistics from var_x[bufferL-L : bufferL+L+1] with the wrap-around
+    inside that slice.  Returns dict(var_x (B,Tbuf,K), A_inter, emit_inter, lb)."""
+    Tb = 2 * bufferL + 1
+    idx = np.asarray(starts)[:, None] + np.arange(Tb)[None]
+    xw = obs[idx]
+    mw = mask[idx] if mask is not None else np.zeros(idx.shape, bool)
+    res = local_update(xw, stationary_init(var_tran), var_tran, emit)
+    A_inter = np.zeros_like(var_tran)
+    emit_inter = None
+    lo, hi = bufferL - L, bufferL + L + 1
+    for b in range(len(starts)):
+        A_i, e_i = intermediate_pars(res['var_x'][b][lo:hi], xw[b][lo:hi], mw[b][lo:hi], prior_tran, True)
+        A_inter += A_i
+        emit_inter = e_i if emit_inter is None else [[u + v for u, v in zip(a, c)] for a, c in zip(emit_inter, e_i)]
+    return dict(var_x=res['var_x'], A_inter=A_inter, emit_inter=emit_inter,
+                lb=float(np.sum(local_lower_bound(res['lalpha']))))

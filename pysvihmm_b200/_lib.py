@@ -31,6 +31,8 @@ SYMBOLS = {
     "svihmm_set_globals": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_get_globals": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_estep": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _vp]),
+    "svihmm_estep_buffered": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _u, _vp]),
+    "svihmm_set_var_init": (_i, [_vp, _vp, _i, _vp]),
     "svihmm_estep_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _vp]),
     "svihmm_prefetch_windows": (_i, [_vp, _vp, _i, _i]),
     "svihmm_estep_streamed": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _u, _vp]),

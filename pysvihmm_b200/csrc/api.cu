@@ -147,7 +147,8 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->pi0, c->lu, c->rowsum, c->ckc, c->par2, c->ckp, c->Rs, c->gk, c->ck, c->obs_own, c->mask_own, c->stage_obs,
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
-                  c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws};
+                  c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
+                  c->qin_ws, c->respin_ws, c->starts_in};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -507,6 +508,39 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
   return SVIHMM_OK;
 }
 
+// Buffered meta-observations (growBuffer, hmmsgd_metaobs.py:932-1008): the recursions run on
+// windows of T rows but only the inner T - 2*trim rows feed the statistics.  The inner rows of a
+// (B, T, W) table are compacted into a dense (B, T - 2*trim, W) one and the window starts shifted,
+// so that the statistics kernels see an ordinary minibatch.
+__global__ void __launch_bounds__(256)
+k_trim_rows(int B, int T, int trim, int W, const float* __restrict__ src, float* __restrict__ dst) {
+  const int Ts = T - 2 * trim;
+  const int64_t n = (int64_t)B * Ts * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / W; const int j = (int)(e - row * W);
+    const int b = (int)(row / Ts); const int t = (int)(row - (int64_t)b * Ts);
+    dst[e] = src[((int64_t)b * T + trim + t) * W + j];
+  }
+}
+__global__ void k_shift_starts(int B, int trim, const int64_t* __restrict__ src, int64_t* __restrict__ dst) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) dst[b] = src[b] + trim;
+}
+
+static int trim_table(svihmm_ctx* c, int B, int T, int trim, int W, const float* src, float** ws, size_t* cap,
+                      cudaStream_t st) {
+  const size_t need = (size_t)B * (T - 2 * trim) * W;
+  if (need > *cap) {
+    if (*ws) CU(cudaFree(*ws));
+    *ws = nullptr; *cap = 0;
+    CU(dalloc(ws, need));
+    *cap = need;
+  }
+  k_trim_rows<<<(unsigned)std::min<size_t>((need + 255) / 256, 148 * 16), 256, 0, st>>>(B, T, trim, W, src, *ws);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
 // launch k_stats for one column range with row splits sized for ~4 CTAs per SM; returns nsplit
 static int launch_kstats(svihmm_ctx* c, StatsArgs a, int Kleft, int n_lo, int n_hi, float** part, size_t* cap,
                          int64_t* nsplit_out, cudaStream_t st) {
@@ -540,10 +574,17 @@ static int launch_kstats(svihmm_ctx* c, StatsArgs a, int Kleft, int n_lo, int n_
 // Mixture statistics: transitions from q, NIW statistics of the K*C components weighted by
 // q[t,k] * resp[t,k,c] (util.py:73-83 with the responsibilities of labels.py:52-65).
 static int stats_mix(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask, const int64_t* starts,
-                     int B, int T, const float* q, double* stats_out, unsigned flags, cudaStream_t st) {
+                     int B, int T, const float* q, int Tfull, int trim, double* stats_out, unsigned flags,
+                     cudaStream_t st) {
   const int K = c->K, KE = c->KE, D = c->D;
   const int64_t R = (int64_t)B * T;
-  k_mix_weights<<<(unsigned)((R * KE + 255) / 256), 256, 0, st>>>(R * KE, c->C, q, c->resp_ws, c->wq_ws);
+  const float* resp = c->resp_ws;
+  if (trim > 0) {                                   // responsibilities of the inner rows only
+    int rc_ = trim_table(c, B, Tfull, trim, KE, c->resp_ws, &c->respin_ws, &c->cap_respin, st);
+    if (rc_) return rc_;
+    resp = c->respin_ws;
+  }
+  k_mix_weights<<<(unsigned)((R * KE + 255) / 256), 256, 0, st>>>(R * KE, c->C, q, resp, c->wq_ws);
   LAUNCHED(c);
   StatsArgs a;
   a.B = B; a.T = T; a.D = D; a.DD = c->DD; a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.cat = 0; a.R = R;
@@ -561,15 +602,102 @@ static int stats_mix(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* m
   return SVIHMM_OK;
 }
 
+// symmetric register-blocked statistics (wide64.cuh) of a dense (B, T, K) table of marginals
+static int stats_sym_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask, const int64_t* starts,
+                           int B, int T, const float* q, double* stats_out, unsigned flags, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  const int64_t R = (int64_t)B * T;
+  StatsSymArgs sa;
+  sa.B = B; sa.T = T; sa.K = K; sa.D = D; sa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+  sa.NF = K + 1 + D + (sa.diag ? D : D * (D + 1) / 2);
+  sa.wrap = (flags & SVIHMM_WRAP) ? 1 : 0; sa.dtype = dtype; sa.R = R;
+  sa.q = q; sa.obs = obs; sa.mask = mask; sa.starts = starts;
+  int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((R + 1023) / 1024, 4096));
+  const int64_t rps = (((R + nsplit - 1) / nsplit) + SS_RC - 1) / SS_RC * SS_RC;
+  nsplit = (R + rps - 1) / rps;
+  sa.rows_per_split = rps;
+  const size_t need_part = (size_t)nsplit * K * sa.NF;
+  if (need_part > c->cap_part) {
+    if (c->part_ws) CU(cudaFree(c->part_ws));
+    c->part_ws = nullptr; c->cap_part = 0;
+    CU(dalloc(&c->part_ws, need_part));
+    c->cap_part = need_part;
+  }
+  sa.part = c->part_ws;
+  dim3 grid((sa.NF + SS_TN - 1) / SS_TN, (unsigned)nsplit);
+  k_stats_sym<<<grid, SS_NT, 0, st>>>(sa);
+  LAUNCHED(c);
+  k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+      B, T, K, D, c->DD, sa.NF, sa.diag, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
+      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
+// generic statistics contraction (stats.cuh) of a dense (B, T, K) table of marginals
+static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
+                               const int64_t* starts, int B, int T, const float* q, double* stats_out,
+                               unsigned flags, bool xi, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  const int64_t R = (int64_t)B * T;
+  // K4: statistics
+  StatsArgs a;
+  a.B = B; a.T = T; a.K = K; a.D = D; a.DD = c->DD; a.N = c->nfeat;
+  a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; a.R = R;
+  a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
+  const int TM = K <= 16 ? 16 : (K <= 32 ? 32 : 64);
+  const int tiles_m = (K + TM - 1) / TM;
+  const int tiles_n = (c->nfeat + ST_TN - 1) / ST_TN;
+  const int64_t chunks = (R + ST_RC - 1) / ST_RC;
+  int64_t nsplit = (4 * 148 + (int64_t)tiles_m * tiles_n - 1) / ((int64_t)tiles_m * tiles_n);
+  if (nsplit > chunks) nsplit = chunks;
+  if (nsplit < 1) nsplit = 1;
+  int64_t rps = ((chunks + nsplit - 1) / nsplit) * ST_RC;
+  nsplit = (R + rps - 1) / rps;
+  a.rows_per_split = rps;
+  const size_t need_part = (size_t)nsplit * K * c->nfeat;
+  if (need_part > c->cap_part) {
+    if (c->part_ws) CU(cudaFree(c->part_ws));
+    c->part_ws = nullptr; c->cap_part = 0;
+    CU(dalloc(&c->part_ws, need_part));
+    c->cap_part = need_part;
+  }
+  a.part = c->part_ws;
+  const size_t xsm = (size_t)ST_RC * D * sizeof(float);
+  auto launch_stats = [&](const float* left, const float* next, int n_lo, int n_hi, int wrap) {
+    a.left = left; a.next = next; a.n_lo = n_lo; a.n_hi = n_hi; a.wrap = wrap;
+    dim3 grid((n_hi - n_lo + ST_TN - 1) / ST_TN, tiles_m, (unsigned)nsplit);
+    if (TM == 16) k_stats<16><<<grid, 256, xsm, st>>>(a);
+    else if (TM == 32) k_stats<32><<<grid, 256, xsm, st>>>(a);
+    else k_stats<64><<<grid, 256, xsm, st>>>(a);
+    c->launches++;
+  };
+  if (xi) {
+    launch_stats(c->alpha_ws, c->r_ws, 0, K, 0);
+    launch_stats(q, q, K, c->nfeat, 0);
+  } else {
+    launch_stats(q, q, 0, c->nfeat, (flags & SVIHMM_WRAP) ? 1 : 0);
+  }
+  CU(cudaGetLastError());
+  k_stats_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+      B, T, K, D, c->DD, c->nfeat, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
+      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, c->Pt, xi ? 1 : 0, stats_out, c->slen);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
 static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                       const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
-                      unsigned flags, cudaStream_t st) {
+                      unsigned flags, cudaStream_t st, int trim = 0) {
   const int K = c->K, D = c->D;
   const bool xi = flags & SVIHMM_EXACT_XI;
+  if (trim < 0 || 2 * trim >= T) return fail(SVIHMM_EINVAL, "trim = %d leaves no inner rows of T = %d", trim, T);
+  if (trim > 0 && xi) return fail(SVIHMM_EUNSUPPORTED, "SVIHMM_EXACT_XI with buffered windows");
   size_t fsmem = 0;
-  if (pipe_eligible(c, T, flags, &fsmem))
+  if (trim > 0) {}    // buffered windows: per-phase kernels (the statistics see the compacted inner rows)
+  else if (pipe_eligible(c, T, flags, &fsmem))
     return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st, true);
-  if (fused_eligible(c, T, flags, &fsmem))
+  else if (fused_eligible(c, T, flags, &fsmem))
     return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st, false);
   int rc = ensure_ws(c, B, T, xi);
   if (rc) return rc;
@@ -641,6 +769,23 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   float* q = var_x_out ? var_x_out : c->q_ws;
   float* r = xi ? c->r_ws : nullptr;
   float* cs = (float*)(c->mx_ws + (size_t)B * T);
+  // the statistics phase works on (qs, starts_s, Ts): the marginals themselves, or their inner rows
+  const float* qs = q; const int64_t* starts_s = starts; int Ts = T;
+  auto trim_for_stats = [&]() -> int {
+    if (trim == 0) return SVIHMM_OK;
+    int rc_ = trim_table(c, B, T, trim, K, q, &c->qin_ws, &c->cap_qin, st);
+    if (rc_) return rc_;
+    if ((size_t)B > c->cap_startsin) {
+      if (c->starts_in) CU(cudaFree(c->starts_in));
+      c->starts_in = nullptr; c->cap_startsin = 0;
+      CU(dalloc(&c->starts_in, (size_t)B));
+      c->cap_startsin = B;
+    }
+    k_shift_starts<<<(B + 255) / 256, 256, 0, st>>>(B, trim, starts, c->starts_in);
+    LAUNCHED(c);
+    qs = c->qin_ws; starts_s = c->starts_in; Ts = T - 2 * trim;
+    return SVIHMM_OK;
+  };
   if (K > 32 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64 && c->kind != SVIHMM_EMIT_CATEGORICAL) {
     // warp-per-chain recursions, marginals, symmetric register-blocked statistics (wide64.cuh)
     if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
@@ -653,36 +798,13 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
       LAUNCHED(c); }
     PhaseTimer pt_stats(c, PH_STATS, st);
+    if ((rc = trim_for_stats())) return rc;
     if (mix) {
       c->last_B = B; c->last_T = T; c->last_fused = 1;
-      return stats_mix(c, obs, dtype, mask, starts, B, T, q, stats_out, flags, st);
+      return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
     }
-    StatsSymArgs sa;
-    sa.B = B; sa.T = T; sa.K = K; sa.D = D; sa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
-    sa.NF = K + 1 + D + (sa.diag ? D : D * (D + 1) / 2);
-    sa.wrap = (flags & SVIHMM_WRAP) ? 1 : 0; sa.dtype = dtype; sa.R = R;
-    sa.q = q; sa.obs = obs; sa.mask = mask; sa.starts = starts;
-    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>((R + 1023) / 1024, 4096));
-    const int64_t rps = (((R + nsplit - 1) / nsplit) + SS_RC - 1) / SS_RC * SS_RC;
-    nsplit = (R + rps - 1) / rps;
-    sa.rows_per_split = rps;
-    const size_t need_part = (size_t)nsplit * K * sa.NF;
-    if (need_part > c->cap_part) {
-      if (c->part_ws) CU(cudaFree(c->part_ws));
-      c->part_ws = nullptr; c->cap_part = 0;
-      CU(dalloc(&c->part_ws, need_part));
-      c->cap_part = need_part;
-    }
-    sa.part = c->part_ws;
-    dim3 grid((sa.NF + SS_TN - 1) / SS_TN, (unsigned)nsplit);
-    k_stats_sym<<<grid, SS_NT, 0, st>>>(sa);
-    LAUNCHED(c);
-    k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
-        B, T, K, D, c->DD, sa.NF, sa.diag, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
-        (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
-    LAUNCHED(c);
     c->last_B = B; c->last_T = T; c->last_fused = 1;     // no lliks/alpha/cs tables in the classic form
-    return SVIHMM_OK;
+    return stats_sym_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, st);
   }
   if (K <= 32) {
     switch (c->KP) {
@@ -712,55 +834,13 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   PhaseTimer pt_stats(c, PH_STATS, st);
   k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
   LAUNCHED(c);
+  if ((rc = trim_for_stats())) return rc;
   if (mix) {
     c->last_B = B; c->last_T = T; c->last_fused = 0;
-    return stats_mix(c, obs, dtype, mask, starts, B, T, q, stats_out, flags, st);
+    return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
   }
-  // K4: statistics
-  StatsArgs a;
-  a.B = B; a.T = T; a.K = K; a.D = D; a.DD = c->DD; a.N = c->nfeat;
-  a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; a.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; a.R = R;
-  a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
-  const int TM = K <= 16 ? 16 : (K <= 32 ? 32 : 64);
-  const int tiles_m = (K + TM - 1) / TM;
-  const int tiles_n = (c->nfeat + ST_TN - 1) / ST_TN;
-  const int64_t chunks = (R + ST_RC - 1) / ST_RC;
-  int64_t nsplit = (4 * 148 + (int64_t)tiles_m * tiles_n - 1) / ((int64_t)tiles_m * tiles_n);
-  if (nsplit > chunks) nsplit = chunks;
-  if (nsplit < 1) nsplit = 1;
-  int64_t rps = ((chunks + nsplit - 1) / nsplit) * ST_RC;
-  nsplit = (R + rps - 1) / rps;
-  a.rows_per_split = rps;
-  const size_t need_part = (size_t)nsplit * K * c->nfeat;
-  if (need_part > c->cap_part) {
-    if (c->part_ws) CU(cudaFree(c->part_ws));
-    c->part_ws = nullptr; c->cap_part = 0;
-    CU(dalloc(&c->part_ws, need_part));
-    c->cap_part = need_part;
-  }
-  a.part = c->part_ws;
-  const size_t xsm = (size_t)ST_RC * D * sizeof(float);
-  auto launch_stats = [&](const float* left, const float* next, int n_lo, int n_hi, int wrap) {
-    a.left = left; a.next = next; a.n_lo = n_lo; a.n_hi = n_hi; a.wrap = wrap;
-    dim3 grid((n_hi - n_lo + ST_TN - 1) / ST_TN, tiles_m, (unsigned)nsplit);
-    if (TM == 16) k_stats<16><<<grid, 256, xsm, st>>>(a);
-    else if (TM == 32) k_stats<32><<<grid, 256, xsm, st>>>(a);
-    else k_stats<64><<<grid, 256, xsm, st>>>(a);
-    c->launches++;
-  };
-  if (xi) {
-    launch_stats(c->alpha_ws, c->r_ws, 0, K, 0);
-    launch_stats(q, q, K, c->nfeat, 0);
-  } else {
-    launch_stats(q, q, 0, c->nfeat, (flags & SVIHMM_WRAP) ? 1 : 0);
-  }
-  CU(cudaGetLastError());
-  k_stats_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
-      B, T, K, D, c->DD, c->nfeat, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
-      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, c->Pt, xi ? 1 : 0, stats_out, c->slen);
-  LAUNCHED(c);
   c->last_B = B; c->last_T = T; c->last_fused = 0;
-  return SVIHMM_OK;
+  return stats_generic_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, xi, st);
 }
 
 static int check_estep_args(svihmm_ctx* c, const void* starts, int B, int T, const void* stats, unsigned flags) {
@@ -780,6 +860,29 @@ extern "C" int svihmm_estep(svihmm_ctx* c, const int64_t* starts, int B, int T, 
   CU(cudaSetDevice(c->device));
   return estep_impl(c, c->obs, c->obs_dtype, c->mask, starts, B, T, var_x_out, stats_out, flags,
                     (cudaStream_t)stream);
+}
+
+/* buffered meta-observations + explicit initial-state parameter (adaptive window machinery) */
+extern "C" int svihmm_estep_buffered(svihmm_ctx* c, const int64_t* starts, int B, int T, int trim,
+                                     float* var_x_out, double* stats_out, unsigned flags, void* stream) {
+  int rc = check_estep_args(c, starts, B, T, stats_out, flags);
+  if (rc) return rc;
+  if (!c->obs) return fail(SVIHMM_ESTATE, "svihmm_set_series has not been called");
+  if (T > c->T_full) return fail(SVIHMM_EINVAL, "T (%d) exceeds the series length (%lld)", T, (long long)c->T_full);
+  CU(cudaSetDevice(c->device));
+  return estep_impl(c, c->obs, c->obs_dtype, c->mask, starts, B, T, var_x_out, stats_out, flags,
+                    (cudaStream_t)stream, trim);
+}
+
+extern "C" int svihmm_set_var_init(svihmm_ctx* c, const double* var_init, int loc, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  if (!c->have_globals) return fail(SVIHMM_ESTATE, "svihmm_set_globals has not been called");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  c->user_init = var_init != nullptr;
+  if (var_init && (rc = copy_in(c->vinit + c->K, var_init, sizeof(double) * c->K, loc, st))) return rc;
+  return run_global(c, GM_PREP, nullptr, 0.0, 0.0, 0.0, st);
 }
 
 // gather B windows of T rows (row = rowbytes) from a mapped host (or device) series into a dense

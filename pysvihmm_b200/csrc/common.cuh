@@ -55,6 +55,7 @@ struct svihmm_ctx {
   size_t cap_rows, cap_B, cap_part;
   double *ll_ws, *mx_ws, *seq_ws, *lt_ws;
   double* ell_ws; float *resp_ws, *wq_ws, *part2_ws; size_t cap_rows_mix, cap_part2;   // mixture workspaces
+  float *qin_ws, *respin_ws; int64_t* starts_in; size_t cap_qin, cap_respin, cap_startsin;   // buffered windows
   int* e_ws;
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
   size_t hostq_cap;

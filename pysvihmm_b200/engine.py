@@ -165,7 +165,13 @@ class EStepEngine(object):
     def new_stats(self):
         return torch.empty(self.slen, dtype=torch.float64, device=self.device)
 
-    def estep(self, starts, T, flags=0, var_x=None, stats=None, want_var_x=True, keep_locals=False):
+    def set_var_init(self, var_init=None):
+        """Explicit initial-state Dirichlet parameter (K,), or None = stationary vector of the current
+        transition parameters (hmmsgd_metaobs.py:413-418)."""
+        vi = None if var_init is None else _f64(var_init)
+        L.check(self.lib.svihmm_set_var_init(self._h, _ptr(vi), L.LOC_HOST, self._stream()))
+
+    def estep(self, starts, T, flags=0, var_x=None, stats=None, want_var_x=True, keep_locals=False, trim=0):
         """E-step over windows obs[starts[b]:starts[b]+T] of the resident series.
         Returns (var_x (B,T,K) float32 CUDA tensor or None, stats float64 CUDA tensor).
         keep_locals: keep the lliks/alpha/scale tables for get_locals (unfused kernels)."""
@@ -179,8 +185,12 @@ class EStepEngine(object):
             var_x = torch.empty((B, T, self.K), dtype=torch.float32, device=self.device)
         if stats is None:
             stats = self.new_stats()
-        L.check(self.lib.svihmm_estep(self._h, _ptr(starts), B, int(T), _ptr(var_x), _ptr(stats),
-                                      int(flags), self._stream()))
+        if trim:          # buffered windows: statistics from the inner T - 2*trim rows only
+            L.check(self.lib.svihmm_estep_buffered(self._h, _ptr(starts), B, int(T), int(trim), _ptr(var_x),
+                                                   _ptr(stats), int(flags), self._stream()))
+        else:
+            L.check(self.lib.svihmm_estep(self._h, _ptr(starts), B, int(T), _ptr(var_x), _ptr(stats),
+                                          int(flags), self._stream()))
         self._keep["starts"] = starts
         return var_x, stats
 

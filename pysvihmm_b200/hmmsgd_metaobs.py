@@ -79,12 +79,9 @@ class VBHMM(VariationalHMMBase):
             raise NotImplementedError("adagrad variant (hmmsgd_metaobs.py:1036-1040) is not on the engine yet")
         self.adagrad = adagrad
         self.maxit = maxit
-        if growBuffer or bufferBudget:
-            raise NotImplementedError("growBuffer/bufferBudget (hmmsgd_metaobs.py:579-661,932-1008) "
-                                      "are 'next' rows of the scope table, not built yet")
         self.growBuffer = growBuffer
         self.bufferBudget = bufferBudget
-        if metaobs_half < 1:
+        if metaobs_half is not None and metaobs_half < 1:
             raise RuntimeError("metaobs (%d) must be >= 1." % (metaobs_half,))
         self.metaobs_half = metaobs_half
         self.mb_sz = mb_sz
@@ -94,7 +91,7 @@ class VBHMM(VariationalHMMBase):
         if pairwise_mode not in ("ref_outer", "exact_xi"):
             raise RuntimeError("pairwise_mode must be 'ref_outer' or 'exact_xi'")
         self.pairwise_mode = pairwise_mode
-        metaobs_sz = 2 * metaobs_half + 1
+        metaobs_sz = 2 * (metaobs_half if metaobs_half is not None else 1) + 1
         self.var_x = np.random.rand(metaobs_sz, self.K)       # :202 (keeps the RNG stream aligned)
         self.var_x /= np.sum(self.var_x, axis=1)[:, np.newaxis]
         self.lalpha = np.empty((metaobs_sz, self.K))
@@ -142,16 +139,17 @@ class VBHMM(VariationalHMMBase):
             f |= L.EXACT_XI
         return f
 
-    def minibatch_estep(self, minibatch, want_var_x=True):
+    def minibatch_estep(self, minibatch, want_var_x=True, trim=0):
         """Batched replacement of the loop hmmsgd_metaobs.py:405-436 for this rank's share of the
-        minibatch; returns the packed, all-reduced statistics tensor (device)."""
+        minibatch; returns the packed, all-reduced statistics tensor (device).  trim > 0: buffered
+        meta-observations, statistics from the inner rows only (intermediate_pars_buffer :932-1008)."""
         eng = self._ensure_engine()
         starts = np.array([m.i1 for m in minibatch], dtype=np.int64)
         T = int(minibatch[0].i2 - minibatch[0].i1 + 1)
         dist = _dist()
         if dist is not None:
             starts = shard_starts(starts, dist.get_rank(), dist.get_world_size())
-        vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x)
+        vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x, trim=trim)
         allreduce_stats(stats, dist)        # one sum all-reduce of the packed statistics per step
         self._var_x_batch = vx
         self._last_B, self._last_T = len(starts), T
@@ -160,22 +158,41 @@ class VBHMM(VariationalHMMBase):
     def infer(self, adaptive=False, perIter=10, epsilon=1e-6, minHalfL=1, avgResidual=False,
               Lincrement=1, Lcutoff=1000):
         """hmmsgd_metaobs.py:298-485."""
-        if adaptive or self.metaobs_half is None:
-            raise NotImplementedError("select_L (hmmsgd_metaobs.py:521-569) is a 'next' row, not built yet")
         np.random.seed(self.seed)
+        growBuffer, bufferBudget = self.growBuffer, self.bufferBudget
         maxit = self.maxit
         if self.metaobs_fun is None:
             self.set_metaobs_fun()
         self.elbo_vec = np.inf * np.ones(maxit)
         self.iter_time = np.inf * np.ones(maxit)
         mb_sz, Lh = self.mb_sz, self.metaobs_half
+        miniL, bufferL = Lh, None
+        if (Lh is None or adaptive) and growBuffer:
+            raise RuntimeError("Cannot specify both adaptive and buffer simultaneously!")   # :344
         eng = self._ensure_engine()
+        track_init = adaptive or Lh is None or growBuffer       # select_* read the previous var_init
         for it in range(maxit):
             start_time = time.time()
             self.lrate = (it + self.tau) ** (-self.kappa)                 # :351
-            minibatch = self.metaobs_fun(self.T, Lh, mb_sz)               # :396
+            if Lh is None or (adaptive and it % perIter == 0):            # :354-369
+                Lh = self.select_L(mb_sz, epsilon=epsilon, minHalfL=minHalfL, avgResidual=avgResidual,
+                                   Lincrement=Lincrement, Lcutoff=Lcutoff)
+                self.metaobs_half = Lh        # global_update scales by the current L (:1033,1048)
+                self._resize_locals(2 * Lh + 1)
+                miniL = Lh
+            if growBuffer and it % perIter == 0:                          # :372-393
+                bufferL = self.select_buffer(self.mb_sz, epsilon=epsilon, halfL=Lh, avgResidual=avgResidual,
+                                             Lincrement=Lincrement, Lcutoff=Lcutoff)
+                self._resize_locals(2 * bufferL + 1)
+                miniL = bufferL
+                if bufferBudget:
+                    mb_sz = self.buffer_budget(bufferL)
+            minibatch = self.metaobs_fun(self.T, miniL, mb_sz)            # :396
             self.cur_mo = minibatch[-1]
-            stats = self.minibatch_estep(minibatch, want_var_x=False)     # :405-436
+            stats = self.minibatch_estep(minibatch, want_var_x=False,
+                                         trim=(bufferL - Lh) if growBuffer else 0)   # :405-436
+            if track_init:
+                self.var_init = eng.get_globals()[1]                      # :418, read by the next select_*
             self.global_update(stats)                                     # :439
             if self.track_elbo:
                 self._last_stats_host = eng.unpack_stats(stats)
@@ -192,6 +209,137 @@ class VBHMM(VariationalHMMBase):
         self._host_stale = True
         self._pull_globals()
         self.metaobs_fun = None          # :485 (picklable)
+
+    # ------------------------------------------------------------------ adaptive window machinery
+    def _resize_locals(self, metaobs_sz):
+        """hmmsgd_metaobs.py:360-367 / :382-388 (the random var_x keeps the RNG stream aligned)."""
+        self.var_x = np.random.rand(metaobs_sz, self.K)
+        self.var_x /= np.sum(self.var_x, axis=1)[:, np.newaxis]
+        self.lalpha = np.empty((metaobs_sz, self.K))
+        self.lbeta = np.empty((metaobs_sz, self.K))
+        self.lliks = np.empty((metaobs_sz, self.K))
+
+    def _window_marginals(self, inds, halflength):
+        """Marginals (n, 2*halflength+1, K) of the windows centred at `inds`: ONE batched E-step
+        instead of the reference's per-index get_local_messages calls (:663-700)."""
+        eng = self._ensure_engine()
+        inds = np.asarray(inds, dtype=np.int64)
+        vx, _ = eng.estep(inds - halflength, 2 * halflength + 1, flags=0)
+        return vx.double().cpu().numpy()
+
+    def get_local_messages(self, ind, halflength):
+        """hmmsgd_metaobs.py:663-700: variational distribution over the window centred at ind, with
+        the initial-state parameter self.var_init as it currently stands."""
+        eng = self._ensure_engine()
+        eng.set_var_init(self.var_init)
+        try:
+            return self._window_marginals([ind], halflength)[0]
+        finally:
+            eng.set_var_init(None if not self._explicit_init else self.var_init)
+
+    def get_marginal(self, var_over_x, index):
+        """hmmsgd_metaobs.py:702-708."""
+        return np.squeeze(var_over_x[index, :])
+
+    def select_L(self, numIndices=1, epsilon=1e-5, minHalfL=1, avgResidual=False, Lincrement=1, Lcutoff=1000):
+        """hmmsgd_metaobs.py:521-569: grow the half-length until the centre marginal moves less than
+        epsilon in L1.  All still-growing indices share the same L in every round, so each round is one
+        batched E-step over them."""
+        indices = npr.choice(self.T - 2 * minHalfL - 1, size=numIndices) + minHalfL
+        eng = self._ensure_engine()
+        eng.set_var_init(self.var_init)
+        try:
+            n = len(indices)
+            L = minHalfL
+            q_old = self._window_marginals(indices, L)[:, L]
+            finalL = np.full(n, minHalfL)
+            active = np.ones(n, dtype=bool)
+            q_diff = np.full(n, np.finfo(np.float64).max)
+            count = np.zeros(n, dtype=int); run_av = np.zeros(n); run_old = np.zeros(n)
+            while active.any():
+                grow = active & ~((indices - L < 1 + Lincrement) | (indices + L + Lincrement + 1 > self.T) | (L > Lcutoff))
+                if not avgResidual:
+                    grow &= ~(q_diff < epsilon)
+                else:
+                    count[grow] += 1
+                    with np.errstate(divide='ignore', invalid='ignore'):
+                        conv = (count > 1) & ((run_av - run_old) / np.maximum(count - 1, 1) < epsilon)
+                    grow &= ~conv
+                finalL[active & ~grow] = L
+                active = grow
+                if not active.any():
+                    break
+                L += Lincrement
+                ia = np.nonzero(active)[0]
+                q_new = self._window_marginals(indices[ia], L)[:, L]
+                d = np.sum(np.abs(q_new - q_old[ia]), axis=1)
+                if not avgResidual:
+                    q_diff[ia] = d
+                else:
+                    run_old[ia] = run_av[ia]
+                    run_av[ia] += d
+                q_old[ia] = q_new
+            return int(finalL.max())
+        finally:
+            eng.set_var_init(None if not self._explicit_init else self.var_init)
+
+    def buffer_budget(self, halfL, budget=400):
+        """hmmsgd_metaobs.py:571-577."""
+        return int(np.ceil(budget / (2 * halfL + 1)))
+
+    def select_buffer(self, numIndices=1, epsilon=1e-5, halfL=10, avgResidual=False, Lincrement=1, Lcutoff=1000):
+        """hmmsgd_metaobs.py:579-661: grow the buffer until the marginals at the two endpoints of the
+        original meta-observation move less than epsilon.  (The reference's avgResidual branch reads
+        an undefined var_new, :642-643; here it is computed like in the plain branch.)"""
+        indices = npr.choice(self.T - 2 * halfL - 1, size=numIndices) + halfL
+        eng = self._ensure_engine()
+        eng.set_var_init(self.var_init)
+        try:
+            n = len(indices)
+            bufL = halfL
+            v = self._window_marginals(indices, bufL)
+            ql, qr = v[:, bufL - halfL].copy(), v[:, bufL + halfL].copy()
+            finalL = np.full(n, halfL)
+            active = np.ones(n, dtype=bool)
+            dl = np.full(n, np.finfo(np.float64).max); dr = dl.copy()
+            count = np.zeros(n, dtype=int)
+            avl = np.zeros(n); avr = np.zeros(n); oldl = np.zeros(n); oldr = np.zeros(n)
+            while active.any():
+                grow = active & ~((indices - bufL < 1 + Lincrement) | (indices + bufL + Lincrement + 1 > self.T) | (bufL > Lcutoff))
+                if not avgResidual:
+                    grow &= ~((dl < epsilon) & (dr < epsilon))
+                else:
+                    count[grow] += 1
+                    cm = np.maximum(count - 1, 1)
+                    grow &= ~((count > 1) & ((avl - oldl) / cm < epsilon) & ((avr - oldr) / cm < epsilon))
+                finalL[active & ~grow] = bufL
+                active = grow
+                if not active.any():
+                    break
+                bufL += Lincrement
+                ia = np.nonzero(active)[0]
+                v = self._window_marginals(indices[ia], bufL)
+                nl, nr = v[:, bufL - halfL], v[:, bufL + halfL]
+                d_l, d_r = np.sum(np.abs(nl - ql[ia]), axis=1), np.sum(np.abs(nr - qr[ia]), axis=1)
+                if not avgResidual:
+                    dl[ia], dr[ia] = d_l, d_r
+                else:
+                    oldl[ia], oldr[ia] = avl[ia], avr[ia]
+                    avl[ia] += d_l; avr[ia] += d_r
+                ql[ia], qr[ia] = nl, nr
+            return int(finalL.max())
+        finally:
+            eng.set_var_init(None if not self._explicit_init else self.var_init)
+
+    def intermediate_pars_buffer(self, metaobs, bufferL, L):
+        """hmmsgd_metaobs.py:932-1008: E-step on the buffered window, statistics from its inner 2L+1
+        rows (engine: svihmm_estep_buffered with trim = bufferL - L)."""
+        eng = self._ensure_engine()
+        T = metaobs.i2 - metaobs.i1 + 1
+        vx, stats = eng.estep([metaobs.i1], T, flags=self._flags(), trim=bufferL - L)
+        self._last_stats_host = eng.unpack_stats(stats)
+        self.var_x = vx[0].double().cpu().numpy()
+        return self.intermediate_pars(metaobs)
 
     def local_update(self, metaobs=None):
         """hmmsgd_metaobs.py:487-519 for one meta-observation (or the full series)."""

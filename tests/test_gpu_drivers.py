@@ -210,3 +210,92 @@ def test_vbhmm_gmm_emissions_follow_oracle_trajectory():
     assert _rel(np.array([m.weights._alpha_mf for m in hmm.var_emit]), np.array([e["omega"] for e in emit])) < 1e-4
     assert _rel(np.array([g.mu_mf for m in hmm.var_emit for g in m.components]),
                 np.array([g["mu"] for e in emit for g in e["comps"]])) < 1e-4
+
+
+def _adaptive_problem():
+    from tests.helpers import make_random_problem
+    p = make_random_problem(seed=6, K=3, D=2, T_full=400, kind="niw_full", miss=0.0, sep=1.5)
+    return p
+
+
+def _gauss_objs(p):
+    from pysvihmm_b200.distributions import Gaussian
+    return np.array([Gaussian(mu=e["mu"].copy(), sigma=e["sigma"].copy(), mu_0=pe["mu"], sigma_0=pe["sigma"],
+                              kappa_0=pe["kappa"], nu_0=pe["nu"], kappa_mf=e["kappa"], nu_mf=e["nu"])
+                     for e, pe in zip(p["emit"], p["prior_emit"])])
+
+
+def test_select_L_and_select_buffer_match_oracle():
+    """select_L / select_buffer (hmmsgd_metaobs.py:521-661) batched over the sampled indices against
+    the oracle's per-index loops, same legacy-RNG index draws."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    p = _adaptive_problem()
+    K = 3
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), _gauss_objs(p), metaobs_half=5, mb_sz=6,
+                  init_tran=p["var_tran"].copy(), maxit=1, seed=3)
+    var_init = hmm.var_init.copy()                       # prior_init / sum (hmmbase.py:108-111)
+    for eps in (1e-2, 1e-4):
+        np.random.seed(10)
+        L_gpu = hmm.select_L(6, epsilon=eps, minHalfL=1, Lincrement=2, Lcutoff=60)
+        np.random.seed(10)
+        idx = np.random.choice(400 - 2 * 1 - 1, size=6) + 1
+        L_ref = O.select_L(p["obs"], idx, var_init, p["var_tran"], p["emit"], epsilon=eps, minHalfL=1,
+                           Lincrement=2, Lcutoff=60)
+        assert L_gpu == L_ref, (eps, L_gpu, L_ref)
+        np.random.seed(11)
+        b_gpu = hmm.select_buffer(5, epsilon=eps, halfL=4, Lincrement=1, Lcutoff=60)
+        np.random.seed(11)
+        idx = np.random.choice(400 - 2 * 4 - 1, size=5) + 4
+        b_ref = O.select_buffer(p["obs"], idx, var_init, p["var_tran"], p["emit"], epsilon=eps, halfL=4,
+                                Lincrement=1, Lcutoff=60)
+        assert b_gpu == b_ref, (eps, b_gpu, b_ref)
+    q = hmm.get_local_messages(100, 7)
+    q_ref = O.get_local_messages(p["obs"], 100, 7, var_init, p["var_tran"], p["emit"])
+    assert np.max(np.abs(q - q_ref)) < 1e-6
+    assert hmm.buffer_budget(10) == 20
+
+
+def test_buffered_estep_uses_inner_rows_only():
+    """svihmm_estep_buffered / intermediate_pars_buffer (hmmsgd_metaobs.py:932-1008)."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    from tests.helpers import make_random_problem, pack_emit_np
+    for K, D, kind, bufL, Lh in [(3, 2, "niw_full", 9, 4), (40, 3, "niw_full", 12, 5), (5, 4, "niw_diag", 6, 6)]:
+        p = make_random_problem(seed=K, K=K, D=D, T_full=300, kind=kind, miss=0.1)
+        starts = np.random.RandomState(2).randint(0, 300 - (2 * bufL + 1), 5)
+        eng = EStepEngine(K, D, kind)
+        eng.set_series(p["obs"], p["mask"], dtype="f64")
+        eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        vx, stats = eng.estep(starts, 2 * bufL + 1, flags=L.WRAP | L.ADD_PRIOR, trim=bufL - Lh)
+        if kind == "niw_full":
+            r = O.buffered_stats(p["obs"], p["mask"], starts, bufL, Lh, p["var_tran"], p["emit"], p["prior_tran"])
+            s = eng.unpack_stats(stats)
+            assert np.max(np.abs(vx.cpu().numpy() - r["var_x"])) < 1e-5
+            assert _rel(s["A"], r["A_inter"]) < 1e-5
+            assert _rel(s["sx"], np.array([e[0] for e in r["emit_inter"]])) < 1e-5
+            assert _rel(s["sxx"], np.array([e[2] for e in r["emit_inter"]])) < 1e-5
+            assert abs(s["lb_q4"] - r["lb"]) < 3e-6 * abs(r["lb"])
+        else:       # trim = 0 must equal the plain call
+            vx0, st0 = eng.estep(starts, 2 * bufL + 1, flags=L.WRAP | L.ADD_PRIOR)
+            np.testing.assert_allclose(stats.cpu().numpy(), st0.cpu().numpy(), rtol=1e-12)
+        eng.close()
+
+
+def test_vbhmm_infer_adaptive_and_growbuffer_run():
+    """infer(adaptive=True) and growBuffer/bufferBudget (hmmsgd_metaobs.py:354-393) end to end."""
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    p = _adaptive_problem()
+    K = 3
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), _gauss_objs(p), metaobs_half=None, mb_sz=4,
+                  init_tran=p["var_tran"].copy(), maxit=4, seed=3)
+    hmm.infer(adaptive=True, perIter=2, epsilon=1e-3, Lincrement=2, Lcutoff=40)
+    assert hmm.metaobs_half >= 1 and np.isfinite(hmm.var_tran).all() and np.isfinite(hmm.elbo_vec).all()
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), _gauss_objs(p), metaobs_half=4, mb_sz=4,
+                  init_tran=p["var_tran"].copy(), maxit=4, seed=3, growBuffer=True, bufferBudget=True)
+    hmm.infer(perIter=2, epsilon=1e-3, Lcutoff=40)
+    assert np.isfinite(hmm.var_tran).all() and np.all(hmm.var_tran > 0)
+    with pytest.raises(RuntimeError):
+        hmm.infer(adaptive=True)
