@@ -111,6 +111,23 @@ class ClockSampler(object):
                 "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(rows)}
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_c2_pipe_ncu_summary.txt), or None when there is no capture for this kernel/config."""
+    if kernel != "fused":
+        return None
+    p = os.path.join(ROOT, "profiles", "r1_c2_pipe_ncu_summary.txt")
+    try:
+        tot, unit = 0.0, {"byte": 1., "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(p):
+            if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+                v = line.split("=")[1].split()
+                tot += float(v[0]) * unit[v[1]]
+        return tot or None
+    except Exception:       # noqa: BLE001
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -367,7 +384,7 @@ def run_ours(args, cfg):
                            "NCCL all-reduce of packed statistics + " if world > 1 else ""),
                        "var_x_written": True},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
+                         "traffic": ncu_traffic(dom[0]) if args.config == "c2" else None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_estep": alg_bytes,
                          "whole_step_achieved": step_ach, "whole_step_frac": step_ach / peak,
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}},
