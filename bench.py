@@ -242,6 +242,9 @@ def run_reference(args, cfg):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, cfg):
+    # libraries (NCCL, symmetric memory) may print to stdout: keep fd 1 for the ONE JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from pysvihmm_b200 import _lib as L
@@ -275,8 +278,18 @@ def run_ours(args, cfg):
     var_x = torch.empty((B, T, K), dtype=torch.float32, device=dev)
     stats = eng.new_stats()
 
+    # N > 1: the sum over ranks of the statistics is taken inside the global-step kernel over NVLink
+    # peer memory (sharding.PeerExchange); --nccl keeps the plain NCCL all-reduce for comparison
+    px = None
+    if world > 1 and not args.nccl:
+        from pysvihmm_b200.sharding import PeerExchange
+        px = PeerExchange(eng, dist)
+
     def step(i, it):
         eng.estep(starts_dev[i], T, flags=flags, var_x=var_x, stats=stats)
+        if px is not None:
+            px.global_update(stats, (it + 1.) ** -0.7, bA, bE)
+            return
         if world > 1:
             allreduce_stats(stats, dist)
         eng.global_update(stats, (it + 1.) ** -0.7, bA, bE)
@@ -335,6 +348,11 @@ def run_ours(args, cfg):
         lr = (it + 1.) ** -0.7
         if world == 1:
             eng.svi_step_host(starts_h[i], T, lr, bA, bE, next_starts=nxt, flags=flags, stats_out=stats_h)
+        elif px is not None:
+            eng.estep_streamed(starts_h[i], T, next_starts=nxt, flags=flags, stats=stats_d)
+            px.global_update(stats_d, lr, bA, bE)
+            stats_pin.copy_(px.reduced_stats(stats_d), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         else:
             eng.estep_streamed(starts_h[i], T, next_starts=nxt, flags=flags, stats=stats_d)
             allreduce_stats(stats_d, dist)
@@ -381,7 +399,8 @@ def run_ours(args, cfg):
                        "series": "%d x %d fp32 (%.0f MB) resident in HBM, larger than L2; fresh random "
                                  "windows every step (no L2 flush needed)" % (T_FULL, D, T_FULL * D * 4 / 1e6),
                        "step": "E-step (B windows) + %sglobal natural-gradient update" % (
-                           "NCCL all-reduce of packed statistics + " if world > 1 else ""),
+                           ("" if world == 1 else "NCCL all-reduce of packed statistics + " if px is None else
+                            "sum over ranks by P2P loads over NVLink inside the ")),
                        "var_x_written": True},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom[0]) if args.config == "c2" else None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
@@ -399,7 +418,7 @@ def run_ours(args, cfg):
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_estep_rate(cfg, 12.0, 400)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -412,6 +431,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: plain NCCL all-reduce instead of the fused peer sum")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

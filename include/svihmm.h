@@ -183,6 +183,23 @@ int svihmm_svi_step_host(svihmm_ctx* ctx, const int64_t* starts_host, int B, int
 int svihmm_global_update(svihmm_ctx* ctx, const double* stats, double lrate, double bfact_A,
                          double bfact_E, void* stream);
 
+/* Multi-GPU (one process per GPU, windows of a minibatch sharded over the ranks): the sum over ranks
+ * of the minibatch statistics (the accumulation hmmsgd_metaobs.py:430-433) is taken INSIDE the
+ * global-step kernel over NVLink peer memory instead of a separate NCCL all-reduce: every block
+ * pushes the statistics it consumes into receive slots of all peers (P2P stores), raises per-block
+ * sequence flags, and sums the received copies in rank order (bitwise identical on every rank).
+ *   svihmm_comm_buffer_len      doubles each rank must allocate as PEER-ACCESSIBLE, zero-initialised
+ *                               device memory (e.g. torch.distributed._symmetric_memory)
+ *   svihmm_comm_attach          peer_ptrs[p] = device address of rank p's area as seen from this rank
+ *   svihmm_global_update_peers  every rank calls it once per step with ITS statistics (device): the
+ *                               exchange and the update hmmsgd_metaobs.py:1010-1084 in one launch
+ *   svihmm_get_reduced_stats    the all-reduced statistics of the last step (for the bound / logging) */
+size_t svihmm_comm_buffer_len(const svihmm_ctx* ctx);
+int svihmm_comm_attach(svihmm_ctx* ctx, int rank, int world, const uint64_t* peer_ptrs);
+int svihmm_global_update_peers(svihmm_ctx* ctx, const double* stats, double lrate, double bfact_A,
+                               double bfact_E, void* stream);
+int svihmm_get_reduced_stats(svihmm_ctx* ctx, double* dst, int loc, void* stream);
+
 /* Batch coordinate-ascent step, hmmbatchcd.py:172-189 + distributions.py:240-276,324-329:
  * var_init = prior_init + q0, var_tran = prior_tran + A, conjugate NIW update per state.
  * stats must come from svihmm_estep with B = 1, flags without WRAP / ADD_PRIOR. */

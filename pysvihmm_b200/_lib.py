@@ -38,6 +38,10 @@ SYMBOLS = {
     "svihmm_estep_streamed": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _u, _vp]),
     "svihmm_svi_step_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _u, _d, _d, _d, _vp]),
     "svihmm_global_update": (_i, [_vp, _vp, _d, _d, _d, _vp]),
+    "svihmm_comm_buffer_len": (C.c_size_t, [_vp]),
+    "svihmm_comm_attach": (_i, [_vp, _i, _i, _vp]),
+    "svihmm_global_update_peers": (_i, [_vp, _vp, _d, _d, _d, _vp]),
+    "svihmm_get_reduced_stats": (_i, [_vp, _vp, _i, _vp]),
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
     "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -246,13 +246,21 @@ extern "C" int svihmm_set_prior(svihmm_ctx* c, const double* prior_tran, const d
 }
 
 // One launch: (optional) global update of the master parameters + all derived per-step constants.
+// blocks of k_global_step (= flags per source rank in the exchange area): transitions + emission
+// blocks + mixture weights, the same on every rank
+static int comm_blocks(const svihmm_ctx* c) {
+  const int KE = c->KE;
+  const int nblk = c->kind == SVIHMM_EMIT_NIW_DIAG ? std::max(1, std::min(KE, (KE * c->D + 255) / 256)) : KE;
+  return 1 + nblk + (c->C > 1 ? 1 : 0);
+}
 static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate, double bA, double bE,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool peers = false) {
   const int K = c->K, D = c->D;
   GlobalArgs ga;
   ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; ga.mode = mode;
   ga.user_init = c->user_init; ga.plen = c->plen;
   ga.KE = c->KE; ga.C = c->C; ga.omega = c->omega; ga.omega_prior = c->omega_prior; ga.lw = c->lw;
+  ga.world = 1; ga.rank = 0; ga.nb = 0; ga.seq = 0; ga.red_out = nullptr; ga.slen = c->slen;
   ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
   ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
@@ -266,6 +274,11 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   size_t smem = (2 * (size_t)K + 2) * sizeof(double);
   if (!ga.diag && !ga.cat) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (peers) {
+    ga.world = c->comm_world; ga.rank = c->comm_rank; ga.seq = ++c->comm_seq; ga.red_out = c->stage_stats;
+    ga.nb = comm_blocks(c);
+    for (int p = 0; p < c->comm_world; ++p) ga.xbase[p] = (unsigned long long*)c->comm_peer[p];
+  }
   static const bool gdbg = getenv("SVIHMM_GLOBAL_DBG") != nullptr;
   ga.dbg = nullptr;
   if (gdbg) CU(cudaMalloc((void**)&ga.dbg, 128));
@@ -1193,6 +1206,38 @@ extern "C" int svihmm_global_update(svihmm_ctx* c, const double* stats, double l
   if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
   CU(cudaSetDevice(c->device));
   return run_global(c, GM_SVI, stats, lrate, bA, bE, (cudaStream_t)stream);
+}
+
+// ---- multi-GPU: one-shot all-reduce over NVLink peer memory fused into the global step --------------
+extern "C" int svihmm_comm_attach(svihmm_ctx* c, int rank, int world, const uint64_t* peer_ptrs) {
+  if (!c || !peer_ptrs) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(SVIHMM_EINVAL, "rank %d / world %d (one node, <= 8 GPUs)", rank, world);
+  c->comm_world = world; c->comm_rank = rank; c->comm_seq = 0;
+  for (int p = 0; p < world; ++p) c->comm_peer[p] = (void*)(uintptr_t)peer_ptrs[p];
+  return SVIHMM_OK;
+}
+
+extern "C" size_t svihmm_comm_buffer_len(const svihmm_ctx* c) {
+  return c ? (size_t)8 * comm_blocks(c) + (size_t)2 * 8 * c->slen : 0;      // sized for any world <= 8
+}
+
+extern "C" int svihmm_global_update_peers(svihmm_ctx* c, const double* stats, double lrate, double bA, double bE,
+                                          void* stream) {
+  if (!c || !stats) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  if (c->comm_world < 2) return fail(SVIHMM_ESTATE, "svihmm_comm_attach has not been called with world >= 2");
+  CU(cudaSetDevice(c->device));
+  return run_global(c, GM_SVI, stats, lrate, bA, bE, (cudaStream_t)stream, true);
+}
+
+extern "C" int svihmm_get_reduced_stats(svihmm_ctx* c, double* dst, int loc, void* stream) {
+  if (!c || !dst) return fail(SVIHMM_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(dst, c->stage_stats, sizeof(double) * c->slen,
+                     loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
 }
 
 extern "C" int svihmm_batch_update(svihmm_ctx* c, const double* stats, void* stream) {

@@ -51,6 +51,8 @@ struct svihmm_ctx {
   int64_t sg_age[SVIHMM_NSLOT], sg_clock;             // last use of each slot (LRU replacement)
   int sg_pending[SVIHMM_NSLOT];                       // staged, not consumed by an E-step yet
   double* pin_stats;
+  // peer exchange (svihmm_comm_attach): [16 u64 flags | stats parity 0 | stats parity 1] per rank
+  int comm_world, comm_rank; unsigned long long comm_seq; void* comm_peer[8];
   // workspaces
   size_t cap_rows, cap_B, cap_part;
   double *ll_ws, *mx_ws, *seq_ws, *lt_ws;

@@ -18,6 +18,15 @@ struct GlobalArgs {
   int K, D, DD, diag, cat, mode, user_init;
   int KE, C;                                // emission components K*C, components per state
   double *omega, *omega_prior, *lw;         // mixtures only
+  // one-shot all-reduce over NVLink peer memory (world > 1).  Exchange area of every rank:
+  // [ flags: world x nb u64 | receive slots: 2 parities x world x slen doubles ]; xbase[p] = rank p's
+  // area as addressed from this rank; stats = this rank's own statistics (plain device memory);
+  // red_out = local buffer receiving the sums
+  int world, rank, nb;
+  unsigned long long* xbase[8];
+  unsigned long long seq;
+  double* red_out;
+  size_t slen;
   size_t plen;
   double *W, *vinit, *emit;                 // vinit: [0,K) the vector in use, [K,2K) the user-given one
   const double *prior_tran, *prior_init, *prior_emit, *stats;
@@ -54,6 +63,56 @@ __device__ inline GStats gstats(const double* s, int K, int KE, int D, int DD) {
   GStats v;
   v.A = s; v.n = s + (size_t)K * K; v.sx = v.n + KE; v.sxx = v.sx + (size_t)KE * D; v.q0 = v.sxx + (size_t)KE * DD;
   return v;
+}
+
+// ---- fused all-reduce of the statistics (multi-GPU) ----------------------------------------------
+// The windows of a minibatch are sharded over the ranks (hmmsgd_metaobs.py:405-433 only ADDS their
+// results), so the global step needs sum_p stats_p.  Instead of an NCCL all-reduce followed by the
+// update kernel, every block of k_global_step exchanges exactly the statistics IT consumes with the
+// same block of every peer over NVLink: it PUSHES its range of the local statistics into a receive
+// slot in each peer's memory (posted P2P stores: one-way latency, no round trip), fences, raises a
+// per-(source, block) sequence flag in the peer's memory, waits on its OWN flags (local polling) and
+// sums the received copies in rank order -- so every rank gets bitwise identical sums and the
+// replicas stay in lock-step -- into red_out, which the update code then reads as usual.  Receive
+// slots alternate by step parity: a peer cannot push step s+2 before this rank has raised its flags
+// of step s+1, i.e. finished reading the slots of step s.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_peer(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+struct CommRange { size_t lo, hi; };
+__device__ void comm_exchange(const GlobalArgs& a, const CommRange* rg, const int nrg) {
+  const int tid = threadIdx.x, nth = blockDim.x, W = a.world, me = a.rank;
+  const size_t nflag = (size_t)W * a.nb;
+  const size_t par = (size_t)(a.seq & 1) * W * a.slen;
+  // push this block's ranges into slot `me` of every peer
+  for (int r = 0; r < nrg; ++r)
+    for (size_t i = rg[r].lo + tid; i < rg[r].hi; i += nth) {
+      const double v = a.stats[i];
+      for (int p = 0; p < W; ++p)
+        if (p != me) st_peer(reinterpret_cast<double*>(a.xbase[p] + nflag) + par + (size_t)me * a.slen + i, v);
+    }
+  __syncthreads();                       // every thread's pushes happen-before the flags below: the release at
+  if (tid < W && tid != me) {            // system scope is cumulative over what the barrier made visible to its thread
+    st_release_sys(a.xbase[tid] + (size_t)me * a.nb + blockIdx.x, a.seq);          // tell peer `tid`
+    const unsigned long long* mine = a.xbase[me] + (size_t)tid * a.nb + blockIdx.x; // hear from peer `tid`
+    while (ld_acquire_sys(mine) < a.seq) {}
+  }
+  __syncthreads();
+  const double* rcv = reinterpret_cast<const double*>(a.xbase[me] + nflag) + par;
+  for (int r = 0; r < nrg; ++r)
+    for (size_t i = rg[r].lo + tid; i < rg[r].hi; i += nth) {
+      double s = 0.0;
+      for (int p = 0; p < W; ++p) s += p == me ? a.stats[i] : __ldcv(rcv + (size_t)p * a.slen + i);
+      a.red_out[i] = s;
+    }
 }
 
 // ---- block 0 -------------------------------------------------------------------------------
@@ -461,8 +520,31 @@ __device__ void global_mix_block(const GlobalArgs& a) {
 }
 
 // grid: 1 + (diag ? nblk_diag : K) blocks.
-__global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a, const int nblk_emit) {
+__global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a_in, const int nblk_emit) {
   extern __shared__ double gsm[];
+  GlobalArgs a = a_in;
+  if (a.world > 1 && a.mode != GM_PREP) {
+    const size_t KK = (size_t)a.K * a.K, o_n = KK, o_sx = o_n + a.KE, o_sxx = o_sx + (size_t)a.KE * a.D,
+                 o_q0 = o_sxx + (size_t)a.KE * a.DD;
+    CommRange rg[4];
+    int nrg = 0;
+    rg[nrg++] = {o_q0 + a.K, a.slen};                            // tail: every block (B count, bounds)
+    if (blockIdx.x == 0) { rg[nrg++] = {0, KK}; rg[nrg++] = {o_q0, o_q0 + a.K}; }
+    else if ((int)blockIdx.x == 1 + nblk_emit) rg[nrg++] = {o_n, o_sx};
+    else {
+      int k0 = blockIdx.x - 1, k1 = k0 + 1;                      // full / categorical: one component per block
+      if (a.diag) { const int per = (a.KE + nblk_emit - 1) / nblk_emit; k0 = (blockIdx.x - 1) * per; k1 = min(a.KE, k0 + per); }
+      if (k0 < k1) {
+        rg[nrg++] = {o_n + k0, o_n + k1};
+        rg[nrg++] = {o_sx + (size_t)k0 * a.D, o_sx + (size_t)k1 * a.D};
+        rg[nrg++] = {o_sxx + (size_t)k0 * a.DD, o_sxx + (size_t)k1 * a.DD};
+      }
+    }
+    comm_exchange(a, rg, nrg);
+    __threadfence();
+    __syncthreads();
+    a.stats = a.red_out;                                         // the update reads the sums
+  }
   if (blockIdx.x == 0) global_tran_block(a, gsm);
   else if ((int)blockIdx.x == 1 + nblk_emit) global_mix_block(a);
   else if (a.cat) global_emit_cat_block(a, blockIdx.x - 1, gsm);

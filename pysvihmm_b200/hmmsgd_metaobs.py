@@ -56,7 +56,7 @@ class VBHMM(VariationalHMMBase):
                  init_init=None, init_tran=None, maxit=100, verbose=False, adagrad=False,
                  metaobs_fun='unif', seed=None, sts=None, fullpred_freq=10, fullpred_sched=None,
                  growBuffer=False, bufferBudget=False, obs_dtype="f64", device=None,
-                 track_elbo=True, pairwise_mode="ref_outer"):
+                 track_elbo=True, pairwise_mode="ref_outer", peer_allreduce=True):
         """hmmsgd_metaobs.py:78-208.  Engine kwargs: obs_dtype, device, track_elbo (False skips the
         per-iteration host read of the bound), pairwise_mode ('ref_outer' = the reference's
         product-of-marginals statistic, 'exact_xi' = true pairwise posteriors)."""
@@ -88,6 +88,8 @@ class VBHMM(VariationalHMMBase):
         self.cur_mo = None
         self.batchfactor = 1.
         self.track_elbo = track_elbo
+        self.peer_allreduce = peer_allreduce   # N > 1: sum over ranks inside the global-step kernel (NVLink P2P)
+        self._px = None
         if pairwise_mode not in ("ref_outer", "exact_xi"):
             raise RuntimeError("pairwise_mode must be 'ref_outer' or 'exact_xi'")
         self.pairwise_mode = pairwise_mode
@@ -150,7 +152,12 @@ class VBHMM(VariationalHMMBase):
         if dist is not None:
             starts = shard_starts(starts, dist.get_rank(), dist.get_world_size())
         vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x, trim=trim)
-        allreduce_stats(stats, dist)        # one sum all-reduce of the packed statistics per step
+        if dist is not None and self.peer_allreduce and dist.get_backend() == "nccl":
+            if self._px is None:            # the sum over ranks happens inside global_update (P2P over NVLink)
+                from .sharding import PeerExchange
+                self._px = PeerExchange(eng, dist)
+        else:
+            allreduce_stats(stats, dist)    # one sum all-reduce of the packed statistics per step
         self._var_x_batch = vx
         self._last_B, self._last_T = len(starts), T
         return stats
@@ -387,7 +394,11 @@ class VBHMM(VariationalHMMBase):
                      np.concatenate([np.asarray(e[2], dtype=float).ravel() for e in emit_inter]),
                      np.zeros(K + 4)]
             stats = torch.from_numpy(np.concatenate(parts)).to(eng.device)
-        eng.global_update(stats, self.lrate, bfact_A, bfact_E)
+        if self._px is not None and isinstance(A_inter, torch.Tensor):
+            self._px.global_update(stats, self.lrate, bfact_A, bfact_E)
+            self._px.reduced_stats(stats)   # callers read the all-reduced statistics from `stats`
+        else:
+            eng.global_update(stats, self.lrate, bfact_A, bfact_E)
         self._host_stale = True
 
     def full_local_update(self):

@@ -28,3 +28,49 @@ def allreduce_stats(stats, dist=None):
     if dist is not None:
         dist.all_reduce(stats)
     return stats
+
+
+class PeerExchange(object):
+    """One-shot all-reduce of the packed statistics over NVLink peer memory, fused into the
+    global-step kernel (svihmm_global_update_peers) instead of a separate NCCL all-reduce.
+
+    PyTorch is plumbing here: torch.distributed._symmetric_memory allocates one peer-accessible
+    exchange area per rank (flags + receive slots) and hands every rank the device addresses of all
+    of them; the exchange itself (P2P pushes, sequence flags, rank-ordered sums, update) is the
+    hand-written kernel.  Usage per global step, on every rank:
+        eng.estep(starts, T, stats=stats)            # (or estep_streamed) this rank's windows
+        px.global_update(stats, lrate, bA, bE)       # replaces all_reduce + eng.global_update
+    """
+
+    def __init__(self, eng, dist):
+        import ctypes as C
+
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self.eng, self.lib, self._L = eng, eng.lib, L
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        n = int(self.lib.svihmm_comm_buffer_len(eng._h))
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=eng.device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        torch.cuda.synchronize(eng.device)
+        dist.barrier()                                    # every rank's flags are zero before first use
+        ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        L.check(self.lib.svihmm_comm_attach(eng._h, self.rank, self.world, ptrs))
+
+    def global_update(self, stats, lrate, bfact_A, bfact_E):
+        import ctypes as C
+        self._L.check(self.lib.svihmm_global_update_peers(self.eng._h, C.c_void_p(stats.data_ptr()), float(lrate),
+                                                          float(bfact_A), float(bfact_E), self.eng._stream()))
+
+    def reduced_stats(self, out=None):
+        """The all-reduced statistics of the last step (device tensor)."""
+        import ctypes as C
+
+        import torch
+        if out is None:
+            out = torch.empty(self.eng.slen, dtype=torch.float64, device=self.eng.device)
+        self._L.check(self.lib.svihmm_get_reduced_stats(self.eng._h, C.c_void_p(out.data_ptr()),
+                                                        self._L.LOC_DEVICE, self.eng._stream()))
+        return out

@@ -1,0 +1,48 @@
+"""torchrun --nproc-per-node N scripts/peer_allreduce_check.py: the fused peer all-reduce + update
+(svihmm_global_update_peers) against NCCL all-reduce + svihmm_global_update, same inputs."""
+import os, sys
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch, torch.distributed as dist
+from pysvihmm_b200 import _lib as L
+from pysvihmm_b200.engine import EStepEngine, pack_emit_dicts
+from pysvihmm_b200.sharding import PeerExchange, allreduce_stats
+from tests.helpers import make_random_problem
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for K, D, kind, T in [(16, 8, "niw_diag", 64), (5, 3, "niw_full", 40), (40, 4, "niw_full", 33)]:
+    p = make_random_problem(seed=K, K=K, D=D, T_full=2000, kind=kind, miss=0.05)
+    rs = np.random.RandomState(7)
+    engs = []
+    for _ in range(2):
+        e = EStepEngine(K, D, kind, device=local)
+        e.set_series(p["obs"], p["mask"], dtype="f64")
+        e.set_prior(p["prior_tran"], pack_emit_dicts(p["prior_emit"]))
+        e.set_globals(p["var_tran"], pack_emit_dicts(p["emit"]))
+        engs.append(e)
+    ref, new = engs
+    px = PeerExchange(new, dist)
+    st = ref.new_stats()
+    for it in range(5):
+        starts = rs.randint(0, 2000 - T, (world, 9))[rank]
+        ref.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR, stats=st, want_var_x=False)
+        allreduce_stats(st, dist)
+        ref.global_update(st, (it + 1.) ** -0.7, 2.0, 1.5)
+        st2 = new.new_stats()
+        new.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR, stats=st2, want_var_x=False)
+        px.global_update(st2, (it + 1.) ** -0.7, 2.0, 1.5)
+        a, b = st.cpu().numpy(), px.reduced_stats().cpu().numpy()
+        ok &= bool(np.allclose(a, b, rtol=1e-12, atol=1e-12))
+    for x, y in zip(ref.get_globals(), new.get_globals()):
+        ok &= bool(np.allclose(x, y, rtol=1e-10, atol=1e-12))
+    # replicas in lock-step: identical bits on every rank
+    g = torch.from_numpy(np.concatenate([v.ravel() for v in new.get_globals()])).cuda()
+    gs = [torch.empty_like(g) for _ in range(world)]
+    dist.all_gather(gs, g)
+    ok &= all(bool(torch.equal(gs[0], x)) for x in gs)
+    print("rank %d K=%d %s: %s" % (rank, K, kind, "OK" if ok else "MISMATCH"), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
