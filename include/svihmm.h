@@ -224,6 +224,15 @@ int svihmm_batchsgd_update(svihmm_ctx* ctx, const double* stats, double lrate, v
 int svihmm_get_locals(svihmm_ctx* ctx, double* lliks, float* alpha, double* mx, float* cs,
                       double* logz, int loc, void* stream);
 
+/* Forward-filter backward-sampling of state paths for the window obs[start : start+T] (the reference's
+ * native kernel hmm_fast.FFBS, hmm_fast.pyx:43-124, bound at hmmbase.py:410-411): forward filter with
+ * initial weights psi(var_init+eps) - psi(sum+eps) and transition weights log(var_tran + eps) (:82-100),
+ * then nsamples independent backward passes (:103-122) with a Philox stream per sample (the reference
+ * draws from libc rand(), so paths agree in distribution only).  z_out: nsamples*T int32 at `loc`.
+ * The forward table of the call stays readable through svihmm_get_locals (alpha, cs, mx). */
+int svihmm_ffbs(svihmm_ctx* ctx, const double* var_init, int64_t start, int T, int nsamples, uint64_t seed,
+                int32_t* z_out, int loc, void* stream);
+
 /* Number of kernels the engine launched on this ctx since creation (bench bookkeeping). */
 int64_t svihmm_launch_count(const svihmm_ctx* ctx);
 

@@ -570,3 +570,26 @@ def buffered_stats(obs, mask, starts, bufferL, L, var_tran, emit, prior_tran):
         emit_inter = e_i if emit_inter is None else [[u + v for u, v in zip(a, c)] for a, c in zip(emit_inter, e_i)]
     return dict(var_x=res['var_x'], A_inter=A_inter, emit_inter=emit_inter,
                 lb=float(np.sum(local_lower_bound(res['lalpha']))))
+
+
+# --------------------------------------------------------------------------
+# forward-filter backward-sampling (hmm_fast.pyx:43-124)
+# --------------------------------------------------------------------------
+def ffbs_tables(obs, var_init, var_tran, emit):
+    """The distribution hmm_fast.FFBS samples from: forward table with log(A + eps) transition weights
+    (hmm_fast.pyx:82-100; DBL_EPSILON) and the exact marginals / pairwise marginals of the sampled
+    path, P(z_t), P(z_t, z_{t+1}), obtained by a backward pass with the same weights."""
+    eps = np.finfo(np.float64).eps
+    mod_init = digamma(var_init + eps) - digamma(np.sum(var_init) + eps)
+    ltran = np.log(var_tran + eps)
+    ll = lliks_gaussian(obs[None], emit)
+    lalpha = forward_msgs(ll, mod_init, ltran)[0]
+    lbeta = backward_msgs(ll, ltran)[0]
+    marg = marginals(lalpha[None], lbeta[None])[0]
+    T, K = marg.shape
+    pair = np.empty((T - 1, K, K))
+    for t in range(T - 1):
+        lx = lalpha[t][:, None] + ltran + (ll[0, t + 1] + lbeta[t + 1])[None, :]
+        x = np.exp(lx - lx.max())
+        pair[t] = x / x.sum()
+    return lalpha, marg, pair

@@ -45,6 +45,7 @@ SYMBOLS = {
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
     "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "svihmm_ffbs": (_i, [_vp, _vp, _i64, _i, _i, C.c_uint64, _vp, _i, _vp]),
     "svihmm_launch_count": (_i64, [_vp]),
     "svihmm_set_profiling": (_i, [_vp, _i]),
     "svihmm_get_phase_ms": (_i, [_vp, _vp, _vp]),

@@ -14,6 +14,7 @@
 #include "fused.cuh"
 #include "fused_pipe.cuh"
 #include "wide64.cuh"
+#include "ffbs.cuh"
 
 static thread_local std::string g_err;
 
@@ -896,6 +897,46 @@ extern "C" int svihmm_set_var_init(svihmm_ctx* c, const double* var_init, int lo
   c->user_init = var_init != nullptr;
   if (var_init && (rc = copy_in(c->vinit + c->K, var_init, sizeof(double) * c->K, loc, st))) return rc;
   return run_global(c, GM_PREP, nullptr, 0.0, 0.0, 0.0, st);
+}
+
+// ---- forward-filter backward-sampling (hmm_fast.pyx:43-124) ---------------------------------------
+extern "C" int svihmm_ffbs(svihmm_ctx* c, const double* var_init, int64_t start, int T, int nsamples,
+                           uint64_t seed, int32_t* z_out, int loc, void* stream) {
+  if (!c || !var_init || !z_out) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals) return fail(SVIHMM_ESTATE, "svihmm_set_globals has not been called");
+  if (!c->obs) return fail(SVIHMM_ESTATE, "svihmm_set_series has not been called");
+  if (T < 1 || nsamples < 1 || start < 0 || start + T > c->T_full)
+    return fail(SVIHMM_EINVAL, "window [%lld, +%d) outside the series / nsamples = %d", (long long)start, T, nsamples);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = c->K;
+  // scratch: P' (K*K) + pi0' (K) floats, var_init (K) doubles, the start index, the sampled paths
+  float* Pf = nullptr; double* vi = nullptr; int64_t* dstart = nullptr; int* zd = nullptr;
+  CU(dalloc(&Pf, (size_t)K * K + K)); CU(dalloc(&vi, (size_t)K)); CU(dalloc(&dstart, (size_t)1));
+  CU(dalloc(&zd, (size_t)nsamples * T));
+  int rc = copy_in(vi, var_init, sizeof(double) * K, loc, st);
+  if (!rc) rc = copy_in(dstart, &start, sizeof(int64_t), SVIHMM_LOC_HOST, st);
+  if (!rc) {
+    k_ffbs_prep<<<1, 256, 0, st>>>(K, c->W, vi, Pf, Pf + (size_t)K * K);
+    c->launches++;
+    // expected log-likelihoods + the scaled forward filter of this ONE window with (P', pi0') swapped in;
+    // the marginals / statistics the E-step also produces are discarded (workspace only)
+    float* Pt_keep = c->Pt; float* pi0_keep = c->pi0;
+    c->Pt = Pf; c->pi0 = Pf + (size_t)K * K;
+    rc = estep_impl(c, c->obs, c->obs_dtype, c->mask, dstart, 1, T, nullptr, c->stage_stats,
+                    SVIHMM_KEEP_LOCALS, st);
+    c->Pt = Pt_keep; c->pi0 = pi0_keep;
+  }
+  if (!rc) {
+    k_ffbs_sample<<<(nsamples * 32 + 127) / 128, 128, 0, st>>>(nsamples, T, K, c->alpha_ws, Pf, seed, zd);
+    c->launches++;
+    cudaError_t e = cudaMemcpyAsync(z_out, zd, sizeof(int) * (size_t)nsamples * T,
+                                    loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(SVIHMM_ECUDA, "svihmm_ffbs: %s", cudaGetErrorString(e));
+  } else cudaStreamSynchronize(st);
+  cudaFree(Pf); cudaFree(vi); cudaFree(dstart); cudaFree(zd);
+  return rc;
 }
 
 // gather B windows of T rows (row = rowbytes) from a mapped host (or device) series into a dense

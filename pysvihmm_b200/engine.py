@@ -271,6 +271,16 @@ class EStepEngine(object):
                                            L.LOC_HOST, self._stream()))
         return dict(lliks=ll, alpha=al, mx=mx, cs=cs, logZ=lz[:, 0], lb_q4=lz[:, 1])
 
+    def ffbs(self, var_init, T=None, start=0, nsamples=1, seed=0):
+        """hmm_fast.FFBS (hmm_fast.pyx:43-124): nsamples state paths (nsamples, T) int32 for the window
+        obs[start:start+T] (default: the whole series)."""
+        T = self.T_full if T is None else int(T)
+        vi = _f64(var_init)
+        z = np.empty((int(nsamples), T), dtype=np.int32)
+        L.check(self.lib.svihmm_ffbs(self._h, _ptr(vi), int(start), T, int(nsamples), int(seed), _ptr(z),
+                                     L.LOC_HOST, self._stream()))
+        return z
+
     def launch_count(self):
         return int(self.lib.svihmm_launch_count(self._h))
 

@@ -259,6 +259,25 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
             elbo += self.var_emit[k].get_vlb()
         return elbo + float(np.sum(self._lb_q4))
 
+    # ------------------------------------------------------------------ FFBS (hmmbase.py:231-264, hmm_fast.pyx)
+    def FFBS(self, var_init, seed=None):
+        """Forward-filter backward-sampling of one state path (hmmbase.py:231-264; the sampling loop
+        follows the native version hmm_fast.pyx:103-122, the numpy one never refreshes p, :260-262)."""
+        return self.ffbs_fast(var_init, seed=seed)[0]
+
+    def ffbs_fast(self, var_init, lalpha_init=None, seed=None):
+        """hmm_fast.FFBS (bound at hmmbase.py:410-411): returns (z, lalpha).  lalpha_init is accepted for
+        signature compatibility; the filter is recomputed on the device (it costs one forward pass)."""
+        eng = self._ensure_engine()
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))      # tied to the legacy global RNG like rand()
+        z = eng.ffbs(np.asarray(var_init, dtype=np.float64), nsamples=1, seed=seed)[0].astype(np.int64)
+        loc = eng.get_locals(1, self.T)
+        with np.errstate(divide='ignore'):
+            cum = np.cumsum(np.log(loc["cs"][0].astype(np.float64)) + loc["mx"][0])
+            lalpha = np.log(loc["alpha"][0].astype(np.float64)) + cum[:, None]
+        return z, lalpha
+
     # ------------------------------------------------------------------ metrics
     def hamming_dist(self, full_var_x, true_sts):
         """hmmbase.py:346-362."""

@@ -299,3 +299,33 @@ def test_vbhmm_infer_adaptive_and_growbuffer_run():
     assert np.isfinite(hmm.var_tran).all() and np.all(hmm.var_tran > 0)
     with pytest.raises(RuntimeError):
         hmm.infer(adaptive=True)
+
+
+def test_ffbs_samples_follow_the_reference_distribution():
+    """svihmm_ffbs / ffbs_fast (hmm_fast.pyx:43-124): the forward table against the oracle's restatement
+    (log(A+eps) transition weights, :97-100) and the empirical marginals / pairwise frequencies of 6000
+    sampled paths against the exact ones of that distribution (5 sigma binomial bands); different RNG
+    than libc rand(), so agreement is in distribution."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import hmmbatchcd as H
+    from tests.helpers import make_random_problem
+    for K, T in [(3, 40), (40, 25)]:
+        p = make_random_problem(seed=K, K=K, D=2, T_full=T, kind="niw_full", miss=0.0, sep=1.0)
+        var_init = 0.5 + np.random.RandomState(1).rand(K)
+        hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), _gauss_objs(p), init_tran=p["var_tran"].copy())
+        lalpha_ref, marg, pair = O.ffbs_tables(p["obs"], var_init, p["var_tran"], p["emit"])
+        z, lalpha = hmm.ffbs_fast(var_init, seed=5)
+        assert z.shape == (T,) and z.min() >= 0 and z.max() < K
+        assert np.max(np.abs(lalpha - lalpha_ref)) < 5e-4 * max(1., np.abs(lalpha_ref).max())
+        n = 6000
+        zs = hmm._ensure_engine().ffbs(var_init, nsamples=n, seed=11)
+        assert zs.shape == (n, T)
+        freq = np.stack([(zs == k).mean(0) for k in range(K)], axis=1)            # (T, K)
+        band = 5. * np.sqrt(np.maximum(marg * (1 - marg), 1e-4) / n) + 2e-3
+        assert np.all(np.abs(freq - marg) < band), float(np.max(np.abs(freq - marg) - band))
+        t = T // 2
+        pf = np.zeros((K, K))
+        np.add.at(pf, (zs[:, t], zs[:, t + 1]), 1. / n)
+        bandp = 5. * np.sqrt(np.maximum(pair[t] * (1 - pair[t]), 1e-4) / n) + 2e-3
+        assert np.all(np.abs(pf - pair[t]) < bandp)
+        assert not np.array_equal(zs[0], zs[1]) or K == 1                         # independent streams
