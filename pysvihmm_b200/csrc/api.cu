@@ -739,7 +739,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     // register-blocked float64 kernel with the row maximum and b = exp(ll - max) fused in
     const unsigned grid = (unsigned)((R + 2 * ERB_NT - 1) / (2 * ERB_NT));
 #define ERB_LAUNCH(DV) do { \
-      const size_t smem = (size_t)ERB_KC * (erb_len(DV) + DV + (DV & 1)) * sizeof(double); \
+      const size_t smem = (size_t)2 * ERB_KC * (erb_len(DV) + DV + (DV & 1)) * sizeof(double); \
+      if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_full_rb<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_emit_full_rb<DV><<<grid, ERB_NT, smem, st>>>(R, T, Ke, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, \
                                                      c->ck, ll_out, b_out, c->mx_ws); } while (0)
     if (D == 8) ERB_LAUNCH(8); else if (D == 16) ERB_LAUNCH(16); else ERB_LAUNCH(32);

@@ -41,7 +41,7 @@ k_emit_full_rb(int64_t R, int T, int K, const void* __restrict__ obs, int dtype,
   constexpr int PL = erb_len(D);                 // padded triangle
   constexpr int SL = PL + D + (D & 1);           // + gk (kept 16-byte aligned)
   constexpr int tri = D * (D + 1) / 2;
-  extern __shared__ __align__(16) double esm[];  // [ERB_KC][SL]
+  extern __shared__ __align__(16) double esm[];  // [2][ERB_KC][SL]
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * (2 * ERB_NT) + tid, r1 = r0 + ERB_NT;
   double x0[D], x1[D];
@@ -74,26 +74,43 @@ k_emit_full_rb(int64_t R, int T, int K, const void* __restrict__ obs, int dtype,
     }
   }
   double m0 = -INFINITY, m1 = -INFINITY;
-  for (int kc = 0; kc < K; kc += ERB_KC) {
-    const int nk = min(ERB_KC, K - kc);
-    __syncthreads();
-    // stage the factors of states kc..kc+nk-1 in the padded layout (pads = 0); an odd tail state
-    // is paired with an all-zero factor
-    const int nks = (nk + 1) & ~1;
-    for (int idx = tid; idx < nks * D * (D + 1); idx += ERB_NT) {    // (state, i, j) with j <= i + 1 (pad)
+  // The factors of ERB_KC states at a time live in shared memory in the padded layout, double
+  // buffered: the refill of the next tile is issued with cp.async (8 bytes per element, remapped on
+  // the fly from the packed-lower layout of the global step) BEFORE the current tile is consumed, so
+  // its L2 latency hides behind ~70 k FP64-pipe cycles of work (ncu on the synchronous version:
+  // long-scoreboard stalls at every refill, FP64 pipe 42 % active).
+  auto stage = [&](const int kc_, double* buf) {
+    const int nk_ = min(ERB_KC, K - kc_);
+    for (int idx = tid; idx < nk_ * D * (D + 1); idx += ERB_NT) {    // (state, i, j), j <= i
       const int s = idx / (D * (D + 1)), e = idx - s * (D * (D + 1));
       const int i = e / (D + 1), j = e - i * (D + 1);
-      if (j <= i) esm[s * SL + erb_off(i) + j] = s < nk ? Rs[(size_t)(kc + s) * tri + (size_t)i * (i + 1) / 2 + j] : 0.0;
-      else if (j == i + 1 && !(i & 1)) esm[s * SL + erb_off(i) + j] = 0.0;
+      if (j <= i) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + s * SL + erb_off(i) + j);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(Rs + (size_t)(kc_ + s) * tri + (size_t)i * (i + 1) / 2 + j) : "memory");
+      }
     }
-    for (int idx = tid; idx < nks * D; idx += ERB_NT) {
+    for (int idx = tid; idx < nk_ * D; idx += ERB_NT) {
       const int s = idx / D, d = idx - s * D;
-      esm[s * SL + PL + d] = s < nk ? gk[(size_t)(kc + s) * D + d] : 0.0;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + s * SL + PL + d);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gk + (size_t)(kc_ + s) * D + d) : "memory");
     }
-    __syncthreads();
+    if (nk_ & 1)                                                   // an odd tail state is paired with an all-zero factor
+      for (int idx = tid; idx < SL; idx += ERB_NT) buf[nk_ * SL + idx] = 0.0;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int idx = tid; idx < 2 * ERB_KC * SL; idx += ERB_NT) esm[idx] = 0.0;   // pads of both buffers stay zero
+  __syncthreads();
+  stage(0, esm);
+  int cur = 0;
+  for (int kc = 0; kc < K; kc += ERB_KC, cur ^= 1) {
+    const int nk = min(ERB_KC, K - kc);
+    const double* tile = esm + (size_t)cur * ERB_KC * SL;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                 // tile kc has landed; everyone is done with the other buffer
+    if (kc + ERB_KC < K) stage(kc + ERB_KC, esm + (size_t)(cur ^ 1) * ERB_KC * SL);
 #pragma unroll 1
     for (int s = 0; s < nk; s += 2) {
-      const double* RA = esm + s * SL;
+      const double* RA = tile + s * SL;
       const double* RB = RA + SL;
       const double2* RA2 = reinterpret_cast<const double2*>(RA);
       const double2* RB2 = reinterpret_cast<const double2*>(RB);
