@@ -638,8 +638,16 @@ static int stats_sym_phase(svihmm_ctx* c, const void* obs, int dtype, const uint
     c->cap_part = need_part;
   }
   sa.part = c->part_ws;
-  dim3 grid((sa.NF + SS_TN - 1) / SS_TN, (unsigned)nsplit);
-  k_stats_sym<<<grid, SS_NT, 0, st>>>(sa);
+  static const bool no_mma = getenv("SVIHMM_STATS_FFMA") != nullptr;      // A/B switch: FFMA version
+  if (no_mma) {
+    dim3 grid((sa.NF + SS_TN - 1) / SS_TN, (unsigned)nsplit);
+    k_stats_sym<<<grid, SS_NT, 0, st>>>(sa);
+  } else {
+    dim3 grid((sa.NF + SM_NT * 8 - 1) / (SM_NT * 8), (unsigned)nsplit);
+    static bool attr_set = false;
+    if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM)); attr_set = true; }
+    k_stats_mma<<<grid, SS_NT, SM_SMEM, st>>>(sa);
+  }
   LAUNCHED(c);
   k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
       B, T, K, D, c->DD, sa.NF, sa.diag, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,

@@ -488,6 +488,191 @@ __global__ void __launch_bounds__(SS_NT) k_stats_sym(const StatsSymArgs a) {
   }
 }
 
+// Tensor-core version of k_stats_sym: the same contraction Out[m][n] = sum_r q[r][m] F[r][n] with
+// mma.m16n8k8 TF32, every operand split hi/lo (3xTF32, float32 accumulators), so the statistics keep
+// float32-level accuracy (the 1e-5 parity bound) at ~1/3 of the issue slots of the FFMA version.
+// CTA = 4 warps, warp w owns the 16-state tile w; the CTA covers SM_NT feature tiles of 8 columns and
+// one row split.  Per stage of 32 rows the feature columns are generated ONCE per CTA (already split
+// into TF32 hi/lo words) into shared memory with a row stride of 136 words, and q with a stride of 72,
+// which makes every fragment load conflict-free (bank = 8*tig + g).
+#define SM_NT 16              // feature tiles (of 8 columns) per CTA
+#define SM_FS 136             // row stride of the feature stage (words)
+#define SM_QS 72              // row stride of the q stage (words)
+#define SM_SMEM (4 * SS_RC * (2 * SM_QS + 2 * SM_FS + 2 * SS_XS) + 2 * 16 * SS_RC + 4 * SS_RC)
+__device__ __forceinline__ void sm_split(const float v, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float r = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void sm_mma(float (&d)[4], const unsigned (&a)[4], const unsigned b0, const unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(SS_NT) k_stats_mma(const StatsSymArgs a) {
+  // dynamic shared memory (SM_SMEM bytes): q rows and observation rows of TWO stages (the next stage is
+  // fetched with cp.async while the current one is consumed), the split feature stage, per-row scalars
+  extern __shared__ __align__(16) unsigned char smm[];
+  float (*Qs)[SS_RC][SM_QS] = reinterpret_cast<float (*)[SS_RC][SM_QS]>(smm);
+  float (*xs)[SS_RC][SS_XS] = reinterpret_cast<float (*)[SS_RC][SS_XS]>(Qs + 2);
+  unsigned (*Fh)[SM_FS] = reinterpret_cast<unsigned (*)[SM_FS]>(xs + 2);
+  unsigned (*Fl)[SM_FS] = Fh + SS_RC;
+  int64_t (*grow)[SS_RC] = reinterpret_cast<int64_t (*)[SS_RC]>(Fl + SS_RC);
+  int64_t (*nrow)[SS_RC] = grow + 2;
+  float* wv = reinterpret_cast<float*>(nrow + 2);
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, g = lane >> 2, tig = lane & 3;
+  const int K = a.K, D = a.D, T = a.T;
+  const int n0 = blockIdx.x * (SM_NT * 8);
+  const int64_t rbeg = (int64_t)blockIdx.y * a.rows_per_split;
+  const int64_t rend = min(a.R, rbeg + a.rows_per_split);
+  const int col = n0 + tid;                       // the feature column this thread generates (128 per CTA)
+  int kind = -1, d1 = D, d2 = D;
+  if (col < K) kind = 0;
+  else if (col < a.NF) {
+    kind = 1;
+    int c = col - K;
+    if (c == 0) { d1 = D; d2 = D; }
+    else if (c <= D) { d1 = c - 1; d2 = D; }
+    else {
+      c -= D + 1;
+      if (a.diag) { d1 = c; d2 = c; }
+      else { int i = 0; while (c >= D - i) { c -= D - i; ++i; } d1 = i; d2 = i + c; }
+    }
+  }
+  const bool need_x = n0 + SM_NT * 8 > K;
+  const bool mact = 16 * wp < K;                  // this warp's state tile exists
+  const bool xvec = a.dtype == SVIHMM_F32 && (D & 3) == 0 && ((((uintptr_t)a.obs) & 15) == 0);
+  const bool qvec = (K & 3) == 0 && ((((uintptr_t)a.q) & 15) == 0);
+  float acc[SM_NT][4];
+#pragma unroll
+  for (int j = 0; j < SM_NT; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+
+  // fetch stage `rc` into buffer `bf`: row indices with plain stores, q / x rows with cp.async
+  auto fetch = [&](const int64_t rc, const int bf) {
+    for (int idx = tid; idx < SS_RC * 16; idx += SS_NT) {          // q rows: 16 float4 per row (zero padded)
+      const int rr = idx >> 4, m4 = (idx & 15) * 4;
+      const int64_t r = rc + rr;
+      float* dst = &Qs[bf][rr][m4];
+      if (r < rend && qvec && m4 + 3 < K) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(a.q + r * K + m4) : "memory");
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = (r < rend && m4 + u < K) ? a.q[r * K + m4 + u] : 0.f;
+      }
+    }
+    if (tid < SS_RC) {
+      const int64_t r = rc + tid;
+      int64_t gg = -1, nx = -1;
+      if (r < rend) {
+        const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+        gg = a.starts[b] + t;
+        if (t + 1 < T) nx = r + 1; else if (a.wrap) nx = (int64_t)b * T;
+      }
+      grow[bf][tid] = gg; nrow[bf][tid] = nx;
+    }
+    if (need_x) {
+      // every thread recomputes the series row of the rows it fetches (grow of this stage is not visible yet)
+      if (xvec) {
+        const int v4 = D >> 2;
+        for (int idx = tid; idx < SS_RC * v4; idx += SS_NT) {
+          const int rr = idx / v4, d4 = (idx - rr * v4) * 4;
+          const int64_t r = rc + rr;
+          float* dst = &xs[bf][rr][d4];
+          if (r < rend) {
+            const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)),
+                         "l"((const float*)a.obs + (a.starts[b] + t) * D + d4) : "memory");
+          } else { dst[0] = dst[1] = dst[2] = dst[3] = 0.f; }
+        }
+      } else {
+        for (int idx = tid; idx < SS_RC * D; idx += SS_NT) {
+          const int rr = idx / D, d = idx - rr * D;
+          const int64_t r = rc + rr;
+          float v = 0.f;
+          if (r < rend) {
+            const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+            v = (float)ld_obs(a.obs, a.dtype, (a.starts[b] + t) * D + d);
+          }
+          xs[bf][rr][d] = v;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  fetch(rbeg, 0);
+  int bf = 0;
+  for (int64_t rc = rbeg; rc < rend; rc += SS_RC, bf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                              // stage rc is in buffer bf; everyone is done with the other buffer and F
+    if (rc + SS_RC < rend) fetch(rc + SS_RC, bf ^ 1);
+    if (need_x) {
+      if (tid < SS_RC) {
+        const int64_t gg = grow[bf][tid];
+        float w = 0.f;
+        if (gg >= 0) {
+          w = (a.mask && a.mask[gg]) ? 0.f : 1.f;
+          bool bad = false;
+          for (int d = 0; d < D; ++d) bad |= isnan(xs[bf][tid][d]);
+          if (bad || w == 0.f) { w = 0.f; for (int d = 0; d < D; ++d) xs[bf][tid][d] = 0.f; }
+        }
+        wv[tid] = w;
+        xs[bf][tid][D] = 1.f;
+      }
+      __syncthreads();
+    }
+    if (kind == 0) {
+#pragma unroll 8
+      for (int rr = 0; rr < SS_RC; ++rr) {
+        const int64_t nx = nrow[bf][rr];
+        unsigned hi, lo;
+        sm_split(nx >= 0 ? a.q[nx * K + col] : 0.f, hi, lo);
+        Fh[rr][tid] = hi; Fl[rr][tid] = lo;
+      }
+    } else {
+      const float live = kind == 1 ? 1.f : 0.f;       // columns beyond NF: zeros
+#pragma unroll 8
+      for (int rr = 0; rr < SS_RC; ++rr) {
+        unsigned hi, lo;
+        sm_split(live * wv[rr] * xs[bf][rr][d1] * xs[bf][rr][d2], hi, lo);
+        Fh[rr][tid] = hi; Fl[rr][tid] = lo;
+      }
+    }
+    __syncthreads();
+    if (mact) {
+#pragma unroll
+      for (int ks = 0; ks < SS_RC / 8; ++ks) {
+        const int r0 = ks * 8 + tig, r1 = r0 + 4, c0 = 16 * wp + g;
+        unsigned ah[4], al[4];
+        sm_split(Qs[bf][r0][c0], ah[0], al[0]); sm_split(Qs[bf][r0][c0 + 8], ah[1], al[1]);
+        sm_split(Qs[bf][r1][c0], ah[2], al[2]); sm_split(Qs[bf][r1][c0 + 8], ah[3], al[3]);
+        // all SM_NT tiles unconditionally (columns beyond NF hold zeros): no branches around the MMAs, and
+        // the three MMAs of a tile are spread over three sweeps so that consecutive MMAs are independent
+        const unsigned* fh0 = &Fh[r0][g]; const unsigned* fh1 = &Fh[r1][g];
+        const unsigned* fl0 = &Fl[r0][g]; const unsigned* fl1 = &Fl[r1][g];
+#pragma unroll
+        for (int j = 0; j < SM_NT; ++j) sm_mma(acc[j], al, fh0[8 * j], fh1[8 * j]);
+#pragma unroll
+        for (int j = 0; j < SM_NT; ++j) sm_mma(acc[j], ah, fl0[8 * j], fl1[8 * j]);
+#pragma unroll
+        for (int j = 0; j < SM_NT; ++j) sm_mma(acc[j], ah, fh0[8 * j], fh1[8 * j]);
+      }
+    }
+  }
+  if (mact) {
+#pragma unroll
+    for (int j = 0; j < SM_NT; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int m = 16 * wp + g + 8 * (c >> 1), n = n0 + 8 * j + 2 * tig + (c & 1);
+        if (m < K && n < a.NF) a.part[((size_t)blockIdx.y * K + m) * a.NF + n] = acc[j][c];
+      }
+  }
+}
+
 // Sum the row-split partials in float64, mirror the symmetric second moments, lay the statistics
 // out as include/svihmm.h documents (same tail as k_stats_finalize).
 __global__ void __launch_bounds__(256)
