@@ -200,6 +200,11 @@ int svihmm_global_update_peers(svihmm_ctx* ctx, const double* stats, double lrat
                                double bfact_E, void* stream);
 int svihmm_get_reduced_stats(svihmm_ctx* ctx, double* dst, int loc, void* stream);
 
+/* AdaGrad-like variant of the transition step in svihmm_global_update (hmmsgd_metaobs.py:1036-1040,
+ * VBHMM(adagrad=True)): ada_G += (var_tran-1)^2, step size ada_G^(-1/4) per entry instead of lrate;
+ * on = 1 (re)initialises ada_G to ones (:183), on = 0 restores the plain step. */
+int svihmm_set_adagrad(svihmm_ctx* ctx, int on, void* stream);
+
 /* Batch coordinate-ascent step, hmmbatchcd.py:172-189 + distributions.py:240-276,324-329:
  * var_init = prior_init + q0, var_tran = prior_tran + A, conjugate NIW update per state.
  * stats must come from svihmm_estep with B = 1, flags without WRAP / ADD_PRIOR. */

@@ -345,12 +345,19 @@ def diag_moment(e1, e2, e3, e4):
     return dict(mu=mu, sigma=e3 - mu * mu * e2, kappa=e2, nu=e4 - 3.)
 
 
-def svi_global_update(var_tran, emit, prior_emit, A_inter, emit_inter, lrate, T_full, L, S):
-    """hmmsgd_metaobs.py:1010-1069 (non-adagrad branch).
+def svi_global_update(var_tran, emit, prior_emit, A_inter, emit_inter, lrate, T_full, L, S, ada_G=None):
+    """hmmsgd_metaobs.py:1010-1069.  ada_G: None = plain step; a (K,K) array = the AdaGrad-like
+    branch :1036-1040 (updated IN PLACE like self.ada_G; the emissions always use lrate).
     emit / prior_emit: lists of dict(mu, sigma, kappa, nu); emit_inter[k] =
     [e1,e2,e3,e4] summed over the minibatch.  Returns (var_tran_new, emit_new)."""
     bfact = (T_full - 2 * L - 1) / (2. * L * S)
-    nats_new = (1. - lrate) * (var_tran - 1.) + lrate * bfact * A_inter
+    nats_old = var_tran - 1.
+    if ada_G is not None:
+        ada_G += nats_old ** 2
+        adaMatrix = ada_G ** .25
+        nats_new = (1. - 1.0 / adaMatrix) * nats_old + bfact * A_inter / adaMatrix
+    else:
+        nats_new = (1. - lrate) * nats_old + lrate * bfact * A_inter
     var_tran_new = nats_new + 1.
     bfact = (T_full - 2 * L - 1) / ((2. * L + 1.) * S)
     emit_new = []
@@ -367,7 +374,7 @@ def svi_global_update(var_tran, emit, prior_emit, A_inter, emit_inter, lrate, T_
 
 
 def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_emit,
-                       lrate, L, S=None, wrap=True, mask_ll=False):
+                       lrate, L, S=None, wrap=True, mask_ll=False, ada_G=None):
     """One global step of hmmsgd_metaobs.VBHMM.infer (:396-439) given the window
     start indices `starts` (window b = obs[starts[b] : starts[b]+T]).
     Returns dict with var_x (B,T,K), A_inter, emit_inter, lb, var_tran_new, emit_new."""
@@ -401,7 +408,7 @@ def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_e
                     emit_inter[k][j] = emit_inter[k][j] + e_i[k][j]
     lb = float(np.sum(local_lower_bound(res['lalpha'])))         # :436
     var_tran_new, emit_new = svi_global_update(var_tran, emit, prior_emit, A_inter,
-                                               emit_inter, lrate, T_full, L, S)
+                                               emit_inter, lrate, T_full, L, S, ada_G=ada_G)
     res.update(A_inter=A_inter, emit_inter=emit_inter, lb=lb, logZ=log_Z(res['lalpha']),
                var_tran_new=var_tran_new, emit_new=emit_new, var_init=var_init)
     return res

@@ -42,6 +42,7 @@ SYMBOLS = {
     "svihmm_comm_attach": (_i, [_vp, _i, _i, _vp]),
     "svihmm_global_update_peers": (_i, [_vp, _vp, _d, _d, _d, _vp]),
     "svihmm_get_reduced_stats": (_i, [_vp, _vp, _i, _vp]),
+    "svihmm_set_adagrad": (_i, [_vp, _i, _vp]),
     "svihmm_batch_update": (_i, [_vp, _vp, _vp]),
     "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -113,6 +113,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   CU(dalloc(&c->W, KK)); CU(dalloc(&c->vinit, 2 * (size_t)K)); CU(dalloc(&c->emit, KE * c->plen));
   CU(dalloc(&c->prior_tran, KK)); CU(dalloc(&c->prior_init, (size_t)K)); CU(dalloc(&c->prior_emit, KE * c->plen));
   CU(dalloc(&c->omega, KE)); CU(dalloc(&c->omega_prior, KE)); CU(dalloc(&c->lw, KE));
+  CU(dalloc(&c->ada_G, KK));
   CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
   CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * KE * D));
   CU(dalloc(&c->par2, 2 * KE * D)); CU(dalloc(&c->ckp, KE));
@@ -149,7 +150,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
-                  c->qin_ws, c->respin_ws, c->starts_in};
+                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -261,6 +262,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; ga.mode = mode;
   ga.user_init = c->user_init; ga.plen = c->plen;
   ga.KE = c->KE; ga.C = c->C; ga.omega = c->omega; ga.omega_prior = c->omega_prior; ga.lw = c->lw;
+  ga.ada_G = c->adagrad ? c->ada_G : nullptr;
   ga.world = 1; ga.rank = 0; ga.nb = 0; ga.seq = 0; ga.red_out = nullptr; ga.slen = c->slen;
   ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
   ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
@@ -1287,6 +1289,21 @@ extern "C" int svihmm_get_reduced_stats(svihmm_ctx* c, double* dst, int loc, voi
   CU(cudaMemcpyAsync(dst, c->stage_stats, sizeof(double) * c->slen,
                      loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
   if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+/* AdaGrad-like transition step of hmmsgd_metaobs.VBHMM(adagrad=True) (:1036-1040):
+ * ada_G += (var_tran-1)^2; var_tran <- (1 - ada_G^-1/4)(var_tran-1) + bfact_A*A*ada_G^-1/4 + 1 (lrate unused);
+ * on = 1 (re)initialises ada_G to ones (:183). */
+extern "C" int svihmm_set_adagrad(svihmm_ctx* c, int on, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  c->adagrad = on ? 1 : 0;
+  if (on) {
+    std::vector<double> ones((size_t)c->K * c->K, 1.0);
+    CU(cudaMemcpyAsync(c->ada_G, ones.data(), sizeof(double) * ones.size(), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+  }
   return SVIHMM_OK;
 }
 

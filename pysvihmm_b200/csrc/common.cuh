@@ -24,6 +24,7 @@ struct svihmm_ctx {
   double *W, *vinit, *emit, *prior_tran, *prior_init, *prior_emit;
   double *omega, *omega_prior, *lw;   // mixtures: Dirichlet weights (KE), their prior, E[ln pi] (KE)
   int have_mix;
+  double* ada_G; int adagrad;         // AdaGrad-like transition step (hmmsgd_metaobs.py:1036-1040)
   int user_init, have_globals, have_prior;
   // derived per-global-step constants
   float *Pt, *PtT, *pi0;          // exp(E[log A]) row-major, its transpose, exp(E[log pi])

@@ -17,6 +17,7 @@ enum { GM_PREP = 0, GM_SVI = 1, GM_BATCH = 2, GM_BSGD = 3 };   // BSGD: hmmbatch
 struct GlobalArgs {
   int K, D, DD, diag, cat, mode, user_init;
   int KE, C;                                // emission components K*C, components per state
+  double* ada_G;                            // non-NULL: AdaGrad-like transition step (hmmsgd_metaobs.py:1036-1040)
   double *omega, *omega_prior, *lw;         // mixtures only
   // one-shot all-reduce over NVLink peer memory (world > 1).  Exchange area of every rank:
   // [ flags: world x nb u64 | receive slots: 2 parities x world x slen doubles ]; xbase[p] = rank p's
@@ -169,7 +170,15 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   const GStats sv = gstats(a.stats, K, a.KE, a.D, a.DD);
   if (a.mode == GM_SVI || a.mode == GM_BSGD) {
 #pragma unroll 1
-    for (int i = tid; i < KK; i += nth) a.W[i] = (1.0 - a.lrate) * (a.W[i] - 1.0) + a.lrate * a.bA * sv.A[i] + 1.0;
+    for (int i = tid; i < KK; i += nth) {
+      const double no = a.W[i] - 1.0;
+      if (a.ada_G && a.mode == GM_SVI) {                       // :1036-1040: lrate is not used in this branch
+        const double G = a.ada_G[i] + no * no;
+        a.ada_G[i] = G;
+        const double m = sqrt(sqrt(G));
+        a.W[i] = (1.0 - 1.0 / m) * no + a.bA * sv.A[i] / m + 1.0;
+      } else a.W[i] = (1.0 - a.lrate) * no + a.lrate * a.bA * sv.A[i] + 1.0;
+    }
     if (a.mode == GM_BSGD) {
 #pragma unroll 1
       for (int i = tid; i < K; i += nth) a.vinit[K + i] = a.prior_init[i] + sv.q0[i];   // hmmbatchsgd.py:216

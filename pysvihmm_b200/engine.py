@@ -249,6 +249,10 @@ class EStepEngine(object):
         L.check(self.lib.svihmm_global_update(self._h, _ptr(stats), float(lrate), float(bfact_A),
                                               float(bfact_E), self._stream()))
 
+    def set_adagrad(self, on=True):
+        """AdaGrad-like transition step (hmmsgd_metaobs.py:1036-1040); on=True resets ada_G to ones."""
+        L.check(self.lib.svihmm_set_adagrad(self._h, int(bool(on)), self._stream()))
+
     def batch_update(self, stats):
         """hmmbatchcd.py:172-189 on the device-resident globals."""
         L.check(self.lib.svihmm_batch_update(self._h, _ptr(stats), self._stream()))

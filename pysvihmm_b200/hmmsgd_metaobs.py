@@ -75,9 +75,9 @@ class VBHMM(VariationalHMMBase):
         self.fullpred_sched = fullpred_sched if fullpred_sched is not None else np.arange(0, maxit, 10)
         self.metaobs_fun_name = metaobs_fun
         self.set_metaobs_fun()
-        if adagrad:
-            raise NotImplementedError("adagrad variant (hmmsgd_metaobs.py:1036-1040) is not on the engine yet")
         self.adagrad = adagrad
+        if adagrad:
+            self.ada_G = 1.0 * np.ones(self.prior_tran.shape)      # :183 (device copy lives in the engine)
         self.maxit = maxit
         self.growBuffer = growBuffer
         self.bufferBudget = bufferBudget
@@ -177,6 +177,8 @@ class VBHMM(VariationalHMMBase):
         if (Lh is None or adaptive) and growBuffer:
             raise RuntimeError("Cannot specify both adaptive and buffer simultaneously!")   # :344
         eng = self._ensure_engine()
+        if self.adagrad:
+            eng.set_adagrad(True)
         track_init = adaptive or Lh is None or growBuffer       # select_* read the previous var_init
         for it in range(maxit):
             start_time = time.time()
@@ -400,6 +402,30 @@ class VBHMM(VariationalHMMBase):
         else:
             eng.global_update(stats, self.lrate, bfact_A, bfact_E)
         self._host_stale = True
+
+    def pred_logprob(self, metaobs=None):
+        """hmmsgd_metaobs.py:1086-1119: mean over the masked rows of the meta-observation of
+        logsumexp_k( log(var_x[t,k] + eps) + E[log p(x_t | k)] ) with x_t the unmasked observation."""
+        metaobs = self.cur_mo if metaobs is None else metaobs
+        self.local_update(metaobs=metaobs)
+        m = np.asarray(self.mask[metaobs.i1:metaobs.i2 + 1], dtype=bool)
+        if m.sum() == 0:
+            return None
+        lp = np.log(self.var_x[m] + eps) + self.lliks[m]
+        return float(np.mean(np.logaddexp.reduce(lp, axis=1)))
+
+    def pred_logprob_full(self):
+        """hmmsgd_metaobs.py:1121-1145: the same over all masked rows of the series, with var_x from
+        full_local_update (masked rows carry no evidence there)."""
+        m = np.asarray(self.mask, dtype=bool)
+        if m.sum() == 0:
+            return None
+        q = self.full_local_update()
+        eng = self._ensure_engine()
+        eng.estep([0], self.T, flags=0, want_var_x=False, keep_locals=True)     # lliks of the unmasked observations
+        ll = eng.get_locals(1, self.T)["lliks"][0]
+        lp = np.log(q[m] + eps) + ll[m]
+        return float(np.mean(np.logaddexp.reduce(lp, axis=1)))
 
     def full_local_update(self):
         """hmmsgd_metaobs.py:1147-1205: posterior over the whole series with masked rows carrying

@@ -68,12 +68,12 @@ def pack_emit(prefix, objs, out):
     out[prefix + "_nu"] = np.array([g.nu_mf for g in objs], dtype=float)
 
 
-def svi_case(name, seed, K, D, T_full, L, mb_sz, sep, miss=0.0, maxit=2):
+def svi_case(name, seed, K, D, T_full, L, mb_sz, sep, miss=0.0, maxit=2, adagrad=False):
     obs, sts, mask, init, prior, init_tran = make_problem(seed, K, D, T_full, sep, miss)
     prior_emit = emit_objects(init, prior)
     hmm = HSGD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7,
                      metaobs_half=L, mb_sz=mb_sz, mask=mask, init_tran=init_tran.copy(),
-                     maxit=maxit, seed=seed)
+                     maxit=maxit, seed=seed, adagrad=adagrad)
     out = dict(obs=obs, sts=sts, mask=mask, init_tran=init_tran, prior_tran=np.ones((K, K)),
                prior_mu=prior['mu'], prior_sigma=prior['sigma'], prior_kappa=prior['kappa'],
                prior_nu=prior['nu'], L=L, mb_sz=mb_sz, tau=1., kappa_lr=0.7, maxit=maxit)
@@ -290,6 +290,7 @@ if __name__ == "__main__":
     svi_case("svi_k5_d3_l20_mask", seed=12, K=5, D=3, T_full=600, L=20, mb_sz=6, sep=0.5, miss=0.15)
     svi_case("svi_k16_d8_l50", seed=13, K=16, D=8, T_full=1500, L=50, mb_sz=3, sep=0.4, maxit=1)
     svi_case("svi_k2_d2_l1", seed=14, K=2, D=2, T_full=60, L=1, mb_sz=5, sep=0.8, maxit=3)
+    svi_case("svi_k3_d2_l5_adagrad", seed=15, K=3, D=2, T_full=300, L=5, mb_sz=4, sep=0.6, maxit=3, adagrad=True)
     cavi_case("cavi_k2_d2_t200", seed=21, T=200)
     bsgd_case("bsgd_k3_d2_t150", seed=22, T=150)
     ell_1d_case("ell_1d", seed=31)

@@ -329,3 +329,41 @@ def test_ffbs_samples_follow_the_reference_distribution():
         bandp = 5. * np.sqrt(np.maximum(pair[t] * (1 - pair[t]), 1e-4) / n) + 2e-3
         assert np.all(np.abs(pf - pair[t]) < bandp)
         assert not np.array_equal(zs[0], zs[1]) or K == 1                         # independent streams
+
+
+def test_vbhmm_adagrad_follows_reference_trajectory():
+    """hmmsgd_metaobs.VBHMM(adagrad=True).infer() against the reference's own run (:1036-1040)."""
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    g = load_golden("svi_k3_d2_l5_adagrad")
+    K = g["init_tran"].shape[0]
+    hmm = H.VBHMM(g["obs"].copy(), np.ones(K), np.ones((K, K)), _emit_objs(g, K), tau=1., kappa=0.7,
+                  metaobs_half=int(g["L"]), mb_sz=int(g["mb_sz"]), mask=g["mask"],
+                  init_tran=g["init_tran"].copy(), maxit=int(g["maxit"]), seed=15, adagrad=True)
+    hmm.infer()
+    assert _rel(hmm.var_tran, g["g_var_tran"][-1]) < 1e-4
+    assert _rel(np.array([e.mu_mf for e in hmm.var_emit]), g["g_mu"][-1]) < 1e-4
+    assert _rel(np.array([e.sigma_mf for e in hmm.var_emit]), g["g_sigma"][-1]) < 1e-4
+
+
+def test_pred_logprob_matches_oracle():
+    """pred_logprob / pred_logprob_full (hmmsgd_metaobs.py:1086-1145)."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import hmmsgd_metaobs as H
+    from tests.helpers import make_random_problem
+    K = 4
+    p = make_random_problem(seed=8, K=K, D=3, T_full=200, kind="niw_full", miss=0.2, sep=1.0)
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(K), np.ones((K, K)), _gauss_objs(p), metaobs_half=10, mb_sz=2,
+                  mask=p["mask"], init_tran=p["var_tran"].copy(), maxit=1, seed=1)
+    mo = H.MetaObs(50, 70)
+    got = hmm.pred_logprob(mo)
+    r = O.local_update(p["obs"][50:71][None], O.stationary_init(p["var_tran"]), p["var_tran"], p["emit"])
+    m = p["mask"][50:71]
+    ref = np.mean(np.logaddexp.reduce(np.log(r["var_x"][0][m] + 1e-9) + r["ll"][0][m], axis=1))
+    assert abs(got - ref) < 1e-5 * max(1., abs(ref))
+    xo = p["obs"].copy(); xo[p["mask"]] = np.nan
+    rf = O.local_update(xo[None], O.stationary_init(p["var_tran"]), p["var_tran"], p["emit"])
+    ll = O.lliks_gaussian(p["obs"][None], p["emit"])[0]
+    mm = p["mask"]
+    ref_full = np.mean(np.logaddexp.reduce(np.log(rf["var_x"][0][mm] + 1e-9) + ll[mm], axis=1))
+    got_full = hmm.pred_logprob_full()
+    assert abs(got_full - ref_full) < 1e-5 * max(1., abs(ref_full))

@@ -140,3 +140,21 @@ def test_categorical_ell_and_update_match_reference():
         new = O.cat_global_update(g["alpha"][k], np.ones_like(g["alpha"][k]), g["emit_inter"][k], 3,
                                   float(g["lrate"]), float(g["bfact"]))
         np.testing.assert_allclose(new, g["alpha_new"][k], rtol=RT, atol=AT)
+
+
+def test_adagrad_branch_matches_reference():
+    """hmmsgd_metaobs.py:1036-1040 (adagrad=True): transition step scaled by ada_G**0.25."""
+    g = load_golden("svi_k3_d2_l5_adagrad")
+    obs, mask = g["obs"], g["mask"]
+    L, S = int(g["L"]), int(g["mb_sz"])
+    K = g["init_tran"].shape[0]
+    var_tran = g["init_tran"].copy()
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    prior_emit = golden_prior_emit(g, K)
+    ada_G = np.ones((K, K))                                   # :183
+    for it in range(int(g["maxit"])):
+        r = O.svi_minibatch_step(obs, mask, g["w_starts"][it], 2 * L + 1, var_tran, emit, g["prior_tran"],
+                                 prior_emit, float(g["g_lrate"][it]), L, S, ada_G=ada_G)
+        np.testing.assert_allclose(r["var_tran_new"], g["g_var_tran"][it], rtol=RT, atol=AT)
+        np.testing.assert_allclose(np.array([e["mu"] for e in r["emit_new"]]), g["g_mu"][it], rtol=1e-9, atol=AT)
+        var_tran, emit = r["var_tran_new"], r["emit_new"]
