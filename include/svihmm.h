@@ -64,7 +64,11 @@ enum {
   SVIHMM_ADD_PRIOR   = 1u << 1, /* add (prior_tran-1) once per window (quirk Q5, :876,881)           */
   SVIHMM_MASK_LL     = 1u << 2, /* masked rows carry no evidence: ll[t,:]=0 (:1167-1168,1176)        */
   SVIHMM_EXACT_XI    = 1u << 3, /* A = sum_t true pairwise posterior instead of outer(q,q) (NOT ref) */
-  SVIHMM_KEEP_LOCALS = 1u << 4  /* keep lliks/alpha/cs tables for svihmm_get_locals (unfused kernels) */
+  SVIHMM_KEEP_LOCALS = 1u << 4, /* keep lliks/alpha/cs tables for svihmm_get_locals (unfused kernels) */
+  SVIHMM_BF16_DENSE  = 1u << 5  /* 64 < K <= 256 (K % 4 == 0): the K x K step of the recursions as a dense
+                                   (128 windows x K).(K x K) contraction on tcgen05 tensor cores, bf16
+                                   messages with float32 accumulators (BASELINE config 4); marginals then
+                                   agree with the float64 reference to ~1e-2 instead of 1e-5 (NOT ref) */
 };
 
 const char* svihmm_last_error(void);

@@ -10,7 +10,7 @@ OK, EINVAL, ECUDA, ENOMEM, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EMIT_NIW_FULL, EMIT_NIW_DIAG, EMIT_CATEGORICAL = 0, 1, 2
 F32, F64 = 0, 1
 LOC_DEVICE, LOC_HOST = 0, 1
-WRAP, ADD_PRIOR, MASK_LL, EXACT_XI, KEEP_LOCALS = 1, 2, 4, 8, 16
+WRAP, ADD_PRIOR, MASK_LL, EXACT_XI, KEEP_LOCALS, BF16_DENSE = 1, 2, 4, 8, 16, 32
 N_PHASES = 8
 
 _vp, _i, _i64, _d, _u = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint

@@ -15,6 +15,7 @@
 #include "fused_pipe.cuh"
 #include "wide64.cuh"
 #include "ffbs.cuh"
+#include "dense.cuh"
 
 static thread_local std::string g_err;
 
@@ -830,6 +831,27 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     }
     c->last_B = B; c->last_T = T; c->last_fused = 1;     // no lliks/alpha/cs tables in the classic form
     return stats_sym_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, st);
+  }
+  if ((flags & SVIHMM_BF16_DENSE) && K > 64 && K <= 256 && (K & 3) == 0 && !xi && !(flags & SVIHMM_KEEP_LOCALS)) {
+    // dense K x K step on tcgen05 (bf16 messages, float32 accumulators in tensor memory): dense.cuh
+    const int KPd = (K + 63) / 64 * 64;
+    const size_t smem = (size_t)DN_M * KPd * 2 + (size_t)KPd * KPd * 2 + 1024;
+    if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
+    CU(cudaFuncSetAttribute(k_chain_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { PhaseTimer pt(c, PH_FORWARD, st);
+      k_chain_dense<<<dim3((B + DN_M - 1) / DN_M, 2), DN_M, smem, st>>>(B, T, K, KPd, c->PtT, c->Pt, c->pi0, c->b_ws,
+                                                                     c->alpha_ws, c->r_ws, c->e_ws);
+      LAUNCHED(c); }
+    { PhaseTimer pt(c, PH_BACKWARD, st);
+      k_marginals_any<<<148 * 8, 256, 0, st>>>(R, K, c->alpha_ws, c->r_ws, c->e_ws, q, c->lt_ws);
+      LAUNCHED(c);
+      k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
+      LAUNCHED(c); }
+    PhaseTimer pt_stats(c, PH_STATS, st);
+    if ((rc = trim_for_stats())) return rc;
+    c->last_B = B; c->last_T = T; c->last_fused = 1;
+    if (mix) return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
+    return stats_generic_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, false, st);
   }
   if (K <= 32) {
     switch (c->KP) {

@@ -338,6 +338,37 @@ def test_gmm_emissions_match_oracle(K, C, D, T, B, kind):
     eng.close()
 
 
+@pytest.mark.parametrize("K,D,T,B", [(256, 8, 64, 130), (128, 4, 40, 7), (96, 4, 33, 129)])
+def test_bf16_dense_tensor_core_step(K, D, T, B):
+    """SVIHMM_BF16_DENSE (BASELINE config 4: the K x K step as a dense contraction on tcgen05 tensor
+    cores, bf16 messages, float32 accumulators).  The reference is float64 only, so the tolerance is
+    restated: |q - q_ref| <= 3e-2 absolute on the marginals (bf16 has 8 mantissa bits; errors do not
+    accumulate because the recursions forget), statistics 3e-2 relative to the largest entry, logZ 1e-2
+    relative.  The same inputs WITHOUT the flag meet the 1e-5 bound (test_estep_matches_oracle)."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    p = make_random_problem(seed=K + T, K=K, D=D, T_full=max(6 * T, 400), kind="niw_diag", miss=0.05, sep=1.5)
+    starts = np.random.RandomState(5).randint(0, p["obs"].shape[0] - T + 1, B)
+    eng = _engine(K, D, "niw_diag")
+    eng.set_series(p["obs"], p["mask"], dtype="f64")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR | L.BF16_DENSE)
+    nb = min(B, 8)                                        # oracle on a few windows of each CTA
+    pick = np.r_[0:nb // 2, B - nb // 2:B]
+    r = O.svi_minibatch_step(p["obs"], p["mask"], starts[pick], T, p["var_tran"], p["emit"], p["prior_tran"],
+                             p["prior_emit"], 0.5, max(T // 2, 1))
+    q = vx.cpu().numpy()[pick]
+    assert np.isfinite(q).all() and np.allclose(q.sum(-1), 1., atol=1e-4)
+    assert float(np.max(np.abs(q - r["var_x"]))) < 3e-2
+    vx32, stats32 = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)          # float32 recursions
+    s16, s32 = eng.unpack_stats(stats), eng.unpack_stats(stats32)
+    for key in ("A", "n", "sx", "sxx"):
+        assert_block(s16[key], s32[key], 3e-2, key)
+    assert abs(s16["logZ"] - s32["logZ"]) < 1e-2 * abs(s32["logZ"])
+    eng.close()
+
+
 def test_exact_xi_option_matches_oracle():
     """SVIHMM_EXACT_XI (not reference behaviour): sum_t of the true pairwise posteriors."""
     from oracle import svihmm_oracle as O
