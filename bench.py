@@ -29,6 +29,11 @@ CONFIGS = {
                workload="configs[1]: K=16 diag-Gaussian, D=8, T=512, 256 meta-obs minibatch per GPU"),
     "c3": dict(K=64, D=32, T=1024, B=512, kind="niw_full",
                workload="configs[2]: K=64 full-cov Gaussian, D=32, T=1024, 512 meta-obs per GPU"),
+    # configs[3]: the K x K step as a dense tensor-core contraction (tcgen05, bf16 messages); diagonal
+    # emissions so that the float64 emission phase does not drown the step being measured
+    "c4": dict(K=256, D=64, T=256, B=1024, kind="niw_diag", bf16_dense=True,
+               workload="configs[3]: K=256 dense tensor-core K x K step (bf16), D=64 diag-Gaussian, T=256, "
+                        "1024 meta-obs per GPU"),
 }
 T_FULL = 1 << 23          # rows of the synthetic series: 8.4M x D fp32 (268 MB at D=8) > 126 MB of L2
 
@@ -266,7 +271,7 @@ def run_ours(args, cfg):
     eng.set_prior(np.ones((K, K)), pack_emit_np(prior))
     em0 = pack_emit_np(emit)
     eng.set_globals(var_tran, em0)
-    flags = L.WRAP | L.ADD_PRIOR
+    flags = L.WRAP | L.ADD_PRIOR | (L.BF16_DENSE if cfg.get("bf16_dense") else 0)
     Lh, S = T // 2, B * world
     bA = (T_FULL - 2 * Lh - 1) / (2. * Lh * S)
     bE = (T_FULL - 2 * Lh - 1) / ((2. * Lh + 1.) * S)
@@ -393,7 +398,9 @@ def run_ours(args, cfg):
         line = {
             "metric": METRIC, "value": value, "unit": "E-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 recursions, f64 emission log-lik + statistics",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("bf16 messages / f32 accumulate (tcgen05) recursions, " if cfg.get("bf16_dense") else "f32 recursions, ")
+                     + "f64 emission log-lik + statistics",
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "K": K, "D": D, "T": T, "B_per_gpu": B,
                        "series": "%d x %d fp32 (%.0f MB) resident in HBM, larger than L2; fresh random "

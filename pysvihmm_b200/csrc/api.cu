@@ -771,11 +771,20 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     k_emit_full<<<(unsigned)((R + EMIT_ROWS - 1) / EMIT_ROWS), EMIT_ROWS, smem, st>>>(
         B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
   } else {
-    const size_t smem = 2 * (size_t)Ke * D * sizeof(double);
-    if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "K*D = %d too large for the diagonal emission kernel", Ke * D);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_emit_diag<<<(unsigned)((R * Ke + 255) / 256), 256, smem, st>>>(
-        B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
+    size_t smem = 2 * (size_t)Ke * D * sizeof(double);
+    if (smem <= 200 * 1024) {
+      if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_emit_diag<<<(unsigned)((R * Ke + 255) / 256), 256, smem, st>>>(
+          B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out, 1);
+    } else {
+      // parameters of all states do not fit: tiles of 32 states (config 4: K*D = 16384)
+      smem = 2 * (size_t)32 * D * sizeof(double);
+      if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the diagonal emission kernel", D);
+      if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned gx = (unsigned)std::min<int64_t>((R + 8 * ED_R - 1) / (8 * ED_R), 148 * 8);
+      k_emit_diag_tiled<<<dim3(gx, (Ke + 31) / 32), 256, smem, st>>>(
+          B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
+    }
   }
   LAUNCHED(c);
   if (!mix) {

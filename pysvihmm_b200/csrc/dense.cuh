@@ -131,6 +131,17 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     sum = 0.f;
+    // b of this step was pulled into L2 two steps ago; pull the row of step s+2 now (8 x 128 B per thread)
+    if (live && s + 2 < T) {
+      const char* pf = reinterpret_cast<const char*>(bw + (size_t)(t + 2 * dt) * K);
+      for (int o = 0; o < K * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+    }
+    float4 bq[8];                                      // b of the chunk being processed, fetched one chunk ahead
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      const int k = q4 * 4;
+      bq[q4] = (live && k < K) ? *reinterpret_cast<const float4*>(bw + (size_t)t * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int c32 = 0; c32 < KP / 32; ++c32) {
       uint32_t a[32];
       const uint32_t ta = tm + ((uint32_t)(wp * 32) << 16) + c32 * 32;
@@ -140,11 +151,16 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
                      "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]),
                      "=r"(a[30]), "=r"(a[31]) : "r"(ta) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float4 bn[8];                                    // next chunk's b: in flight while this chunk is processed
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {                 // 4 columns at a time: one LDG.128 of b, one STG.128
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const int k = (c32 + 1) * 32 + q4 * 4;
+        bn[q4] = (live && k < K) ? *reinterpret_cast<const float4*>(bw + (size_t)t * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {                 // 4 columns at a time: one STG.128
         const int k = c32 * 32 + q4 * 4;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && k < K) bb = *reinterpret_cast<const float4*>(bw + (size_t)t * K + k);
+        const float4 bb = bq[q4];
         const float m0 = __uint_as_float(a[q4 * 4]) * r, m1 = __uint_as_float(a[q4 * 4 + 1]) * r;
         const float m2 = __uint_as_float(a[q4 * 4 + 2]) * r, m3 = __uint_as_float(a[q4 * 4 + 3]) * r;
         const float v0 = m0 * bb.x, v1 = m1 * bb.y, v2 = m2 * bb.z, v3 = m3 * bb.w;
@@ -153,6 +169,8 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
         a[q4 * 4] = __float_as_uint(v0); a[q4 * 4 + 1] = __float_as_uint(v1);
         a[q4 * 4 + 2] = __float_as_uint(v2); a[q4 * 4 + 3] = __float_as_uint(v3);
       }
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) bq[q4] = bn[q4];
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8)                   // the carried vector, rounded to bf16, back into the A operand
         *reinterpret_cast<uint4*>(sA + dn_chunk(tid, c32 * 4 + c8, DN_M)) =

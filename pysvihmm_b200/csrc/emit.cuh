@@ -66,11 +66,14 @@ __global__ void __launch_bounds__(256)
 k_emit_diag(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
             const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
             const double* __restrict__ Rs, const double* __restrict__ gk,
-            const double* __restrict__ ck, double* __restrict__ ll) {
+            const double* __restrict__ ck, double* __restrict__ ll, int p_smem) {
   extern __shared__ double sm[];
-  double* rr_ = sm; double* mm_ = sm + (size_t)K * D;
-  for (int idx = threadIdx.x; idx < K * D; idx += blockDim.x) { rr_[idx] = Rs[idx]; mm_[idx] = gk[idx]; }
-  __syncthreads();
+  // parameters in shared memory when 2*K*D doubles fit, else read through L1/L2 (K*D = 16384 at config 4)
+  const double* rr_ = p_smem ? sm : Rs; const double* mm_ = p_smem ? sm + (size_t)K * D : gk;
+  if (p_smem) {
+    for (int idx = threadIdx.x; idx < K * D; idx += blockDim.x) { sm[idx] = Rs[idx]; sm[(size_t)K * D + idx] = gk[idx]; }
+    __syncthreads();
+  }
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t R = (int64_t)B * T;
   if (e >= R * K) return;
@@ -86,6 +89,56 @@ k_emit_diag(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
     acc = fma(rr_[k * D + d] * df, df, acc);
   }
   ll[e] = dead ? 0.0 : ck[k] - acc;
+}
+
+// Diagonal emissions for large K*D (parameters do not fit in shared memory at once): the CTA owns a
+// tile of 32 states (their parameters in shared memory: 2*32*D doubles) and a block of rows; a warp =
+// the 32 states of ONE row, so the observation loads are warp-uniform broadcasts, and every thread
+// keeps ED_R rows in flight so that each parameter load feeds ED_R*2 DFMA.
+#define ED_R 4
+__global__ void __launch_bounds__(256)
+k_emit_diag_tiled(int B, int T, int K, int D, const void* __restrict__ obs, int dtype,
+                  const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+                  const double* __restrict__ Rs, const double* __restrict__ gk,
+                  const double* __restrict__ ck, double* __restrict__ ll) {
+  extern __shared__ double sm[];                  // [D][32] rs, [D][32] mu
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int k0 = blockIdx.y * 32, k = k0 + lane;
+  for (int idx = threadIdx.x; idx < 32 * D; idx += blockDim.x) {
+    const int d = idx >> 5, kk = idx & 31;
+    sm[idx] = k0 + kk < K ? Rs[(size_t)(k0 + kk) * D + d] : 0.0;
+    sm[32 * D + idx] = k0 + kk < K ? gk[(size_t)(k0 + kk) * D + d] : 0.0;
+  }
+  __syncthreads();
+  const int64_t R = (int64_t)B * T;
+  const double c = k < K ? ck[k] : 0.0;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + wp) * ED_R; r0 < R; r0 += (int64_t)gridDim.x * 8 * ED_R) {
+    int64_t gi[ED_R]; bool dead[ED_R]; double acc[ED_R];
+#pragma unroll
+    for (int u = 0; u < ED_R; ++u) {
+      const int64_t r = r0 + u;
+      gi[u] = 0; dead[u] = r >= R; acc[u] = 0.0;
+      if (r < R) {
+        const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+        gi[u] = starts[b] + t;
+        dead[u] = mask_ll && mask && mask[gi[u]];
+      }
+    }
+    for (int d = 0; d < D; ++d) {
+      const double rs = sm[d * 32 + lane], mu = sm[32 * D + d * 32 + lane];
+#pragma unroll
+      for (int u = 0; u < ED_R; ++u) {
+        const double x = ld_obs(obs, dtype, gi[u] * D + d);       // same address on every lane: broadcast
+        if (isnan(x)) dead[u] = true;
+        const double df = x - mu;
+        acc[u] = fma(rs * df, df, acc[u]);
+      }
+    }
+    if (k < K) {
+#pragma unroll
+      for (int u = 0; u < ED_R; ++u) if (r0 + u < R) ll[(r0 + u) * K + k] = dead[u] ? 0.0 : c - acc[u];
+    }
+  }
 }
 
 // Categorical emissions (pybasicbayes/distributions.py:1383-1386): ll[r][k] = logp[k][x_r] with the
