@@ -43,6 +43,22 @@ for K, D, kind, T in [(16, 8, "niw_diag", 64), (5, 3, "niw_full", 40), (40, 4, "
     dist.all_gather(gs, g)
     ok &= all(bool(torch.equal(gs[0], x)) for x in gs)
     print("rank %d K=%d %s: %s" % (rank, K, kind, "OK" if ok else "MISMATCH"), flush=True)
+# the driver: hmmsgd_metaobs.VBHMM.infer with the sum over ranks inside the global-step kernel vs NCCL
+from pysvihmm_b200 import hmmsgd_metaobs as H
+from pysvihmm_b200.distributions import Gaussian
+p = make_random_problem(seed=3, K=4, D=2, T_full=600, kind="niw_full", miss=0.1)
+res = []
+for peer in (True, False):
+    objs = np.array([Gaussian(mu=e["mu"].copy(), sigma=e["sigma"].copy(), mu_0=pe["mu"], sigma_0=pe["sigma"],
+                              kappa_0=pe["kappa"], nu_0=pe["nu"], kappa_mf=e["kappa"], nu_mf=e["nu"])
+                     for e, pe in zip(p["emit"], p["prior_emit"])])
+    hmm = H.VBHMM(p["obs"].copy(), np.ones(4), np.ones((4, 4)), objs, metaobs_half=8, mb_sz=3 * world, mask=p["mask"],
+                  init_tran=p["var_tran"].copy(), maxit=4, seed=9, device=local, peer_allreduce=peer)
+    hmm.infer()
+    res.append((hmm.var_tran.copy(), np.array([g.mu_mf for g in hmm.var_emit]), hmm.elbo_vec.copy()))
+okd = all(np.allclose(a, b, rtol=1e-9, atol=1e-10) for a, b in zip(res[0], res[1]))
+print("rank %d VBHMM.infer peer vs nccl: %s" % (rank, "OK" if okd else "MISMATCH"), flush=True)
+ok &= okd
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
