@@ -116,7 +116,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   CU(dalloc(&c->omega, KE)); CU(dalloc(&c->omega_prior, KE)); CU(dalloc(&c->lw, KE));
   CU(dalloc(&c->ada_G, KK));
   CU(dalloc(&c->Pt, KK)); CU(dalloc(&c->PtT, KK)); CU(dalloc(&c->pi0, (size_t)K));
-  CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1))); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * KE * D));
+  CU(dalloc(&c->lu, 2 * (size_t)K * (K + 1) + 8 * (size_t)K + 16)); CU(dalloc(&c->rowsum, (size_t)K)); CU(dalloc(&c->ckc, 2 * KE * D));
   CU(dalloc(&c->par2, 2 * KE * D)); CU(dalloc(&c->ckp, KE));
   CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, KE * D)); CU(dalloc(&c->ck, KE));
   CU(dalloc(&c->stage_stats, c->slen));
@@ -264,7 +264,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.user_init = c->user_init; ga.plen = c->plen;
   ga.KE = c->KE; ga.C = c->C; ga.omega = c->omega; ga.omega_prior = c->omega_prior; ga.lw = c->lw;
   ga.ada_G = c->adagrad ? c->ada_G : nullptr;
-  ga.world = 1; ga.rank = 0; ga.nb = 0; ga.seq = 0; ga.red_out = nullptr; ga.slen = c->slen;
+  ga.world = 1; ga.rank = 0; ga.nb = 0; ga.seq = 0; ga.red_out = nullptr; ga.stats_local = nullptr; ga.slen = c->slen;
   ga.W = c->W; ga.vinit = c->vinit; ga.emit = c->emit;
   ga.prior_tran = c->prior_tran; ga.prior_init = c->prior_init; ga.prior_emit = c->prior_emit;
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
@@ -281,6 +281,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   if (peers) {
     ga.world = c->comm_world; ga.rank = c->comm_rank; ga.seq = ++c->comm_seq; ga.red_out = c->stage_stats;
     ga.nb = comm_blocks(c);
+    ga.stats_local = stats; ga.stats = c->stage_stats;          // the update reads the sums from red_out
     for (int p = 0; p < c->comm_world; ++p) ga.xbase[p] = (unsigned long long*)c->comm_peer[p];
   }
   static const bool gdbg = getenv("SVIHMM_GLOBAL_DBG") != nullptr;
@@ -288,6 +289,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   if (gdbg) CU(cudaMalloc((void**)&ga.dbg, 128));
   {
     PhaseTimer pt(c, PH_UPDATE, st);
+    // K*K digamma threads + one warp for the stationary vector
     // K*K digamma threads + one warp for the stationary vector
     const int nthr = std::min(512, ((K * K + 31) / 32) * 32 + 32);
     k_global_step<<<1 + nblk + (c->C > 1 ? 1 : 0), std::max(nthr, 128), smem, st>>>(ga, nblk);

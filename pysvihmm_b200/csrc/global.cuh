@@ -27,6 +27,7 @@ struct GlobalArgs {
   unsigned long long* xbase[8];
   unsigned long long seq;
   double* red_out;
+  const double* stats_local;                // this rank's own statistics (stats = red_out when world > 1)
   size_t slen;
   size_t plen;
   double *W, *vinit, *emit;                 // vinit: [0,K) the vector in use, [K,2K) the user-given one
@@ -96,7 +97,7 @@ __device__ void comm_exchange(const GlobalArgs& a, const CommRange* rg, const in
   // push this block's ranges into slot `me` of every peer
   for (int r = 0; r < nrg; ++r)
     for (size_t i = rg[r].lo + tid; i < rg[r].hi; i += nth) {
-      const double v = a.stats[i];
+      const double v = a.stats_local[i];
       for (int p = 0; p < W; ++p)
         if (p != me) st_peer(reinterpret_cast<double*>(a.xbase[p] + nflag) + par + (size_t)me * a.slen + i, v);
     }
@@ -111,7 +112,7 @@ __device__ void comm_exchange(const GlobalArgs& a, const CommRange* rg, const in
   for (int r = 0; r < nrg; ++r)
     for (size_t i = rg[r].lo + tid; i < rg[r].hi; i += nth) {
       double s = 0.0;
-      for (int p = 0; p < W; ++p) s += p == me ? a.stats[i] : __ldcv(rcv + (size_t)p * a.slen + i);
+      for (int p = 0; p < W; ++p) s += p == me ? a.stats_local[i] : __ldcv(rcv + (size_t)p * a.slen + i);
       a.red_out[i] = s;
     }
 }
@@ -162,9 +163,52 @@ __device__ void gth_warp(const int K, const double* __restrict__ W, const double
   if (lane < K) pi_out[lane] = pv;
 }
 
+// Normalisation of the stationary vector and pi0 = exp(psi(v) - psi(sum v)) (hmmsgd_metaobs.py:418,502),
+// one warp.  (Tried: a spare warp executing this code on scratch data beforehand to warm the
+// instruction cache -- no change in the clock64 stamps, so the serial tail is not fetch-bound.)
+__device__ __noinline__ void pi0_section(const int user_init, const int K, const double* pi, double* vinit,
+                                         float* pi0, const int lane, long long* dbg) {
+#define PSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  if (!user_init) {
+    double n2 = 0.0;
+#pragma unroll 1
+    for (int j = lane; j < K; j += 32) n2 += pi[j] * pi[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    n2 = sqrt(n2);
+    PSTAMP(6);
+#pragma unroll 1
+    for (int j = lane; j < K; j += 32) vinit[j] = fabs(pi[j]) / n2;
+  } else {
+#pragma unroll 1
+    for (int j = lane; j < K; j += 32) vinit[j] = vinit[K + j];
+  }
+  __syncwarp();
+  PSTAMP(7);
+  double n1 = 0.0;
+#pragma unroll 1
+  for (int j = lane; j < K; j += 32) n1 += vinit[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+  PSTAMP(8);
+  if (K < 32) {                                        // one call: lanes < K their own entry, lane 31 the sum
+    const double arg = lane < K ? vinit[lane] : n1;
+    const double dg = digamma_fast(arg + SVIHMM_EPS);
+    const double dgs = __shfl_sync(0xffffffffu, dg, 31);
+    if (lane < K) pi0[lane] = (float)dexp_ni(dg - dgs);
+  } else {
+    const double dgs = digamma_fast(n1 + SVIHMM_EPS);
+#pragma unroll 1
+    for (int j = lane; j < K; j += 32) pi0[j] = (float)dexp_ni(digamma_fast(vinit[j] + SVIHMM_EPS) - dgs);
+  }
+  PSTAMP(9);
+#undef PSTAMP
+}
+
 __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   const int K = a.K, tid = threadIdx.x, nth = blockDim.x;
 #define GSTAMP(i) do { if (a.dbg && tid == 0) a.dbg[i] = clock64(); } while (0)
+#define GSYNC() __syncthreads()
   GSTAMP(0);
   const int KK = K * K;
   const GStats sv = gstats(a.stats, K, a.KE, a.D, a.DD);
@@ -189,7 +233,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
 #pragma unroll 1
     for (int i = tid; i < K; i += nth) a.vinit[K + i] = a.prior_init[i] + sv.q0[i];
   }
-  __syncthreads();
+  GSYNC();
   // row sums: one warp per row
   const int lane = tid & 31, wp = tid >> 5, nw = nth >> 5;
 #pragma unroll 1
@@ -201,7 +245,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) a.rowsum[i] = s;
   }
-  __syncthreads();
+  GSYNC();
   GSTAMP(1);
   double* pi = sm;                                        // K + 1 doubles
   double* G = a.gth;                                      // K*K doubles of scratch (K > 32 only)
@@ -226,7 +270,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
       if (!inwarp) G[idx] = w / a.rowsum[i];
     }
   }
-  __syncthreads();
+  GSYNC();
   GSTAMP(2);
   if (!a.user_init && !inwarp) {
     // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
@@ -242,13 +286,13 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) G[i * K + n] *= rinv;
       }
-      __syncthreads();
+      GSYNC();
 #pragma unroll 1
       for (int idx = tid; idx < n * n; idx += nth) {
         const int i = idx / n, j = idx - i * n;
         G[i * K + j] = fma(G[i * K + n], G[n * K + j], G[i * K + j]);
       }
-      __syncthreads();
+      GSYNC();
     }
     // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]: column j accumulates as the pi[i] become final
     if (wp == 0) {
@@ -264,41 +308,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
       }
     }
   }
-  if (wp == 0) {
-    if (!a.user_init) {
-      double n2 = 0.0;
-#pragma unroll 1
-      for (int j = lane; j < K; j += 32) n2 += pi[j] * pi[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-      n2 = sqrt(n2);
-      GSTAMP(6);
-#pragma unroll 1
-      for (int j = lane; j < K; j += 32) a.vinit[j] = fabs(pi[j]) / n2;
-    } else {
-#pragma unroll 1
-      for (int j = lane; j < K; j += 32) a.vinit[j] = a.vinit[K + j];
-    }
-    __syncwarp();
-    GSTAMP(7);
-    double n1 = 0.0;
-#pragma unroll 1
-    for (int j = lane; j < K; j += 32) n1 += a.vinit[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n1 += __shfl_xor_sync(0xffffffffu, n1, o);
-    GSTAMP(8);
-    if (K < 32) {                                        // one call: lanes < K their own entry, lane 31 the sum
-      const double arg = lane < K ? a.vinit[lane] : n1;
-      const double dg = digamma_fast(arg + SVIHMM_EPS);
-      const double dgs = __shfl_sync(0xffffffffu, dg, 31);
-      if (lane < K) a.pi0[lane] = (float)dexp_ni(dg - dgs);
-    } else {
-      const double dgs = digamma_fast(n1 + SVIHMM_EPS);
-#pragma unroll 1
-      for (int j = lane; j < K; j += 32) a.pi0[j] = (float)dexp_ni(digamma_fast(a.vinit[j] + SVIHMM_EPS) - dgs);
-    }
-    GSTAMP(9);
-  }
+  if (wp == 0) pi0_section(a.user_init, K, pi, a.vinit, a.pi0, lane, a.dbg && tid == 0 ? a.dbg : nullptr);
   GSTAMP(3);
 }
 
@@ -529,9 +539,8 @@ __device__ void global_mix_block(const GlobalArgs& a) {
 }
 
 // grid: 1 + (diag ? nblk_diag : K) blocks.
-__global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a_in, const int nblk_emit) {
+__global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a, const int nblk_emit) {
   extern __shared__ double gsm[];
-  GlobalArgs a = a_in;
   if (a.world > 1 && a.mode != GM_PREP) {
     const size_t KK = (size_t)a.K * a.K, o_n = KK, o_sx = o_n + a.KE, o_sxx = o_sx + (size_t)a.KE * a.D,
                  o_q0 = o_sxx + (size_t)a.KE * a.DD;
@@ -552,7 +561,6 @@ __global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a_in, cons
     comm_exchange(a, rg, nrg);
     __threadfence();
     __syncthreads();
-    a.stats = a.red_out;                                         // the update reads the sums
   }
   if (blockIdx.x == 0) global_tran_block(a, gsm);
   else if ((int)blockIdx.x == 1 + nblk_emit) global_mix_block(a);
