@@ -169,12 +169,15 @@ __device__ void gth_warp(const int K, const double* __restrict__ W, const double
 __device__ __noinline__ void pi0_section(const int user_init, const int K, const double* pi, double* vinit,
                                          float* pi0, const int lane, long long* dbg) {
 #define PSTAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+  PSTAMP(11);
   if (!user_init) {
     double n2 = 0.0;
 #pragma unroll 1
     for (int j = lane; j < K; j += 32) n2 += pi[j] * pi[j];
+    PSTAMP(12);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    PSTAMP(13);
     n2 = sqrt(n2);
     PSTAMP(6);
 #pragma unroll 1
