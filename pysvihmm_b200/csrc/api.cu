@@ -299,7 +299,8 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
     long long h[16];
     CU(cudaStreamSynchronize(st));
     CU(cudaMemcpy(h, ga.dbg, 128, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[global dbg] into pi0_section=%lld n2 loop=%lld shuffles=%lld sqrt=%lld\n", h[11] - h[2], h[12] - h[11], h[13] - h[12], h[6] - h[13]);
+    fprintf(stderr, "[global dbg] stationary warp done %lld cycles after the row sums; into pi0_section=%lld n2 loop=%lld shuffles=%lld sqrt=%lld\n",
+            h[14] - h[1], h[11] - h[2], h[12] - h[11], h[13] - h[12], h[6] - h[13]);
     fprintf(stderr, "[global dbg] squarings=%lld pi0 section: norm2=%lld store=%lld n1=%lld dgs=%lld rest=%lld\n", h[10], h[6] - h[2], h[7] - h[6], h[8] - h[7], h[9] - h[8], h[3] - h[9]);
     CU(cudaFree(ga.dbg));
     fprintf(stderr, "[global dbg] mode=%d cycles: update+rowsum=%lld P||stationary=%lld gth=%lld pi0=%lld | emission block=%lld\n", mode,

@@ -261,6 +261,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
     else if (K <= 8) gth_warp<8>(K, a.W, a.rowsum, pi, lane);
     else if (K <= 16) gth_warp<16>(K, a.W, a.rowsum, pi, lane);
     else gth_warp<32>(K, a.W, a.rowsum, pi, lane);
+    if (a.dbg && lane == 0) a.dbg[14] = clock64();
   } else {
     const int nt = inwarp ? nth - 32 : nth;
 #pragma unroll 1
