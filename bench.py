@@ -31,6 +31,10 @@ CONFIGS = {
                workload="configs[2]: K=64 full-cov Gaussian, D=32, T=1024, 512 meta-obs per GPU"),
     # configs[3]: the K x K step as a dense tensor-core contraction (tcgen05, bf16 messages); diagonal
     # emissions so that the float64 emission phase does not drown the step being measured
+    # configs[4]: 4-component NIW mixtures per state (extension; per-phase kernels with K*C = 128 components)
+    "c5": dict(K=32, D=16, T=2048, B=128, kind="niw_full", components=4,
+               workload="configs[4]: K=32 states x 4-component full-cov GMM emissions, D=16, T=2048, "
+                        "128 meta-obs per GPU"),
     "c4": dict(K=256, D=64, T=256, B=1024, kind="niw_diag", bf16_dense=True,
                workload="configs[3]: K=256 dense tensor-core K x K step (bf16), D=64 diag-Gaussian, T=256, "
                         "1024 meta-obs per GPU"),
@@ -265,11 +269,18 @@ def run_ours(args, cfg):
         dist.init_process_group("nccl", device_id=dev)
     K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], cfg["B"], cfg["kind"]
     obs_host, mus = synthetic_series(K, D, T_FULL, seed=8675309)       # same series on every rank
+    C_mix = int(cfg.get("components", 1))
     var_tran, emit, prior = globals_for(K, D, kind, mus, seed=8675309)
-    eng = EStepEngine(K, D, kind, device=local)
+    if C_mix > 1:                       # component c of state k: the state's parameters with a jittered mean
+        rsm = np.random.RandomState(7)
+        emit = [dict(e, mu=e["mu"] + 0.7 * rsm.randn(D)) for e in emit for _ in range(C_mix)]
+        prior = [p_ for p_ in prior for _ in range(C_mix)]
+    eng = EStepEngine(K, D, kind, device=local, components=C_mix)
     eng.set_series(torch.from_numpy(obs_host).to(dev))
     eng.set_prior(np.ones((K, K)), pack_emit_np(prior))
     em0 = pack_emit_np(emit)
+    if C_mix > 1:
+        eng.set_mix_weights(2. * np.ones((K, C_mix)), np.ones((K, C_mix)))
     eng.set_globals(var_tran, em0)
     flags = L.WRAP | L.ADD_PRIOR | (L.BF16_DENSE if cfg.get("bf16_dense") else 0)
     Lh, S = T // 2, B * world
@@ -336,6 +347,8 @@ def run_ours(args, cfg):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the host-buffer call --------------------------------
+    if C_mix > 1:
+        eng.set_mix_weights(2. * np.ones((K, C_mix)), np.ones((K, C_mix)))
     eng.set_globals(var_tran, em0)
     eng.set_series_streamed(obs_host)
     stats_h = np.empty(eng.slen)
@@ -422,7 +435,7 @@ def run_ours(args, cfg):
                             if world == 1 else "svihmm_estep_streamed + NCCL all-reduce + svihmm_global_update + D2H"},
             "gpu_launches": int(launches), "clocks": clk,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and C_mix == 1:     # the reference has no mixture-emission E-step
             cb, _, _ = cpu_estep_rate(cfg, 12.0, 400)
             line["cpu_baseline"] = cb
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -825,7 +825,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     qs = c->qin_ws; starts_s = c->starts_in; Ts = T - 2 * trim;
     return SVIHMM_OK;
   };
-  if (K > 32 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64 && c->kind != SVIHMM_EMIT_CATEGORICAL) {
+  if (K > 16 && K <= 64 && !xi && !(flags & SVIHMM_KEEP_LOCALS) && D <= 64 && c->kind != SVIHMM_EMIT_CATEGORICAL) {
     // warp-per-chain recursions, marginals, symmetric register-blocked statistics (wide64.cuh)
     if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
     { PhaseTimer pt(c, PH_FORWARD, st);
