@@ -299,7 +299,15 @@ def run_ours(args, cfg):
     px = None
     if world > 1 and not args.nccl:
         from pysvihmm_b200.sharding import PeerExchange
-        px = PeerExchange(eng, dist)
+        try:
+            px = PeerExchange(eng, dist)
+            okflag = torch.ones(1, device=dev)
+        except Exception as e:          # noqa: BLE001  (no peer access / symmetric memory on this box)
+            sys.stderr.write("rank %d: peer exchange unavailable (%r), using the NCCL all-reduce\n" % (rank, e))
+            px, okflag = None, torch.zeros(1, device=dev)
+        dist.all_reduce(okflag, op=dist.ReduceOp.MIN)          # all ranks must agree on the path
+        if okflag.item() < 1:
+            px = None
 
     def step(i, it):
         eng.estep(starts_dev[i], T, flags=flags, var_x=var_x, stats=stats)

@@ -155,7 +155,8 @@ class VBHMM(VariationalHMMBase):
         if dist is not None and self.peer_allreduce and dist.get_backend() == "nccl":
             if self._px is None:            # the sum over ranks happens inside global_update (P2P over NVLink)
                 from .sharding import PeerExchange
-                self._px = PeerExchange(eng, dist)
+                self._px = PeerExchange(eng, dist)   # raises if the ranks cannot address each other's memory;
+                                                     # construct with peer_allreduce=False for the NCCL all-reduce
         else:
             allreduce_stats(stats, dist)    # one sum all-reduce of the packed statistics per step
         self._var_x_batch = vx
