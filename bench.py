@@ -428,7 +428,7 @@ def run_ours(args, cfg):
                                  "windows every step (no L2 flush needed)" % (T_FULL, D, T_FULL * D * 4 / 1e6),
                        "step": "E-step (B windows) + %sglobal natural-gradient update" % (
                            ("" if world == 1 else "NCCL all-reduce of packed statistics + " if px is None else
-                            "sum over ranks by P2P loads over NVLink inside the ")),
+                            "sum over ranks by P2P pushes over NVLink inside the ")),
                        "var_x_written": True},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom[0]) if args.config == "c2" else None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
