@@ -126,21 +126,33 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // elimination inside ONE warp: lane i keeps row i in registers, the pivot row travels by shuffles.
 // No subtractions, so the result is componentwise accurate (~1e-15); ~4k cycles at K = 16
 // (measured alternatives: block-wide elimination through memory ~22k, repeated squaring ~22k).
+// 1/s to full double precision without the ~120-cycle division routine: rcp.approx + Newton steps
+__device__ __forceinline__ double gth_rcp(const double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) { const double e = fma(-s, r, 1.0); r = fma(r, e, r); }
+  return r;
+}
+
 template <int KP>
 __device__ void gth_warp(const int K, const double* __restrict__ W, const double* __restrict__ rowsum,
                          double* __restrict__ pi_out, const int lane) {
+  __shared__ double Gs[KP][KP + 1];                     // eliminated matrix for the back-substitution
   double row[KP];
-  const double rs = lane < K ? 1.0 / rowsum[lane] : 0.0;
+  const double rs = lane < K ? gth_rcp(rowsum[lane]) : 0.0;
 #pragma unroll
   for (int j = 0; j < KP; ++j) row[j] = (lane < K && j < K) ? W[lane * K + j] * rs : 0.0;
 #pragma unroll
   for (int n = KP - 1; n >= 1; --n) {
     if (n < K) {                                       // warp-uniform
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four partial sums: the dependent chain is n/4 adds
 #pragma unroll
-      for (int j = 0; j < n; ++j) s += row[j];
-      s = __shfl_sync(0xffffffffu, s, n);
-      const double f = row[n] * (1.0 / s);
+      for (int j = 0; j < n; ++j) {
+        if ((j & 3) == 0) s0 += row[j]; else if ((j & 3) == 1) s1 += row[j]; else if ((j & 3) == 2) s2 += row[j]; else s3 += row[j];
+      }
+      const double s = __shfl_sync(0xffffffffu, (s0 + s1) + (s2 + s3), n);
+      const double f = row[n] * gth_rcp(s);
 #pragma unroll
       for (int j = 0; j < n; ++j) {
         const double g = __shfl_sync(0xffffffffu, row[j], n);
@@ -149,15 +161,19 @@ __device__ void gth_warp(const int K, const double* __restrict__ W, const double
       if (lane < n) row[n] = f;
     }
   }
-  // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]
+  // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j].  G[i][j] (i < j) sits in register row[j] of lane i: transpose
+  // through shared memory so that lane j owns column j, then one broadcast + one FMA per i (no reductions)
+  if (lane < KP) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) Gs[lane][j] = row[j];
+  }
+  __syncwarp();
   double pv = lane == 0 ? 1.0 : 0.0;
 #pragma unroll
-  for (int j = 1; j < KP; ++j) {
-    if (j < K) {
-      double t = lane < j ? pv * row[j] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == j) pv = t;
+  for (int i = 0; i < KP - 1; ++i) {
+    if (i + 1 < K) {
+      const double pi_i = __shfl_sync(0xffffffffu, pv, i);
+      if (lane > i && lane < K) pv = fma(pi_i, Gs[i][lane], pv);
     }
   }
   if (lane < K) pi_out[lane] = pv;
