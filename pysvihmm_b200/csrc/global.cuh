@@ -46,14 +46,23 @@ struct GlobalArgs {
 __device__ __noinline__ double dlog_ni(double x) { return log(x); }
 __device__ __noinline__ double dexp_ni(double x) { return exp(x); }
 
+// 1/s to full double precision without the ~120-cycle division routine: rcp.approx + Newton steps
+__device__ __forceinline__ double gth_rcp(const double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) { const double e = fma(-s, r, 1.0); r = fma(r, e, r); }
+  return r;
+}
+
 // psi(x), float64: recurrence up to x >= 10, then the asymptotic series through B14 (truncation
 // error < 5e-17 there).  x > 0 only.
 __device__ __noinline__ double digamma_fast(double x) {
   double r = 0.0;
   if (!(x > 0.0)) return nan("");                   // Dirichlet / NIW parameters are positive
 #pragma unroll 1
-  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
-  const double xi = 1.0 / x, x2 = xi * xi;
+  while (x < 10.0) { r -= gth_rcp(x); x += 1.0; }       // up to 10 reciprocals on the serial tail of the kernel
+  const double xi = gth_rcp(x), x2 = xi * xi;
   r += dlog_ni(x) - 0.5 * xi
      - x2 * (1.0 / 12 - x2 * (1.0 / 120 - x2 * (1.0 / 252 - x2 * (1.0 / 240
      - x2 * (1.0 / 132 - x2 * (691.0 / 32760 - x2 * (1.0 / 12)))))));
@@ -126,15 +135,6 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // elimination inside ONE warp: lane i keeps row i in registers, the pivot row travels by shuffles.
 // No subtractions, so the result is componentwise accurate (~1e-15); ~4k cycles at K = 16
 // (measured alternatives: block-wide elimination through memory ~22k, repeated squaring ~22k).
-// 1/s to full double precision without the ~120-cycle division routine: rcp.approx + Newton steps
-__device__ __forceinline__ double gth_rcp(const double s) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
-#pragma unroll
-  for (int it = 0; it < 3; ++it) { const double e = fma(-s, r, 1.0); r = fma(r, e, r); }
-  return r;
-}
-
 template <int KP>
 __device__ void gth_warp(const int K, const double* __restrict__ W, const double* __restrict__ rowsum,
                          double* __restrict__ pi_out, const int lane) {
