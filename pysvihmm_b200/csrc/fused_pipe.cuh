@@ -26,7 +26,7 @@
 
 #define FP_NT 256
 #define FP_NW 224            // worker threads when one warp runs both chains (K <= 16); 192 for 16 < K <= 32
-#define FP_TB 64             // chain steps per hand-off tile
+#define FP_TB 48             // chain steps per hand-off tile (96 rows = two rounds of 8-row MMA groups over 6 warps; measured 64: 59.9, 48: 58.4, 32: 60.4 us)
 #define FP_LA 8              // b-table lookahead of the chain (steps)
 #define FP_MAXBAR 48
 
