@@ -89,3 +89,32 @@ def test_pack_emit_layout():
     assert np.array_equal(pack_emit_np(e)[0], [0, 1, 2, .5, .5, 3, .3, 5])
     e = [dict(mu=np.arange(2.), sigma=np.array([2., 3.]), kappa=0.3, nu=np.array([5., 6.]))]
     assert np.array_equal(pack_emit_np(e)[0], [0, 1, 2, 3, .3, .3, 5, 6])
+
+
+def test_gen_synthetic_variants_and_mmap(tmp_path):
+    """generate_data_smoothing / _prediction (gen_synthetic.py:59-155) share the draw order of
+    generate_data; the memmap writer/reader round-trips (:158-191)."""
+    import numpy as np
+    from pysvihmm_b200 import gen_synthetic as GS
+
+    class E(object):
+        def __init__(self, mu):
+            self.mu = np.asarray(mu, dtype=float)
+
+        def rvs(self, size=None):
+            return self.mu + np.random.normal(size=(1, len(self.mu)))
+
+    tran = np.array([[0.9, 0.1], [0.2, 0.8]])
+    emit = [E([0., 0.]), E([3., 3.])]
+    np.random.seed(3); o1, s1, _ = GS.generate_data(tran, emit, 300)
+    np.random.seed(3); o2, s2, m2 = GS.generate_data_smoothing(tran, emit, 300, miss=0.2, left=100)
+    np.random.seed(3); o3, s3, m3 = GS.generate_data_prediction(tran, emit, 300, miss=0.1)
+    assert np.array_equal(o1, o2) and np.array_equal(o1, o3) and np.array_equal(s1, s3)
+    assert m2.dtype == bool and not m2[:100].any() and m2.sum() > 0
+    assert m3[-30:].all() and not m3[:-30].any()
+    f = str(tmp_path / "obs.dat")
+    np.random.seed(4); sts = GS.generate_data_mmap(tran, emit, 250, f, chunk=100)
+    mm = GS.read_data_mmap(f, 250, 2)
+    assert mm.shape == (250, 2) and sts.shape == (250,)
+    chunks = list(GS.read_data_chunks(f, 250, 2, 100))
+    assert len(chunks) == 2 and np.array_equal(chunks[1], np.asarray(mm[100:200]))
