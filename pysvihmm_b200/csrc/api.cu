@@ -151,7 +151,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
-                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G};
+                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->dn_b, c->dn_a, c->dn_r, c->dn_e};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -849,14 +849,25 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     // dense K x K step on tcgen05 (bf16 messages, float32 accumulators in tensor memory): dense.cuh
     const int KPd = (K + 63) / 64 * 64;
     const size_t smem = (size_t)DN_M * KPd * 2 + (size_t)KPd * KPd * 2 + 1024;
-    if (!c->r_ws) CU(dalloc(&c->r_ws, c->cap_rows * K));
+    const int tiles = (B + DN_M - 1) / DN_M;
+    const size_t need = (size_t)tiles * DN_M * T * K;
+    if (need > c->cap_dn) {
+      void* olds[] = {c->dn_b, c->dn_a, c->dn_r, c->dn_e};
+      for (void* p : olds) if (p) CU(cudaFree(p));
+      c->dn_b = c->dn_a = c->dn_r = nullptr; c->dn_e = nullptr; c->cap_dn = 0;
+      CU(dalloc(&c->dn_b, need)); CU(dalloc(&c->dn_a, need)); CU(dalloc(&c->dn_r, need));
+      CU(dalloc(&c->dn_e, (size_t)tiles * DN_M * T));
+      c->cap_dn = need;
+    }
     CU(cudaFuncSetAttribute(k_chain_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PhaseTimer pt(c, PH_FORWARD, st);
-      k_chain_dense<<<dim3((B + DN_M - 1) / DN_M, 2), DN_M, smem, st>>>(B, T, K, KPd, c->PtT, c->Pt, c->pi0, c->b_ws,
-                                                                     c->alpha_ws, c->r_ws, c->e_ws);
+      k_dense_tile_b<<<dim3(T, tiles), 256, 0, st>>>(B, T, K, c->b_ws, c->dn_b);
+      LAUNCHED(c);
+      k_chain_dense<<<dim3(tiles, 2), DN_M * DN_NS, smem, st>>>(B, T, K, KPd, c->PtT, c->Pt, c->pi0, c->dn_b,
+                                                       c->dn_a, c->dn_r, c->dn_e);
       LAUNCHED(c); }
     { PhaseTimer pt(c, PH_BACKWARD, st);
-      k_marginals_any<<<148 * 8, 256, 0, st>>>(R, K, c->alpha_ws, c->r_ws, c->e_ws, q, c->lt_ws);
+      k_marginals_tiled<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, K, c->dn_a, c->dn_r, c->dn_e, q, c->lt_ws);
       LAUNCHED(c);
       k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
       LAUNCHED(c); }

@@ -14,7 +14,8 @@
 //                  all threads: tcgen05.ld their accumulator row (32 columns at a time), multiply by
 //                  b[t] (and by an exact power of two taken from the previous step's row sum: the row
 //                  sum is thread-local, no shuffles), write the float32 message to HBM and its bf16
-//                  rounding into the A operand
+//                  rounding into the A operand.  The step tables are kept window-minor ("tile
+//                  layout", below) so that these per-thread accesses are one 128-byte line per warp.
 // The descriptor encodings (shared-memory matrix descriptor, instruction descriptor) and the TMEM
 // addressing were validated stand-alone by scripts/probes/umma_probe.cu (max error 9e-6 on a
 // 128 x 256 x 256 bf16 GEMM against the host).
@@ -23,6 +24,7 @@
 #include "common.cuh"
 
 #define DN_M 128
+#define DN_NS 4          // threads per window in k_chain_dense: each owns every DN_NS-th 32-column chunk
 
 __device__ __forceinline__ uint32_t dn_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // shared-memory matrix descriptor: K-major operand, 64-column (128-byte) slabs, SWIZZLE_128B
@@ -44,60 +46,94 @@ __device__ __forceinline__ uint32_t dn_pack(const float a, const float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Mrow: the B operand source, row-major [n][k] float (forward: P^T, backward: P).  Tables as in
-// k_chain_wide: alpha_out scaled by 2^-E (E per row), beta_out arbitrary power-of-two scale per row.
-__global__ void __launch_bounds__(DN_M)
+// Tile layout of the step tables (bT, alphaT, betaT): [tile][t][k][128 windows], so that thread = window
+// accesses are fully coalesced (one 128-byte line per warp and state) and one step of a tile is one
+// contiguous K x 512-byte block; ET is [tile][t][128].
+__device__ __forceinline__ size_t dn_tile_off(const int tile, const int T, const int K, const int t) {
+  return ((size_t)tile * T + t) * K * DN_M;
+}
+
+// b[w][t][k] (row-major, k_ll_to_b) -> bT in tile layout; rows of windows beyond B are zero
+__global__ void __launch_bounds__(256)
+k_dense_tile_b(int B, int T, int K, const float* __restrict__ b, float* __restrict__ bT) {
+  __shared__ float s[32][DN_M + 1];
+  const int t = blockIdx.x, tile = blockIdx.y, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  float* out = bT + dn_tile_off(tile, T, K, t);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int wl = wp * 16 + i, w = tile * DN_M + wl, k = k0 + lane;
+      s[lane][wl] = (w < B && k < K) ? __ldg(b + ((size_t)w * T + t) * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = wp * 4 + i;
+      if (k0 + kk < K)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[(size_t)(k0 + kk) * DN_M + j * 32 + lane] = s[kk][j * 32 + lane];
+    }
+    __syncthreads();
+  }
+}
+
+// Mrow: the B operand source, row-major [n][k] float (forward: P^T, backward: P).  Tables in tile
+// layout: alphaT scaled by 2^-E (E per row, ET), betaT arbitrary power-of-two scale per row.
+__global__ void __launch_bounds__(DN_M * DN_NS)
 k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const float* __restrict__ Pbwd,
-              const float* __restrict__ pi0, const float* __restrict__ b, float* __restrict__ alpha_out,
-              float* __restrict__ beta_out, int* __restrict__ E_out) {
+              const float* __restrict__ pi0, const float* __restrict__ bT, float* __restrict__ alphaT,
+              float* __restrict__ betaT, int* __restrict__ ET) {
   extern __shared__ __align__(1024) uint8_t dsm_raw[];
   uint8_t* dsm = dsm_raw + ((1024u - (dn_smem(dsm_raw) & 1023u)) & 1023u);   // SWIZZLE_128B atoms: 1024-byte aligned
   uint8_t* sA = dsm;                               // DN_M x KP bf16
   uint8_t* sB = dsm + (size_t)DN_M * KP * 2;       // KP x KP bf16
   __shared__ __align__(8) unsigned long long bar;
   __shared__ uint32_t tmem_base;
-  const int tid = threadIdx.x, wp = tid >> 5;
+  __shared__ float psum[2][DN_NS][DN_M];           // partial row sums of the DN_NS threads of a window, by step parity
+  const int tid = threadIdx.x & (DN_M - 1), wp = tid >> 5, part = threadIdx.x >> 7;
   const bool fwd = blockIdx.y == 0;
-  const int w = blockIdx.x * DN_M + tid;            // this thread's window
-  const bool live = w < B;
+  const int tile = blockIdx.x;
   const float* Mrow = fwd ? Pfwd : Pbwd;
   // B operand: row n, column k (zero padded to KP x KP)
-  for (int i = tid; i < KP * (KP / 8); i += DN_M) {
+  for (int i = threadIdx.x; i < KP * (KP / 8); i += DN_M * DN_NS) {
     const int n = i / (KP / 8), c = i - n * (KP / 8);
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { const int k = 8 * c + u; v[u] = (n < K && k < K) ? __ldg(Mrow + (size_t)n * K + k) : 0.f; }
     *reinterpret_cast<uint4*>(sB + dn_chunk(n, c, KP)) = make_uint4(dn_pack(v[0], v[1]), dn_pack(v[2], v[3]), dn_pack(v[4], v[5]), dn_pack(v[6], v[7]));
   }
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(&bar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (wp == 0) {
+  if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dn_smem(&tmem_base)), "r"(256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // step 0: forward alpha_0 = pi0 * b_0; backward beta_{T-1} = 1, carried b_{T-1}
   const int dt = fwd ? 1 : -1;
   int t = fwd ? 0 : T - 1;
-  const size_t wbase = (size_t)(live ? w : 0) * T * K;
-  float* outp = (fwd ? alpha_out : beta_out) + wbase;
-  const float* bw = b + wbase;
+  const size_t tb = dn_tile_off(tile, T, K, 0) + tid;      // + (t*K + k)*DN_M
+  float* outp = (fwd ? alphaT : betaT) + tb;
+  const float* bw = bT + tb;
+  int* Ep = ET + (size_t)tile * T * DN_M + tid;
   float sum = 0.f;
+  if (part == 0)
   for (int c = 0; c < KP / 8; ++c) {
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int k = 8 * c + u;
-      const float bb = (live && k < K) ? bw[(size_t)t * K + k] : 0.f;
-      v[u] = fwd ? ((live && k < K) ? __ldg(pi0 + k) * bb : 0.f) : bb;
-      if (live && k < K) outp[(size_t)t * K + k] = fwd ? v[u] : 1.f;
+      const float bb = (k < K) ? bw[((size_t)t * K + k) * DN_M] : 0.f;
+      v[u] = fwd ? ((k < K) ? __ldg(pi0 + k) * bb : 0.f) : bb;
+      if (k < K) outp[((size_t)t * K + k) * DN_M] = fwd ? v[u] : 1.f;
       sum += v[u];
     }
     *reinterpret_cast<uint4*>(sA + dn_chunk(tid, c, DN_M)) = make_uint4(dn_pack(v[0], v[1]), dn_pack(v[2], v[3]), dn_pack(v[4], v[5]), dn_pack(v[6], v[7]));
   }
   int E = 0;
-  if (fwd && live) E_out[(size_t)w * T + t] = 0;
+  if (fwd && part == 0) Ep[(size_t)t * DN_M] = 0;
+  psum[0][part][tid] = sum;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -108,7 +144,10 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
   uint32_t phase = 0;
   for (int s = 1; s < T; ++s) {
     t += dt;
-    if (tid == 0) {
+    sum = 0.f;
+#pragma unroll
+    for (int p2 = 0; p2 < DN_NS; ++p2) sum += psum[(s - 1) & 1][p2][tid];     // same order in every thread of the window
+    if (threadIdx.x == 0) {
       for (int ks = 0; ks < KP / 16; ++ks) {
         const uint64_t da = dn_desc(aA + (ks >> 2) * (DN_M * 128) + (ks & 3) * 32);
         const uint64_t db = dn_desc(aB + (ks >> 2) * (KP * 128) + (ks & 3) * 32);
@@ -124,25 +163,32 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
     d = max(-100, min(100, d));
     const float r = __uint_as_float((unsigned)(127 - d) << 23);
     E += d;
+    const float* bt = bw + (size_t)t * K * DN_M;
+    float* ot = outp + (size_t)t * K * DN_M;
+    // the tile of step s+2 (contiguous K x 512 bytes) into L2: K*4 bytes per thread
+    if (s + 2 < T) {
+      const char* pf = reinterpret_cast<const char*>(bT + dn_tile_off(tile, T, K, t + 2 * dt)) + (size_t)threadIdx.x * K;
+      for (int o = 0; o < K; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
+    }
+    float bq[2][32];                                   // this thread's b of the whole step: in flight under the MMA
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int k = (part + ci * DN_NS) * 32 + j;
+        bq[ci][j] = (k < K) ? bt[(size_t)k * DN_M] : 0.f;
+      }
     uint32_t ok = 0;
     while (!ok)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(dn_smem(&bar)), "r"(phase) : "memory");
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    sum = 0.f;
-    // b of this step was pulled into L2 two steps ago; pull the row of step s+2 now (8 x 128 B per thread)
-    if (live && s + 2 < T) {
-      const char* pf = reinterpret_cast<const char*>(bw + (size_t)(t + 2 * dt) * K);
-      for (int o = 0; o < K * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + o));
-    }
-    float4 bq[8];                                      // b of the chunk being processed, fetched one chunk ahead
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
-      const int k = q4 * 4;
-      bq[q4] = (live && k < K) ? *reinterpret_cast<const float4*>(bw + (size_t)t * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int c32 = 0; c32 < KP / 32; ++c32) {
+    for (int ci = 0; ci < 2; ++ci) {                   // KP <= 256: at most two 32-column chunks per thread
+      const int c32 = part + ci * DN_NS;
+      if (c32 >= KP / 32) break;
       uint32_t a[32];
       const uint32_t ta = tm + ((uint32_t)(wp * 32) << 16) + c32 * 32;
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -151,26 +197,22 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
                      "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]),
                      "=r"(a[30]), "=r"(a[31]) : "r"(ta) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float4 bn[8];                                    // next chunk's b: in flight while this chunk is processed
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const int k = (c32 + 1) * 32 + q4 * 4;
-        bn[q4] = (live && k < K) ? *reinterpret_cast<const float4*>(bw + (size_t)t * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 32; j += 4) {
+        const int k = c32 * 32 + j;
+        const float m0 = __uint_as_float(a[j]) * r, m1 = __uint_as_float(a[j + 1]) * r;
+        const float m2 = __uint_as_float(a[j + 2]) * r, m3 = __uint_as_float(a[j + 3]) * r;
+        const float v0 = m0 * bq[ci][j], v1 = m1 * bq[ci][j + 1], v2 = m2 * bq[ci][j + 2], v3 = m3 * bq[ci][j + 3];
+        if (k < K) {                                   // K % 4 == 0: whole groups of four
+          ot[(size_t)k * DN_M] = fwd ? v0 : m0;
+          ot[(size_t)(k + 1) * DN_M] = fwd ? v1 : m1;
+          ot[(size_t)(k + 2) * DN_M] = fwd ? v2 : m2;
+          ot[(size_t)(k + 3) * DN_M] = fwd ? v3 : m3;
+        }
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        a[j] = __float_as_uint(v0); a[j + 1] = __float_as_uint(v1);
+        a[j + 2] = __float_as_uint(v2); a[j + 3] = __float_as_uint(v3);
       }
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {                 // 4 columns at a time: one STG.128
-        const int k = c32 * 32 + q4 * 4;
-        const float4 bb = bq[q4];
-        const float m0 = __uint_as_float(a[q4 * 4]) * r, m1 = __uint_as_float(a[q4 * 4 + 1]) * r;
-        const float m2 = __uint_as_float(a[q4 * 4 + 2]) * r, m3 = __uint_as_float(a[q4 * 4 + 3]) * r;
-        const float v0 = m0 * bb.x, v1 = m1 * bb.y, v2 = m2 * bb.z, v3 = m3 * bb.w;
-        if (live && k < K) *reinterpret_cast<float4*>(outp + (size_t)t * K + k) = fwd ? make_float4(v0, v1, v2, v3) : make_float4(m0, m1, m2, m3);
-        sum += (v0 + v1) + (v2 + v3);
-        a[q4 * 4] = __float_as_uint(v0); a[q4 * 4 + 1] = __float_as_uint(v1);
-        a[q4 * 4 + 2] = __float_as_uint(v2); a[q4 * 4 + 3] = __float_as_uint(v3);
-      }
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) bq[q4] = bn[q4];
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8)                   // the carried vector, rounded to bf16, back into the A operand
         *reinterpret_cast<uint4*>(sA + dn_chunk(tid, c32 * 4 + c8, DN_M)) =
@@ -179,29 +221,41 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
                        dn_pack(__uint_as_float(a[c8 * 8 + 4]), __uint_as_float(a[c8 * 8 + 5])),
                        dn_pack(__uint_as_float(a[c8 * 8 + 6]), __uint_as_float(a[c8 * 8 + 7])));
     }
-    if (fwd && live) E_out[(size_t)w * T + t] = E;
+    if (fwd && part == 0) Ep[(size_t)t * DN_M] = E;
+    psum[s & 1][part][tid] = (s0 + s1) + (s2 + s3);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  if (wp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256) : "memory");
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256) : "memory");
 }
 
-// q[r] = alpha[r]*beta[r] / sum, lt[r] = log(sum_k alpha[r][k]) + E[r] ln 2 for any K (warp per row)
-__global__ void __launch_bounds__(256)
-k_marginals_any(int64_t R, int K, const float* __restrict__ alpha, const float* __restrict__ beta,
-                const int* __restrict__ E, float* __restrict__ q, double* __restrict__ lt) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t r = w0; r < R; r += nw) {
-    float sa = 0.f, sp = 0.f;
-    for (int k = lane; k < K; k += 32) { const float al = alpha[r * K + k]; sa += al; sp += al * beta[r * K + k]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sp += __shfl_xor_sync(0xffffffffu, sp, o); }
-    const float inv = 1.f / sp;
-    for (int k = lane; k < K; k += 32) q[r * K + k] = alpha[r * K + k] * beta[r * K + k] * inv;
-    if (lane == 0) lt[r] = (double)logf(sa) + (double)E[r] * M_LN2;
+// tile layout -> q[w][t][k] = alpha*beta / sum (row-major, coalesced through shared memory),
+// lt[w][t] = log(sum_k alpha) + E ln 2.  One CTA per (t, tile), thread = window.
+__global__ void __launch_bounds__(DN_M)
+k_marginals_tiled(int B, int T, int K, const float* __restrict__ alphaT, const float* __restrict__ betaT,
+                  const int* __restrict__ ET, float* __restrict__ q, double* __restrict__ lt) {
+  __shared__ float s[32][DN_M + 1];
+  const int t = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  const int w = tile * DN_M + tid;
+  const size_t base = dn_tile_off(tile, T, K, t) + tid;
+  const float* al = alphaT + base;
+  const float* be = betaT + base;
+  float sa = 0.f, sp = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) { const float a = al[(size_t)k * DN_M]; sa += a; sp = fmaf(a, be[(size_t)k * DN_M], sp); }
+  const float inv = 1.f / sp;
+  if (w < B) lt[(size_t)w * T + t] = (double)logf(sa) + (double)ET[((size_t)tile * T + t) * DN_M + tid] * M_LN2;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk)
+      s[kk][tid] = (k0 + kk < K) ? al[(size_t)(k0 + kk) * DN_M] * be[(size_t)(k0 + kk) * DN_M] * inv : 0.f;
+    __syncthreads();
+    for (int i = 0; i < 32; ++i) {
+      const int wl = wp * 32 + i, ww = tile * DN_M + wl;
+      if (ww < B && k0 + lane < K) q[((size_t)ww * T + t) * K + k0 + lane] = s[lane][wl];
+    }
+    __syncthreads();
   }
 }
