@@ -151,7 +151,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
-                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->dn_b, c->dn_a, c->dn_r, c->dn_e};
+                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -666,7 +666,7 @@ static int stats_sym_phase(svihmm_ctx* c, const void* obs, int dtype, const uint
 // generic statistics contraction (stats.cuh) of a dense (B, T, K) table of marginals
 static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                                const int64_t* starts, int B, int T, const float* q, double* stats_out,
-                               unsigned flags, bool xi, cudaStream_t st) {
+                               unsigned flags, bool xi, cudaStream_t st, const uint16_t* q16 = nullptr) {
   const int K = c->K, D = c->D;
   const int64_t R = (int64_t)B * T;
   // K4: statistics
@@ -701,7 +701,51 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
     else k_stats<64><<<grid, 256, xsm, st>>>(a);
     c->launches++;
   };
-  if (xi) {
+  int nsplit_fin = (int)nsplit;
+  if (q16) {
+    // dense path: the K x K transition block on the tensor cores from the bf16 marginals in tile layout
+    // (k_tran_stats_dense adds into split 0 of the zeroed partials); the emission columns likewise when
+    // the feature rows fit one operand slot (k_emit_stats_dense), else by k_stats
+    const int KPd = (K + 63) / 64 * 64, tiles = (B + DN_M - 1) / DN_M;
+    const int NB = c->nfeat - K;
+    const bool tc_emit = !a.cat && NB <= ESD_NB && !getenv("SVIHMM_DENSE_FFMA_EMIT_STATS");
+    if (tc_emit) {
+      const size_t needf = (size_t)tiles * T * NB * DN_M;
+      if (needf > c->cap_dnf) {
+        if (c->dn_fhi) CU(cudaFree(c->dn_fhi));
+        if (c->dn_flo) CU(cudaFree(c->dn_flo));
+        c->dn_fhi = c->dn_flo = nullptr; c->cap_dnf = 0;
+        CU(dalloc(&c->dn_fhi, needf)); CU(dalloc(&c->dn_flo, needf));
+        c->cap_dnf = needf;
+      }
+      nsplit_fin = 1;
+      CU(cudaMemsetAsync(c->part_ws, 0, (size_t)K * c->nfeat * sizeof(float), st));
+      k_dense_tile_feat<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, D, NB, a.diag, obs, dtype, mask, starts,
+                                                        reinterpret_cast<__nv_bfloat16*>(c->dn_fhi),
+                                                        reinterpret_cast<__nv_bfloat16*>(c->dn_flo));
+      LAUNCHED(c);
+      const int TSe = std::max(1, std::min(T, 148 / tiles));
+      const size_t smem_e = (size_t)TSD_SLOT + 2 * (size_t)ESD_NB * 256 + 1024;
+      CU(cudaFuncSetAttribute(k_emit_stats_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+      k_emit_stats_dense<<<dim3(tiles, TSe), 256, smem_e, st>>>(T, K, KPd, NB, TSe, reinterpret_cast<const __nv_bfloat16*>(q16),
+                                                               reinterpret_cast<const __nv_bfloat16*>(c->dn_fhi),
+                                                               reinterpret_cast<const __nv_bfloat16*>(c->dn_flo),
+                                                               c->part_ws, c->nfeat, K);
+      LAUNCHED(c);
+    } else {
+      launch_stats(q, q, K, c->nfeat, 0);
+      CU(cudaMemset2DAsync(c->part_ws, (size_t)c->nfeat * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)nsplit * K, st));
+    }
+    const int NP = (flags & SVIHMM_WRAP) ? T : T - 1;
+    const int TS = std::max(1, std::min(NP, 148 / tiles));
+    const size_t smem = 3 * (size_t)TSD_SLOT + 1024;
+    CU(cudaFuncSetAttribute(k_tran_stats_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (NP > 0) {
+      k_tran_stats_dense<<<dim3(tiles, TS), 256, smem, st>>>(T, K, KPd, NP, TS, reinterpret_cast<const __nv_bfloat16*>(q16),
+                                                            c->part_ws, c->nfeat);
+      LAUNCHED(c);
+    }
+  } else if (xi) {
     launch_stats(c->alpha_ws, c->r_ws, 0, K, 0);
     launch_stats(q, q, K, c->nfeat, 0);
   } else {
@@ -709,7 +753,7 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
   }
   CU(cudaGetLastError());
   k_stats_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
-      B, T, K, D, c->DD, c->nfeat, (int)nsplit, c->part_ws, q, c->seq_ws, c->prior_tran,
+      B, T, K, D, c->DD, c->nfeat, nsplit_fin, c->part_ws, q, c->seq_ws, c->prior_tran,
       (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, c->Pt, xi ? 1 : 0, stats_out, c->slen);
   LAUNCHED(c);
   return SVIHMM_OK;
@@ -850,11 +894,13 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     const int KPd = (K + 63) / 64 * 64;
     const size_t smem = (size_t)DN_M * KPd * 2 + (size_t)KPd * KPd * 2 + 1024;
     const int tiles = (B + DN_M - 1) / DN_M;
+    const bool tc_tran = trim == 0 && !mix && !getenv("SVIHMM_DENSE_FFMA_STATS");   // transition statistic on tcgen05
     const size_t need = (size_t)tiles * DN_M * T * K;
     if (need > c->cap_dn) {
-      void* olds[] = {c->dn_b, c->dn_a, c->dn_r, c->dn_e};
+      void* olds[] = {c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16};
       for (void* p : olds) if (p) CU(cudaFree(p));
-      c->dn_b = c->dn_a = c->dn_r = nullptr; c->dn_e = nullptr; c->cap_dn = 0;
+      c->dn_b = c->dn_a = c->dn_r = nullptr; c->dn_e = nullptr; c->dn_q16 = nullptr; c->cap_dn = 0;
+      CU(dalloc(&c->dn_q16, need));
       CU(dalloc(&c->dn_b, need)); CU(dalloc(&c->dn_a, need)); CU(dalloc(&c->dn_r, need));
       CU(dalloc(&c->dn_e, (size_t)tiles * DN_M * T));
       c->cap_dn = need;
@@ -867,7 +913,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
                                                        c->dn_a, c->dn_r, c->dn_e);
       LAUNCHED(c); }
     { PhaseTimer pt(c, PH_BACKWARD, st);
-      k_marginals_tiled<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, K, c->dn_a, c->dn_r, c->dn_e, q, c->lt_ws);
+      k_marginals_tiled<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, K, c->dn_a, c->dn_r, c->dn_e, q, c->lt_ws,
+                                                         tc_tran ? reinterpret_cast<__nv_bfloat16*>(c->dn_q16) : nullptr);
       LAUNCHED(c);
       k_seq_logz_lt<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, c->lt_ws, c->mx_ws, c->seq_ws);
       LAUNCHED(c); }
@@ -875,7 +922,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     if ((rc = trim_for_stats())) return rc;
     c->last_B = B; c->last_T = T; c->last_fused = 1;
     if (mix) return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
-    return stats_generic_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, false, st);
+    return stats_generic_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, false, st,
+                               tc_tran ? c->dn_q16 : nullptr);
   }
   if (K <= 32) {
     switch (c->KP) {

@@ -60,7 +60,7 @@ struct svihmm_ctx {
   double* ell_ws; float *resp_ws, *wq_ws, *part2_ws; size_t cap_rows_mix, cap_part2;   // mixture workspaces
   float *qin_ws, *respin_ws; int64_t* starts_in; size_t cap_qin, cap_respin, cap_startsin;   // buffered windows
   int* e_ws;
-  float *dn_b, *dn_a, *dn_r; int* dn_e; size_t cap_dn;   // dense (tcgen05) recursion tables, tile layout
+  float *dn_b, *dn_a, *dn_r; int* dn_e; uint16_t *dn_q16, *dn_fhi, *dn_flo; size_t cap_dn, cap_dnf;   // dense (tcgen05) recursion tables, tile layout
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
   size_t hostq_cap;
   int last_B, last_T, last_fused;

@@ -232,10 +232,12 @@ k_chain_dense(int B, int T, int K, int KP, const float* __restrict__ Pfwd, const
 }
 
 // tile layout -> q[w][t][k] = alpha*beta / sum (row-major, coalesced through shared memory),
-// lt[w][t] = log(sum_k alpha) + E ln 2.  One CTA per (t, tile), thread = window.
+// lt[w][t] = log(sum_k alpha) + E ln 2, and optionally q16 = bf16(q) in tile layout.  One CTA per
+// (t, tile), thread = window.
 __global__ void __launch_bounds__(DN_M)
 k_marginals_tiled(int B, int T, int K, const float* __restrict__ alphaT, const float* __restrict__ betaT,
-                  const int* __restrict__ ET, float* __restrict__ q, double* __restrict__ lt) {
+                  const int* __restrict__ ET, float* __restrict__ q, double* __restrict__ lt,
+                  __nv_bfloat16* __restrict__ q16) {
   __shared__ float s[32][DN_M + 1];
   const int t = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   const int w = tile * DN_M + tid;
@@ -249,8 +251,12 @@ k_marginals_tiled(int B, int T, int K, const float* __restrict__ alphaT, const f
   if (w < B) lt[(size_t)w * T + t] = (double)logf(sa) + (double)ET[((size_t)tile * T + t) * DN_M + tid] * M_LN2;
   for (int k0 = 0; k0 < K; k0 += 32) {
 #pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk)
-      s[kk][tid] = (k0 + kk < K) ? al[(size_t)(k0 + kk) * DN_M] * be[(size_t)(k0 + kk) * DN_M] * inv : 0.f;
+    for (int kk = 0; kk < 32; ++kk) {
+      const float v = (k0 + kk < K) ? al[(size_t)(k0 + kk) * DN_M] * be[(size_t)(k0 + kk) * DN_M] * inv : 0.f;
+      s[kk][tid] = v;
+      // the same marginal in tile layout, rounded to bf16: operand of k_tran_stats_dense (zero beyond B)
+      if (q16 && k0 + kk < K) q16[base + (size_t)(k0 + kk) * DN_M] = __float2bfloat16_rn(w < B ? v : 0.f);
+    }
     __syncthreads();
     for (int i = 0; i < 32; ++i) {
       const int wl = wp * 32 + i, ww = tile * DN_M + wl;
@@ -258,4 +264,253 @@ k_marginals_tiled(int B, int T, int K, const float* __restrict__ alphaT, const f
     }
     __syncthreads();
   }
+}
+
+// Transition statistic of the dense path on the tensor cores (replaces the [0, K) columns of k_stats,
+// i.e. hmmsgd_metaobs.py:876-878 with quirks Q1/Q2): A[i][j] = sum over windows w and pairs (t, t+1)
+// (and (T-1, 0) when wrap) of q[w][t][i] q[w][t+1][j].  In tile layout the bf16 marginals of one
+// (tile, t) are a K x 128 matrix with the reduction index (the window) contiguous, i.e. directly a
+// K-major tcgen05 operand: one pair is Q_t (M = K rows, two halves of 128) times Q_{t+1} (N = K rows) over
+// 128 windows = 16 tcgen05.mma of 128 x KP x 16, accumulated in TENSOR MEMORY across all pairs of the CTA
+// (2 x KP float32 columns).  grid (tiles, TS): a CTA owns pairs [p0, p1) of one tile; three 64 KB
+// operand slots (Q_t, Q_{t+1}, Q_{t+2} in flight by cp.async).  The epilogue adds the accumulators
+// to split 0 of the k_stats partials (float atomics), summed in float64 by k_stats_finalize.
+#define TSD_SLOT 65536
+__global__ void __launch_bounds__(256)
+k_tran_stats_dense(int T, int K, int KP, int NP, int TS, const __nv_bfloat16* __restrict__ q16,
+                   float* __restrict__ part, int N) {
+  extern __shared__ __align__(1024) uint8_t tsm_raw[];
+  uint8_t* sm = tsm_raw + ((1024u - (dn_smem(tsm_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int p0 = (int)((int64_t)blockIdx.y * NP / TS), p1 = (int)((int64_t)(blockIdx.y + 1) * NP / TS);
+  const int n = p1 - p0;
+  if (n <= 0) return;
+  for (int i = tid; i < 3 * TSD_SLOT / 16; i += 256) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dn_smem(&tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t sbase = dn_smem(sm);
+  auto load = [&](int t, int slot) {                  // Q_t: K rows x 128 windows (256 bytes per row) into a swizzled slot
+    if (t >= T) t -= T;
+    const __nv_bfloat16* src = q16 + dn_tile_off(tile, T, K, t);
+    const uint32_t dst = sbase + (uint32_t)slot * TSD_SLOT;
+    for (int i = tid; i < K * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + dn_chunk(r, c, 256)), "l"(src + (size_t)r * DN_M + c * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load(p0, 0);
+  load(p0 + 1, 1);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int MH = (KP + 127) >> 7;
+  uint32_t phase = 0;
+  for (int i = 0; i < n; ++i) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (i >= 1) {                                      // the MMAs of pair i-1 are done: slot (i+2) % 3 is free again
+      uint32_t ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(dn_smem(&bar)), "r"(phase) : "memory");
+      phase ^= 1;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (i + 2 <= n) load(p0 + i + 2, (i + 2) % 3);
+    if (tid == 0) {
+      const uint32_t aA = sbase + (uint32_t)(i % 3) * TSD_SLOT, aB = sbase + (uint32_t)((i + 1) % 3) * TSD_SLOT;
+      for (int h = 0; h < MH; ++h)
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t da = dn_desc(aA + (ks >> 2) * (256 * 128) + h * (128 * 128) + (ks & 3) * 32);
+          const uint64_t db = dn_desc(aB + (ks >> 2) * (256 * 128) + (ks & 3) * 32);
+          const uint32_t acc = (i > 0) || (ks > 0);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tm + h * 256), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dn_smem(&bar)) : "memory");
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(dn_smem(&bar)), "r"(phase) : "memory");
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // epilogue: warp (wp & 3) owns TMEM lanes 32 (wp & 3) .. +31; the two warp groups alternate 32-column chunks
+  const int wq = wp & 3, wh = wp >> 2;
+  for (int h = 0; h < MH; ++h) {
+    const int row = h * 128 + wq * 32 + lane;
+    for (int c32 = wh; c32 < KP / 32; c32 += 2) {
+      uint32_t a[32];
+      const uint32_t ta = tm + ((uint32_t)(wq * 32) << 16) + h * 256 + c32 * 32;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]),
+                     "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]),
+                     "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]),
+                     "=r"(a[30]), "=r"(a[31]) : "r"(ta) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < K)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c32 * 32 + j;
+          if (col < K) atomicAdd(part + (size_t)row * N + col, __uint_as_float(a[j]));
+        }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+}
+
+// Emission statistics of the dense path on the tensor cores (replaces the [K, K + NB) columns of
+// k_stats: n, sum w x, sum w x x^T / x^2; hmmsgd_metaobs.py:861-874 through the distribution's
+// expected statistics): S[i][f] = sum over windows and t of q[w][t][i] F[w][t][f].  The features are
+// built once per step in tile layout as bf16 hi + lo pairs (f = hi + lo to 2^-17, so only q carries
+// bf16 rounding), one CTA-step is Q_t (K x 128 windows) times [F_hi ; F_lo] accumulated into the same
+// TENSOR MEMORY columns.
+#define ESD_NB 144                                    // feature rows of an operand slot (N of the MMA)
+__global__ void __launch_bounds__(DN_M)
+k_dense_tile_feat(int B, int T, int D, int NB, int diag, const void* __restrict__ obs, int dtype,
+                  const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts,
+                  __nv_bfloat16* __restrict__ fhi, __nv_bfloat16* __restrict__ flo) {
+  const int t = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x;
+  const int w = tile * DN_M + tid;
+  const size_t base = ((size_t)tile * T + t) * NB * DN_M + tid;
+  float wv = 0.f;
+  int64_t r = 0;
+  if (w < B) {
+    r = starts[w] + t;
+    wv = (mask && mask[r]) ? 0.f : 1.f;
+    if (wv != 0.f) {
+      bool bad = false;
+      for (int d = 0; d < D; ++d) bad |= isnan((float)ld_obs(obs, dtype, r * D + d));
+      if (bad) wv = 0.f;
+    }
+  }
+  auto put = [&](const int f, const float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    fhi[base + (size_t)f * DN_M] = h;
+    flo[base + (size_t)f * DN_M] = __float2bfloat16_rn(v - __bfloat162float(h));
+  };
+  put(0, wv);
+  for (int d = 0; d < D; ++d) put(1 + d, wv != 0.f ? (float)ld_obs(obs, dtype, r * D + d) : 0.f);
+  for (int m = 0; m < NB - 1 - D; ++m) {
+    float v = 0.f;
+    if (wv != 0.f) {
+      if (diag) { const float x = (float)ld_obs(obs, dtype, r * D + m); v = x * x; }
+      else { const int d1 = m / D, d2 = m - d1 * D; v = (float)ld_obs(obs, dtype, r * D + d1) * (float)ld_obs(obs, dtype, r * D + d2); }
+    }
+    put(1 + D + m, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_emit_stats_dense(int T, int K, int KP, int NB, int TS, const __nv_bfloat16* __restrict__ q16,
+                   const __nv_bfloat16* __restrict__ fhi, const __nv_bfloat16* __restrict__ flo,
+                   float* __restrict__ part, int N, int col0) {
+  extern __shared__ __align__(1024) uint8_t esm_raw[];
+  uint8_t* sm = esm_raw + ((1024u - (dn_smem(esm_raw) & 1023u)) & 1023u);
+  constexpr int BSLOT = ESD_NB * 256;                 // 144 rows x 128 windows bf16
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  const int t0 = (int)((int64_t)blockIdx.y * T / TS), t1 = (int)((int64_t)(blockIdx.y + 1) * T / TS);
+  if (t1 <= t0) return;
+  for (int i = tid; i < (TSD_SLOT + 2 * BSLOT) / 16; i += 256) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dn_smem(&tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t aA = dn_smem(sm), aBh = aA + TSD_SLOT, aBl = aBh + BSLOT;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ESD_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int MH = (KP + 127) >> 7;
+  uint32_t phase = 0;
+  for (int t = t0; t < t1; ++t) {
+    const __nv_bfloat16* qs = q16 + dn_tile_off(tile, T, K, t);
+    for (int i = tid; i < K * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(aA + dn_chunk(r, c, 256)), "l"(qs + (size_t)r * DN_M + c * 8) : "memory");
+    }
+    const size_t fo = ((size_t)tile * T + t) * NB * DN_M;
+    for (int i = tid; i < NB * 16; i += 256) {
+      const int r = i >> 4, c = i & 15;
+      const uint32_t off = dn_chunk(r, c, ESD_NB);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(aBh + off), "l"(fhi + fo + (size_t)r * DN_M + c * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(aBl + off), "l"(flo + fo + (size_t)r * DN_M + c * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      for (int h = 0; h < MH; ++h)
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t da = dn_desc(aA + (ks >> 2) * (256 * 128) + h * (128 * 128) + (ks & 3) * 32);
+          const uint64_t dbh = dn_desc(aBh + (ks >> 2) * (ESD_NB * 128) + (ks & 3) * 32);
+          const uint64_t dbl = dn_desc(aBl + (ks >> 2) * (ESD_NB * 128) + (ks & 3) * 32);
+          const uint32_t acc = (t > t0) || (ks > 0);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tm + h * 256), "l"(da), "l"(dbh), "r"(idesc), "r"(acc) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tm + h * 256), "l"(da), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
+        }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dn_smem(&bar)) : "memory");
+    }
+    uint32_t ok = 0;                                   // single stage: the slots are rewritten after the MMAs have read them
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(dn_smem(&bar)), "r"(phase) : "memory");
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  const int wq = wp & 3, wh = wp >> 2;
+  for (int h = 0; h < MH; ++h) {
+    const int row = h * 128 + wq * 32 + lane;
+    for (int c32 = wh; c32 < (ESD_NB + 31) / 32; c32 += 2) {
+      uint32_t a[32];
+      const uint32_t ta = tm + ((uint32_t)(wq * 32) << 16) + h * 256 + c32 * 32;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]),
+                     "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]),
+                     "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]),
+                     "=r"(a[30]), "=r"(a[31]) : "r"(ta) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < K)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c32 * 32 + j;
+          if (col < NB) atomicAdd(part + (size_t)row * N + col0 + col, __uint_as_float(a[j]));
+        }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
 }
