@@ -296,21 +296,43 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
     // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
 #pragma unroll 1
     for (int n = K - 1; n >= 1; --n) {
-      if (wp == 0) {
-        double s = 0.0;
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) s += G[n * K + j];
+      // every warp: s = sum_{j<n} G[n][j] (same order in all warps), then its rows i = wp, wp + nw, ...:
+      // f = G[i][n] / s (kept for the back-substitution), G[i][j] += f G[n][j] for j < n
+      const double* rown = G + (size_t)n * K;
+      double s = 0.0;
+      if (K <= 256) {
+        double rn[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; rn[u] = j < n ? rown[j] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (lane + 32 * u < n) s += rn[u];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const double rinv = 1.0 / s;
 #pragma unroll 1
-        for (int i = lane; i < n; i += 32) G[i * K + n] *= rinv;
-      }
-      GSYNC();
+        for (int i = wp; i < n; i += nw) {
+          double* rowi = G + (size_t)i * K;
+          const double f = rowi[n] * rinv;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; if (j < n) rowi[j] = fma(f, rn[u], rowi[j]); }
+          __syncwarp();
+          if (lane == 0) rowi[n] = f;
+        }
+      } else {
 #pragma unroll 1
-      for (int idx = tid; idx < n * n; idx += nth) {
-        const int i = idx / n, j = idx - i * n;
-        G[i * K + j] = fma(G[i * K + n], G[n * K + j], G[i * K + j]);
+        for (int j = lane; j < n; j += 32) s += rown[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double rinv = 1.0 / s;
+#pragma unroll 1
+        for (int i = wp; i < n; i += nw) {
+          double* rowi = G + (size_t)i * K;
+          const double f = rowi[n] * rinv;
+#pragma unroll 4
+          for (int j = lane; j < n; j += 32) rowi[j] = fma(f, rown[j], rowi[j]);
+          __syncwarp();
+          if (lane == 0) rowi[n] = f;
+        }
       }
       GSYNC();
     }
