@@ -135,6 +135,72 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // elimination inside ONE warp: lane i keeps row i in registers, the pivot row travels by shuffles.
 // No subtractions, so the result is componentwise accurate (~1e-15); ~4k cycles at K = 16
 // (measured alternatives: block-wide elimination through memory ~22k, repeated squaring ~22k).
+// Grassmann-Taksar-Heyman elimination for K > 32 (one block, matrix in L2): censor states K-1, ..., 1.
+// Step n: every warp forms s = sum_{j<n} G[n][j] (same order in all warps), then for its rows
+// i = wp, wp + nw, ...: f = G[i][n] / s (kept for the back-substitution), G[i][j] += f G[n][j], j < n.
+// The step is bound by the L2 round trip of the rows, so R rows of a warp are in flight together.
+template <int R>
+__device__ __noinline__ void gth_block(const int K, double* __restrict__ G) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll 1
+  for (int n = K - 1; n >= 1; --n) {
+    const double* rown = G + (size_t)n * K;
+    double s = 0.0;
+    if (K <= 256) {
+      double rn[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; rn[u] = j < n ? rown[j] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (lane + 32 * u < n) s += rn[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const double rinv = 1.0 / s;
+#pragma unroll 1
+      for (int i0 = wp; i0 < n; i0 += R * nw) {
+        double* rp[R];
+        double g[R], v[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = i0 + r * nw;
+          rp[r] = G + (size_t)(i < n ? i : i0) * K;      // rows beyond n: re-read row i0, never stored
+          g[r] = rp[r][n];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; v[r][u] = j < n ? rp[r][j] : 0.0; }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          g[r] *= rinv;
+          if (i0 + r * nw < n) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; if (j < n) rp[r][j] = fma(g[r], rn[u], v[r][u]); }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) if (i0 + r * nw < n) rp[r][n] = g[r];
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = lane; j < n; j += 32) s += rown[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const double rinv = 1.0 / s;
+#pragma unroll 1
+      for (int i = wp; i < n; i += nw) {
+        double* rowi = G + (size_t)i * K;
+        const double f = rowi[n] * rinv;
+#pragma unroll 4
+        for (int j = lane; j < n; j += 32) rowi[j] = fma(f, rown[j], rowi[j]);
+        __syncwarp();
+        if (lane == 0) rowi[n] = f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int KP>
 __device__ void gth_warp(const int K, const double* __restrict__ W, const double* __restrict__ rowsum,
                          double* __restrict__ pi_out, const int lane) {
@@ -294,48 +360,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   GSTAMP(2);
   if (!a.user_init && !inwarp) {
     // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
-#pragma unroll 1
-    for (int n = K - 1; n >= 1; --n) {
-      // every warp: s = sum_{j<n} G[n][j] (same order in all warps), then its rows i = wp, wp + nw, ...:
-      // f = G[i][n] / s (kept for the back-substitution), G[i][j] += f G[n][j] for j < n
-      const double* rown = G + (size_t)n * K;
-      double s = 0.0;
-      if (K <= 256) {
-        double rn[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; rn[u] = j < n ? rown[j] : 0.0; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) if (lane + 32 * u < n) s += rn[u];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const double rinv = 1.0 / s;
-#pragma unroll 1
-        for (int i = wp; i < n; i += nw) {
-          double* rowi = G + (size_t)i * K;
-          const double f = rowi[n] * rinv;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; if (j < n) rowi[j] = fma(f, rn[u], rowi[j]); }
-          __syncwarp();
-          if (lane == 0) rowi[n] = f;
-        }
-      } else {
-#pragma unroll 1
-        for (int j = lane; j < n; j += 32) s += rown[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const double rinv = 1.0 / s;
-#pragma unroll 1
-        for (int i = wp; i < n; i += nw) {
-          double* rowi = G + (size_t)i * K;
-          const double f = rowi[n] * rinv;
-#pragma unroll 4
-          for (int j = lane; j < n; j += 32) rowi[j] = fma(f, rown[j], rowi[j]);
-          __syncwarp();
-          if (lane == 0) rowi[n] = f;
-        }
-      }
-      GSYNC();
-    }
+    gth_block<4>(K, G);
     // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]: column j accumulates as the pi[i] become final
     if (wp == 0) {
 #pragma unroll 1

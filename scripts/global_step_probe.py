@@ -3,8 +3,8 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import bench
 from pysvihmm_b200.engine import EStepEngine, pack_emit_dicts
-cfg = bench.CONFIGS["c2"]
-K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], cfg["B"], cfg["kind"]
+cfg = bench.CONFIGS[os.environ.get("DBG_CONFIG", "c2")]
+K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], int(os.environ.get("DBG_B", cfg["B"])), cfg["kind"]
 obs, mus = bench.synthetic_series(K, D, 1 << 18, 1)
 vt, em, pr = bench.globals_for(K, D, kind, mus, 1)
 eng = EStepEngine(K, D, kind)
