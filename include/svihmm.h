@@ -67,8 +67,10 @@ enum {
   SVIHMM_KEEP_LOCALS = 1u << 4, /* keep lliks/alpha/cs tables for svihmm_get_locals (unfused kernels) */
   SVIHMM_BF16_DENSE  = 1u << 5  /* 64 < K <= 256 (K % 4 == 0): the K x K step of the recursions as a dense
                                    (128 windows x K).(K x K) contraction on tcgen05 tensor cores, bf16
-                                   messages with float32 accumulators (BASELINE config 4); marginals then
-                                   agree with the float64 reference to ~1e-2 instead of 1e-5 (NOT ref) */
+                                   messages with float32 accumulators (BASELINE config 4), and the
+                                   statistics as tcgen05 contractions over the windows from bf16-rounded
+                                   marginals; marginals and statistics then agree with the float64
+                                   reference to ~1e-2 instead of 1e-5 (NOT ref) */
 };
 
 const char* svihmm_last_error(void);
