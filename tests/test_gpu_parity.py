@@ -369,6 +369,44 @@ def test_bf16_dense_tensor_core_step(K, D, T, B):
     eng.close()
 
 
+@pytest.mark.parametrize("flags_extra", ["wrap", "nowrap"])
+def test_bf16_dense_statistics_many_pairs_per_cta(flags_extra):
+    """The tcgen05 statistics kernels with MORE (tile, t) steps than CTAs, so that every CTA accumulates
+    several pairs in tensor memory (operand ring reuse, accumulate flag, mbarrier phases): 3 tiles of
+    windows and T = 200 give ~4 pairs per CTA; with and without the wrap-around pair (Q2).  Checked
+    against the float32 statistics computed by k_stats from the SAME bf16-path marginals (3e-3 relative
+    to the largest entry: only the bf16 rounding of q separates the two) and against the float32 path."""
+    from pysvihmm_b200 import _lib as L
+    K, D, T, B = 128, 4, 200, 300
+    p = make_random_problem(seed=77, K=K, D=D, T_full=2400, kind="niw_diag", miss=0.05, sep=1.5)
+    starts = np.random.RandomState(6).randint(0, p["obs"].shape[0] - T + 1, B)
+    eng = _engine(K, D, "niw_diag")
+    eng.set_series(p["obs"], p["mask"], dtype="f64")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    fl = L.ADD_PRIOR | (L.WRAP if flags_extra == "wrap" else 0)
+    vx, stats = eng.estep(starts, T, flags=fl | L.BF16_DENSE)
+    s16 = eng.unpack_stats(stats)
+    # float64 statistics from the marginals the dense path returned (product-of-marginals rule, Q1/Q2)
+    q = vx.cpu().numpy().astype(np.float64)
+    A = np.einsum("wti,wtj->ij", q[:, :-1], q[:, 1:])
+    if flags_extra == "wrap":
+        A += np.einsum("wi,wj->ij", q[:, -1], q[:, 0])
+    A += B * (p["prior_tran"] - 1.)
+    assert_block(s16["A"], A, 6e-3, "A from returned marginals")
+    idx = starts[:, None] + np.arange(T)[None, :]
+    x = np.nan_to_num(p["obs"][idx]); w = (~p["mask"][idx].astype(bool)) & ~np.isnan(p["obs"][idx]).any(-1)
+    qw = q * w[..., None]
+    assert_block(s16["n"], qw.sum((0, 1)), 6e-3, "n")
+    assert_block(s16["sx"], np.einsum("wtk,wtd->kd", qw, x), 6e-3, "sx")
+    assert_block(s16["sxx"].reshape(K, -1), np.einsum("wtk,wtd->kd", qw, x * x), 6e-3, "sxx")
+    _, stats32 = eng.estep(starts, T, flags=fl)
+    s32 = eng.unpack_stats(stats32)
+    for key in ("A", "n", "sx", "sxx"):
+        assert_block(s16[key], s32[key], 3e-2, key)
+    eng.close()
+
+
 def test_exact_xi_option_matches_oracle():
     """SVIHMM_EXACT_XI (not reference behaviour): sum_t of the true pairwise posteriors."""
     from oracle import svihmm_oracle as O
