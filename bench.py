@@ -443,6 +443,21 @@ def run_ours(args, cfg):
                             if world == 1 else "svihmm_estep_streamed + NCCL all-reduce + svihmm_global_update + D2H"},
             "gpu_launches": int(launches), "clocks": clk,
         }
+        if cfg.get("bf16_dense"):
+            # the dense K x K work (forward + backward matvecs + transition statistic =
+            # 6 K^2 T flop per E-step) against the measured bf16 tensor peak, over the phases that hold it
+            try:
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                tpeak, tsrc = float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+            except Exception:
+                tpeak, tsrc = 1357.7, "fallback (SURVEY section 8d bf16_tflops_sustained)"
+            ph = line["roofline"]["phases_ms_per_step"]
+            dense_ms = ph.get("forward", 0.0) + ph.get("stats", 0.0)
+            if dense_ms > 0:
+                tf = B * 6.0 * K * K * T / (dense_ms * 1e-3) / 1e12
+                line["roofline"]["tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                                              "frac": tf / tpeak, "flops_fb_per_estep": 6 * K * K * T,
+                                              "phases": "forward (both chains) + stats", "peak_source": tsrc}
         if world == 1 and not args.no_cpu and C_mix == 1:     # the reference has no mixture-emission E-step
             cb, _, _ = cpu_estep_rate(cfg, 12.0, 400)
             line["cpu_baseline"] = cb
