@@ -215,6 +215,43 @@ def multivariate_t_loglik(y, nu, mu, lmbda):
 '''
 
 
+# hmm_fast.pyx (the reference's only native binding): mechanical patches for Cython 3 / numpy 2
+PYX_PATCHES = [
+    ("xrange -> range", re.compile(r"\bxrange\b"), "range"),
+    ("np.int_t is gone from numpy.pxd", re.compile(r"np\.int_t\b"), "np.int64_t"),
+    ("np.int_ -> fixed width to match the buffer type", re.compile(r"dtype=np\.int_\b"), "dtype=np.int64"),
+    ("array == None", re.compile(r"lalpha_init == None"), "lalpha_init is None"),
+]
+
+
+def build_hmm_fast(src, dst, verbose=True):
+    """Cythonize and compile the reference's FFBS sampler (hmm_fast.pyx) into dst; returns the path
+    of the extension module or None (the stub hmm_fast.py then stays in charge)."""
+    import subprocess
+    import sysconfig
+    try:
+        import numpy
+        text = open(os.path.join(src, "hmm_fast.pyx")).read()
+        for _, rx, rep in PYX_PATCHES:
+            text = rx.sub(rep, text)
+        pyx = os.path.join(dst, "hmm_fast.pyx")
+        with open(pyx, "w") as f:
+            f.write("# GENERATED by oracle/build_ref.py from hmm_fast.pyx -- do not commit\n" + text)
+        subprocess.check_call([sys.executable, "-m", "cython", "-3", pyx, "-o", os.path.join(dst, "hmm_fast.c")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        so = os.path.join(dst, "hmm_fast" + sysconfig.get_config_var("EXT_SUFFIX"))
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-w", "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
+                               "-I", sysconfig.get_paths()["include"], "-I", numpy.get_include(),
+                               os.path.join(dst, "hmm_fast.c"), "-o", so])
+        if verbose:
+            print("hmm_fast.pyx                       cythonized and compiled -> %s" % os.path.basename(so))
+        return so
+    except Exception as e:                      # no compiler / cython: the E-step path does not need it
+        if verbose:
+            print("hmm_fast.pyx                       NOT built (%s); stub kept" % e)
+        return None
+
+
 def patch_text(text):
     applied = []
     for desc, rx, rep in PATCHES:
@@ -252,6 +289,7 @@ def build(src, dst, verbose=True):
         f.write(UTIL_STATS_SHIM)
     with open(os.path.join(dst, "__init__.py"), "w") as f:
         f.write("")
+    build_hmm_fast(src, dst, verbose)
     return dst
 
 

@@ -285,6 +285,93 @@ def gen_case(name, seed):
     print("%-22s gen_synthetic T=%d masked=%d" % (name, T, int(mask.sum())))
 
 
+def adaptive_case(name, seed, K, D, T_full, sep):
+    """The adaptive-window machinery of hmmsgd_metaobs.VBHMM run by the reference itself:
+    get_local_messages (:663-700), select_L (:521-569, non-averaged branch), select_buffer (:579-661)
+    and local_update + intermediate_pars_buffer (:932-1008) on buffered windows.  The centre indices
+    the reference draws (npr.choice, first RNG call of each function) are re-drawn from the same seed
+    and stored, so that the oracle can be driven with them explicitly."""
+    obs, sts, mask, init, prior, init_tran = make_problem(seed, K, D, T_full, sep, miss=0.08)
+    prior_emit = emit_objects(init, prior)
+    hmm = HSGD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7,
+                     metaobs_half=5, mb_sz=3, mask=mask, init_tran=init_tran.copy(), maxit=1, seed=seed)
+    # var_init as infer sets it before every local update (hmmsgd_metaobs.py:413-418)
+    A_mean = hmm.var_tran / np.sum(hmm.var_tran, axis=1)[:, None]
+    ew, ev = np.linalg.eig(A_mean.T)
+    hmm.var_init = np.abs(ev[:, np.argsort(ew)[::-1][0]])
+    out = dict(obs=obs, sts=sts, mask=mask, init_tran=init_tran, prior_tran=np.ones((K, K)),
+               prior_mu=prior['mu'], prior_sigma=prior['sigma'], prior_kappa=prior['kappa'],
+               prior_nu=prior['nu'], var_init=hmm.var_init.copy())
+    pack_emit("init", hmm.var_emit, out)
+    out["glm_ind"], out["glm_half"] = 100, 7
+    out["glm_var_x"] = hmm.get_local_messages(100, 7).copy()
+    sl = dict(numIndices=4, epsilon=1e-3, minHalfL=2, Lincrement=2, Lcutoff=40)
+    np.random.seed(seed + 1)
+    out["selL"] = int(hmm.select_L(**sl))
+    np.random.seed(seed + 1)
+    out["selL_indices"] = np.random.choice(T_full - 2 * sl["minHalfL"] - 1, size=sl["numIndices"]) + sl["minHalfL"]
+    out["selL_args"] = np.array([sl["epsilon"], sl["minHalfL"], sl["Lincrement"], sl["Lcutoff"]])
+    sb = dict(numIndices=4, epsilon=1e-3, halfL=5, Lincrement=1, Lcutoff=40)
+    np.random.seed(seed + 2)
+    out["selB"] = int(hmm.select_buffer(**sb))
+    np.random.seed(seed + 2)
+    out["selB_indices"] = np.random.choice(T_full - 2 * sb["halfL"] - 1, size=sb["numIndices"]) + sb["halfL"]
+    out["selB_args"] = np.array([sb["epsilon"], sb["halfL"], sb["Lincrement"], sb["Lcutoff"]])
+    # buffered windows as in infer's growBuffer branch (:371-433)
+    L, bufferL = 5, max(int(out["selB"]), 7)
+    centres = np.array([40, 133, 250])
+    n = 2 * bufferL + 1
+    hmm.var_x = np.ones((n, K)) / K
+    hmm.lalpha, hmm.lbeta, hmm.lliks = np.empty((n, K)), np.empty((n, K)), np.empty((n, K))
+    A_inter = np.zeros((K, K))
+    e1, e2, e3, vx, lb = 0., 0., 0., [], 0.
+    for c in centres:
+        mo = HSGD.MetaObs(int(c - bufferL), int(c + bufferL))
+        hmm.cur_mo = mo
+        hmm.local_update(metaobs=mo)
+        A_i, e_i = hmm.intermediate_pars_buffer(mo, bufferL, L)
+        A_inter += A_i
+        e1 = e1 + np.array([e[0] for e in e_i])
+        e2 = e2 + np.array([e[1] for e in e_i], dtype=float)
+        e3 = e3 + np.array([e[2] for e in e_i])
+        vx.append(hmm.var_x.copy())
+        lb += hmm.local_lower_bound()
+    out.update(buf_L=L, buf_bufferL=bufferL, buf_starts=centres - bufferL, buf_var_x=np.array(vx),
+               buf_A_inter=A_inter, buf_e1=e1, buf_e2=e2, buf_e3=e3, buf_lb=lb)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s K=%d D=%d  select_L=%d select_buffer=%d bufferL=%d" % (name, K, D, out["selL"], out["selB"], bufferL))
+
+
+def ffbs_case(name, seed, K, D, T, sep, npaths=20000):
+    """The reference's native sampler hmm_fast.FFBS (hmm_fast.pyx:43-124, compiled by
+    oracle/build_ref.py) on one short series: its forward table (deterministic) and the empirical
+    state / pair frequencies of `npaths` sampled paths (libc rand() seeded through srand)."""
+    import ctypes
+    import hmm_fast
+    obs, sts, mask, init, prior, init_tran = make_problem(seed, K, D, T, sep)
+    prior_emit = emit_objects(init, prior)
+    hmm = HSGD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7,
+                     metaobs_half=2, mb_sz=1, mask=mask, init_tran=init_tran.copy(), maxit=1, seed=seed)
+    A_mean = hmm.var_tran / np.sum(hmm.var_tran, axis=1)[:, None]
+    ew, ev = np.linalg.eig(A_mean.T)
+    var_init = np.abs(ev[:, np.argsort(ew)[::-1][0]])
+    ctypes.CDLL(None).srand(seed)
+    z, lalpha = hmm_fast.FFBS(hmm, var_init)
+    cnt = np.zeros((T, K))
+    pair = np.zeros((T - 1, K, K))
+    tt = np.arange(T)
+    for _ in range(npaths):
+        z, _la = hmm_fast.FFBS(hmm, var_init, lalpha)
+        cnt[tt, z] += 1
+        pair[tt[:-1], z[:-1], z[1:]] += 1
+    out = dict(obs=obs, init_tran=init_tran, var_init=var_init, lalpha=np.array(lalpha), counts=cnt,
+               pair_counts=pair, npaths=npaths)
+    pack_emit("init", hmm.var_emit, out)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s K=%d D=%d T=%d paths=%d  frac(max freq<0.99)=%.2f" % (
+        name, K, D, T, npaths, float(np.mean(cnt.max(1) / npaths < 0.99))))
+
+
 if __name__ == "__main__":
     svi_case("svi_k3_d2_l5", seed=11, K=3, D=2, T_full=300, L=5, mb_sz=4, sep=0.6)
     svi_case("svi_k5_d3_l20_mask", seed=12, K=5, D=3, T_full=600, L=20, mb_sz=6, sep=0.5, miss=0.15)
@@ -296,3 +383,5 @@ if __name__ == "__main__":
     ell_1d_case("ell_1d", seed=31)
     cat_case("cat_ell", seed=32)
     gen_case("gen_synthetic_k4", seed=8675309)
+    adaptive_case("adaptive_k3_d2", seed=41, K=3, D=2, T_full=320, sep=0.6)
+    ffbs_case("ffbs_k3_d2_t40", seed=51, K=3, D=2, T=40, sep=0.5)

@@ -158,3 +158,48 @@ def test_adagrad_branch_matches_reference():
         np.testing.assert_allclose(r["var_tran_new"], g["g_var_tran"][it], rtol=RT, atol=AT)
         np.testing.assert_allclose(np.array([e["mu"] for e in r["emit_new"]]), g["g_mu"][it], rtol=1e-9, atol=AT)
         var_tran, emit = r["var_tran_new"], r["emit_new"]
+
+
+def test_adaptive_window_machinery_matches_reference():
+    """get_local_messages / select_L / select_buffer / intermediate_pars_buffer of the reference
+    (hmmsgd_metaobs.py:521-700,932-1008; fixture adaptive_k3_d2 made by running them) against the
+    oracle's restatements, driven with the centre indices the reference drew."""
+    g = load_golden("adaptive_k3_d2")
+    obs, mask = g["obs"], g["mask"]
+    K = g["init_tran"].shape[0]
+    var_tran, var_init = g["init_tran"], g["var_init"]
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    np.testing.assert_allclose(O.stationary_init(var_tran), var_init, rtol=1e-9, atol=AT)
+    vx = O.get_local_messages(obs, int(g["glm_ind"]), int(g["glm_half"]), var_init, var_tran, emit)
+    np.testing.assert_allclose(vx, g["glm_var_x"], rtol=1e-9, atol=AT)
+    eps, minL, inc, cut = g["selL_args"]
+    assert O.select_L(obs, g["selL_indices"], var_init, var_tran, emit, epsilon=float(eps), minHalfL=int(minL),
+                      Lincrement=int(inc), Lcutoff=int(cut)) == int(g["selL"])
+    eps, halfL, inc, cut = g["selB_args"]
+    assert O.select_buffer(obs, g["selB_indices"], var_init, var_tran, emit, epsilon=float(eps), halfL=int(halfL),
+                           Lincrement=int(inc), Lcutoff=int(cut)) == int(g["selB"])
+    r = O.buffered_stats(obs, mask, g["buf_starts"], int(g["buf_bufferL"]), int(g["buf_L"]), var_tran, emit,
+                         g["prior_tran"])
+    np.testing.assert_allclose(r["var_x"], g["buf_var_x"], rtol=1e-9, atol=AT)
+    np.testing.assert_allclose(r["A_inter"], g["buf_A_inter"], rtol=RT, atol=AT)
+    np.testing.assert_allclose(np.array([e[0] for e in r["emit_inter"]]), g["buf_e1"], rtol=RT, atol=AT)
+    np.testing.assert_allclose(np.array([e[1] for e in r["emit_inter"]]), g["buf_e2"], rtol=RT, atol=AT)
+    np.testing.assert_allclose(np.array([e[2] for e in r["emit_inter"]]), g["buf_e3"], rtol=RT, atol=AT)
+    np.testing.assert_allclose(r["lb"], float(g["buf_lb"]), rtol=RT)
+
+
+def test_ffbs_tables_match_reference_sampler():
+    """oracle.ffbs_tables against the reference's own native sampler (hmm_fast.FFBS, compiled from
+    hmm_fast.pyx by oracle/build_ref.py; fixture ffbs_k3_d2_t40): the forward table it returns
+    (log(A + eps) transition weights, hmm_fast.pyx:82-100) to round-off, and the state / pair
+    frequencies of its 20000 sampled paths within 5-sigma binomial bands of the exact marginals of
+    the law the oracle says it samples from."""
+    g = load_golden("ffbs_k3_d2_t40")
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    lalpha, marg, pair = O.ffbs_tables(g["obs"], g["var_init"], g["init_tran"], emit)
+    np.testing.assert_allclose(lalpha, g["lalpha"], rtol=RT, atol=1e-9)
+    n = float(g["npaths"])
+    for p, cnt in ((marg, g["counts"]), (pair, g["pair_counts"])):
+        sd = np.sqrt(np.maximum(p * (1. - p), 1e-12) / n)
+        assert np.all(np.abs(cnt / n - p) <= 5. * sd + 2. / n), float(np.max(np.abs(cnt / n - p) / sd))
+    assert np.mean(marg.max(1) < 0.99) > 0.5            # not a vacuous (one-hot) case
