@@ -580,6 +580,27 @@ def buffered_stats(obs, mask, starts, bufferL, L, var_tran, emit, prior_tran):
 
 
 # --------------------------------------------------------------------------
+# predictive log-probability of the held-out rows (hmmsgd_metaobs.py:1086-1205)
+# --------------------------------------------------------------------------
+def full_local_update(obs, mask, var_init, var_tran, emit):
+    """hmmsgd_metaobs.py:1147-1205: marginals of the whole series with the masked rows NaN-ed
+    (they carry no evidence: ll = 0 through nan_to_num)."""
+    xo = obs.copy()
+    xo[np.asarray(mask, bool)] = np.nan
+    return local_update(xo[None], var_init, var_tran, emit)['var_x'][0]
+
+
+def pred_logprob(var_x, obs, mask, emit):
+    """hmmsgd_metaobs.py:1111-1119 / :1139-1145: mean over the masked rows of
+    logsumexp_k(log(var_x + eps) + ELL_k(x)) with the TRUE observations; None without masked rows."""
+    m = np.asarray(mask, bool)
+    if not m.any():
+        return None
+    ll = lliks_gaussian(obs[m][None], emit)[0]
+    return float(np.mean(np.logaddexp.reduce(np.log(var_x[m] + EPS) + ll, axis=1)))
+
+
+# --------------------------------------------------------------------------
 # forward-filter backward-sampling (hmm_fast.pyx:43-124)
 # --------------------------------------------------------------------------
 def ffbs_tables(obs, var_init, var_tran, emit):

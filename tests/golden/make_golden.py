@@ -372,6 +372,55 @@ def ffbs_case(name, seed, K, D, T, sep, npaths=20000):
         name, K, D, T, npaths, float(np.mean(cnt.max(1) / npaths < 0.99))))
 
 
+def pred_case(name, seed, K, D, T_full, sep):
+    """pred_logprob (hmmsgd_metaobs.py:1086-1119), full_local_update (:1147-1205) and
+    pred_logprob_full (:1121-1145) run by the reference.  `obs_full` is never assigned by the reference
+    itself (its assignment at :315 is commented out); the caller supplies it, as done here."""
+    obs, sts, mask, init, prior, init_tran = make_problem(seed, K, D, T_full, sep, miss=0.2)
+    prior_emit = emit_objects(init, prior)
+    hmm = HSGD.VBHMM(obs.copy(), np.ones(K), np.ones((K, K)), prior_emit, tau=1., kappa=0.7,
+                     metaobs_half=10, mb_sz=2, mask=mask, init_tran=init_tran.copy(), maxit=1, seed=seed)
+    A_mean = hmm.var_tran / np.sum(hmm.var_tran, axis=1)[:, None]
+    ew, ev = np.linalg.eig(A_mean.T)
+    hmm.var_init = np.abs(ev[:, np.argsort(ew)[::-1][0]])
+    hmm.obs_full = obs.copy()
+    mo = HSGD.MetaObs(50, 70)
+    hmm.cur_mo = HSGD.MetaObs(0, 20)
+    out = dict(obs=obs, mask=mask, init_tran=init_tran, var_init=hmm.var_init.copy(), mo=np.array([50, 70]))
+    pack_emit("init", hmm.var_emit, out)
+    out["pred_window"] = hmm.pred_logprob(mo)
+    out["full_var_x"] = hmm.full_local_update()
+    out["pred_full"] = hmm.pred_logprob_full()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s K=%d D=%d T=%d masked=%d  pred_window=%.6f pred_full=%.6f" % (
+        name, K, D, T_full, int(mask.sum()), out["pred_window"], out["pred_full"]))
+
+
+def util_case(name, seed):
+    """Host-side helpers of the reference run as shipped: make_mask (util.py:164-192, draws from the
+    global numpy RNG), make_mask_prediction (:195-207), munkres_match (:237-277, vendored Munkres)."""
+    import util as RU
+    from scipy.spatial import distance
+    rs = np.random.RandomState(seed)
+    K = 5
+    sts = rs.choice(K, size=600, p=[0.3, 0.25, 0.2, 0.15, 0.1])
+    out = dict(sts=sts)
+    np.random.seed(seed)
+    out["mask_a"] = RU.make_mask(sts, miss=0.2)
+    np.random.seed(seed + 1)
+    out["mask_b"] = RU.make_mask(sts, miss=0.1, left=150)
+    out["mask_pred"] = RU.make_mask_prediction(sts, miss=0.15)
+    perm_true = rs.permutation(K)
+    pred = perm_true[sts].copy()
+    flip = rs.rand(600) < 0.25
+    pred[flip] = rs.choice(K, size=int(flip.sum()))
+    match = RU.munkres_match(sts, pred, K)
+    out.update(pred=pred, match=match, hamming=distance.hamming(sts, match[pred]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s masks %d/%d/%d  hamming=%.4f" % (name, out["mask_a"].sum(), out["mask_b"].sum(),
+                                                  out["mask_pred"].sum(), out["hamming"]))
+
+
 if __name__ == "__main__":
     svi_case("svi_k3_d2_l5", seed=11, K=3, D=2, T_full=300, L=5, mb_sz=4, sep=0.6)
     svi_case("svi_k5_d3_l20_mask", seed=12, K=5, D=3, T_full=600, L=20, mb_sz=6, sep=0.5, miss=0.15)
@@ -385,3 +434,5 @@ if __name__ == "__main__":
     gen_case("gen_synthetic_k4", seed=8675309)
     adaptive_case("adaptive_k3_d2", seed=41, K=3, D=2, T_full=320, sep=0.6)
     ffbs_case("ffbs_k3_d2_t40", seed=51, K=3, D=2, T=40, sep=0.5)
+    pred_case("pred_k4_d3", seed=61, K=4, D=3, T_full=200, sep=0.8)
+    util_case("util_helpers", seed=71)

@@ -118,3 +118,23 @@ def test_gen_synthetic_variants_and_mmap(tmp_path):
     assert mm.shape == (250, 2) and sts.shape == (250,)
     chunks = list(GS.read_data_chunks(f, 250, 2, 100))
     assert len(chunks) == 2 and np.array_equal(chunks[1], np.asarray(mm[100:200]))
+
+
+def test_util_helpers_match_reference_fixture():
+    """make_mask / make_mask_prediction bit for bit (same draws from the global numpy RNG) and
+    munkres_match to the same Hamming distance as the reference's own util.py (fixture util_helpers,
+    made by running it; the reference solves the assignment with its vendored Munkres, here scipy)."""
+    from scipy.spatial import distance
+    from pysvihmm_b200 import util
+    from tests.helpers import load_golden
+    g = load_golden("util_helpers")
+    sts = g["sts"]
+    np.random.seed(71)
+    assert np.array_equal(util.make_mask(sts, miss=0.2), g["mask_a"])
+    np.random.seed(72)
+    assert np.array_equal(util.make_mask(sts, miss=0.1, left=150), g["mask_b"])
+    assert np.array_equal(util.make_mask_prediction(sts, miss=0.15), g["mask_pred"])
+    match = util.munkres_match(sts, g["pred"], 5)
+    assert sorted(match) == list(range(5))
+    assert np.isclose(distance.hamming(sts, match[g["pred"]]), float(g["hamming"]))
+    assert np.array_equal(match, g["match"])            # unique optimum on this input

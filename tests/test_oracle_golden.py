@@ -203,3 +203,19 @@ def test_ffbs_tables_match_reference_sampler():
         sd = np.sqrt(np.maximum(p * (1. - p), 1e-12) / n)
         assert np.all(np.abs(cnt / n - p) <= 5. * sd + 2. / n), float(np.max(np.abs(cnt / n - p) / sd))
     assert np.mean(marg.max(1) < 0.99) > 0.5            # not a vacuous (one-hot) case
+
+
+def test_pred_logprob_matches_reference():
+    """pred_logprob / full_local_update / pred_logprob_full of the reference (hmmsgd_metaobs.py:
+    1086-1205; fixture pred_k4_d3) against the oracle's restatements."""
+    g = load_golden("pred_k4_d3")
+    obs, mask, var_tran, var_init = g["obs"], g["mask"], g["init_tran"], g["var_init"]
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    i1, i2 = (int(v) for v in g["mo"])
+    r = O.local_update(obs[i1:i2 + 1][None], var_init, var_tran, emit)    # infer does not NaN the masked rows
+    got = O.pred_logprob(r["var_x"][0], obs[i1:i2 + 1], mask[i1:i2 + 1], emit)
+    np.testing.assert_allclose(got, float(g["pred_window"]), rtol=RT)
+    vx = O.full_local_update(obs, mask, var_init, var_tran, emit)
+    np.testing.assert_allclose(vx, g["full_var_x"], rtol=1e-9, atol=AT)
+    np.testing.assert_allclose(O.pred_logprob(vx, obs, mask, emit), float(g["pred_full"]), rtol=RT)
+    assert O.pred_logprob(vx, obs, np.zeros_like(mask), emit) is None
