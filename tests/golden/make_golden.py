@@ -416,6 +416,22 @@ def util_case(name, seed):
     pred[flip] = rs.choice(K, size=int(flip.sum()))
     match = RU.munkres_match(sts, pred, K)
     out.update(pred=pred, match=match, hamming=distance.hamming(sts, match[pred]))
+    # small-K exhaustive matcher, KL between Gaussians, NIW natural -> moment conversion, mvnrand draws
+    K2 = 4
+    t2 = rs.choice(K2, size=200)
+    p2 = rs.permutation(K2)[t2]
+    bad = rs.rand(200) < 0.3
+    p2[bad] = rs.choice(K2, size=int(bad.sum()))
+    out.update(t2=t2, p2=p2, match_seq=RU.match_state_seq(t2, p2, K2))
+    A0, A1 = rs.randn(3, 3), rs.randn(3, 3)
+    kl_in = dict(mu0=rs.randn(3), sig0=A0.dot(A0.T) + np.eye(3), mu1=rs.randn(3), sig1=A1.dot(A1.T) + 2 * np.eye(3))
+    out.update({"kl_" + k: v for k, v in kl_in.items()})
+    out["kl"] = RU.KL_gaussian(kl_in["mu0"], kl_in["sig0"], kl_in["mu1"], kl_in["sig1"])
+    e = RU.NIW_mf_natural_pars(kl_in["mu0"], kl_in["sig0"], 1.7, 6.5)
+    m = RU.NIW_nat2moment_pars(*e)
+    out.update(n2m_mu=m[0], n2m_sigma=m[1], n2m_kappa=float(m[2]), n2m_nu=float(m[3]))
+    np.random.seed(seed + 2)
+    out["mvn"] = RU.mvnrand(kl_in["mu1"], kl_in["sig1"], size=5)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print("%-22s masks %d/%d/%d  hamming=%.4f" % (name, out["mask_a"].sum(), out["mask_b"].sum(),
                                                   out["mask_pred"].sum(), out["hamming"]))

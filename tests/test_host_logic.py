@@ -138,3 +138,22 @@ def test_util_helpers_match_reference_fixture():
     assert sorted(match) == list(range(5))
     assert np.isclose(distance.hamming(sts, match[g["pred"]]), float(g["hamming"]))
     assert np.array_equal(match, g["match"])            # unique optimum on this input
+
+
+def test_util_diagnostics_match_reference_fixture():
+    """match_state_seq, KL_gaussian, NIW_nat2moment_pars and mvnrand against the reference's own
+    outputs (fixture util_helpers)."""
+    from pysvihmm_b200 import util
+    from tests.helpers import load_golden
+    g = load_golden("util_helpers")
+    assert np.array_equal(util.match_state_seq(g["t2"], g["p2"], 4), g["match_seq"])
+    kl = util.KL_gaussian(g["kl_mu0"], g["kl_sig0"], g["kl_mu1"], g["kl_sig1"])
+    assert np.isclose(kl, float(g["kl"]), rtol=1e-12)
+    with pytest.raises(RuntimeError):
+        util.KL_gaussian(np.zeros(2), np.eye(2), np.zeros(3), np.eye(3))
+    e = util.NIW_mf_natural_pars(g["kl_mu0"], g["kl_sig0"], 1.7, 6.5)
+    mu, sigma, kappa, nu = util.NIW_nat2moment_pars(*e)
+    assert np.allclose(mu, g["n2m_mu"], rtol=1e-13) and np.allclose(sigma, g["n2m_sigma"], rtol=1e-13)
+    assert np.isclose(kappa, float(g["n2m_kappa"])) and np.isclose(nu, float(g["n2m_nu"]))
+    np.random.seed(73)
+    assert np.allclose(util.mvnrand(g["kl_mu1"], g["kl_sig1"], size=5), g["mvn"], rtol=1e-13, atol=1e-15)
