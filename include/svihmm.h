@@ -235,6 +235,30 @@ int svihmm_batchsgd_update(svihmm_ctx* ctx, const double* stats, double lrate, v
 int svihmm_get_locals(svihmm_ctx* ctx, double* lliks, float* alpha, double* mx, float* cs,
                       double* logz, int loc, void* stream);
 
+/* nsteps global steps of hmmsgd_metaobs.VBHMM.infer (hmmsgd_metaobs.py:396-439) enqueued by ONE call:
+ * starts_all is nsteps*B window starts (device; the samplers :210-255 do not depend on the globals, so
+ * the minibatches of all steps are drawn up front); step i runs the E-step over its B windows of the
+ * resident series and the natural-gradient update with lrate = (it0 + i + tau)^-kappa (:351).
+ * var_x_out (B*T*K, may be NULL) and stats_out hold the LAST step's values on return.  peers != 0: the
+ * statistics are summed over the attached ranks inside the update (svihmm_global_update_peers). */
+int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B, int T, float* var_x_out,
+                   double* stats_out, unsigned flags, double tau, double kappa, int64_t it0, double bfact_A,
+                   double bfact_E, int peers, void* stream);
+
+/* Tuning knobs.  SVIHMM_TUNE_B16_MIN_B: smallest minibatch (windows per call) that takes the batched
+ * tensor-core path for K <= 16 diagonal models (sixteen windows per chain warp, batch16.cuh); smaller
+ * calls use the one-CTA-per-window pipelined kernel.  0 disables the batched path. */
+enum { SVIHMM_TUNE_B16_MIN_B = 1 };
+int svihmm_set_tuning(svihmm_ctx* ctx, int key, int value);
+
+/* Backward table of the last SVIHMM_KEEP_LOCALS E-step (self.lbeta, hmmsgd_metaobs.py:828-855 /
+ * hmmbase.py:297-320):
+ *   beta  B*T*K float32  normalised backward messages = softmax_k(self.lbeta[t]); beta[T-1] = 1
+ *   sb    B*T   float32  backward scale factors d_t (d_{T-1} = 1), so that
+ *                        self.lbeta[t,k] = log beta[t,k] + sum_{u=t}^{T-2} (log sb[u] + mx[u+1])
+ * Finite wherever the reference's table is (no reconstruction through the marginals). */
+int svihmm_get_locals_beta(svihmm_ctx* ctx, float* beta, float* sb, int loc, void* stream);
+
 /* Forward-filter backward-sampling of state paths for the window obs[start : start+T] (the reference's
  * native kernel hmm_fast.FFBS, hmm_fast.pyx:43-124, bound at hmmbase.py:410-411): forward filter with
  * initial weights psi(var_init+eps) - psi(sum+eps) and transition weights log(var_tran + eps) (:82-100),

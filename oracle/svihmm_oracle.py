@@ -148,7 +148,7 @@ def lliks_gmm(xw, emit):
 
 
 def gmm_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_emit, lrate, L, S=None,
-                       wrap=True):
+                       wrap=True, scaled=False):
     """svi_minibatch_step with GMM emissions (EXTENSION, see lliks_gmm).  Component (k,c) collects
     the NIW statistics (util.py:73-83) weighted by q[t,k] r[t,k,c]; its natural-gradient step is
     hmmsgd_metaobs.py:1048-1069 verbatim; the Dirichlet weights move like the transition rows
@@ -162,8 +162,11 @@ def gmm_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_e
     var_init = stationary_init(var_tran)
     mod_init, mod_tran = mod_params(var_init, var_tran)
     ll, r = lliks_gmm(xw, emit)
-    lalpha = forward_msgs(ll, mod_init, mod_tran)
-    lbeta = backward_msgs(ll, mod_tran)
+    if scaled:
+        lalpha, lbeta = messages_scaled(ll, mod_init, mod_tran)
+    else:
+        lalpha = forward_msgs(ll, mod_init, mod_tran)
+        lbeta = backward_msgs(ll, mod_tran)
     q = marginals(lalpha, lbeta)
     A_inter = np.zeros_like(var_tran)
     full = np.ndim(emit[0]['comps'][0]['sigma']) == 2
@@ -239,6 +242,40 @@ def backward_msgs(ll, mod_tran):
     return lbeta
 
 
+def messages_scaled(ll, mod_init, mod_tran):
+    """Scaled-domain float64 form of forward_msgs / backward_msgs / marginals (the algebra of
+    SURVEY.md section 10): alpha-hat_t = normalise((alpha-hat_{t-1} P~) * b_t) with P~ =
+    exp(mod_tran), b_t = exp(ll_t - max_k ll_t); beta-hat likewise; the log-domain tables follow as
+    lalpha[t] = log alpha-hat_t + sum_{s<=t}(log c_s + max ll_s), lbeta[t] = log beta-hat_t +
+    sum_{s>t}(log d_s + max ll_{s+1}).  One (B,K)x(K,K) product per step instead of B*K*K
+    logaddexp, for the BASELINE-size parity cases where the reference-shaped recursions above
+    take minutes; tests/test_oracle_golden.py holds it to them (and so to the reference-made
+    fixtures) at round-off.  Returns (lalpha, lbeta)."""
+    B, T, K = ll.shape
+    P = np.exp(mod_tran)
+    mx = np.max(ll, axis=-1)
+    b = np.exp(ll - mx[..., None])
+    ah = np.empty((B, T, K)); lc = np.empty((B, T))
+    a = np.exp(mod_init)[None] * b[:, 0]
+    for t in range(T):
+        if t:
+            a = ah[:, t - 1].dot(P) * b[:, t]
+        c = a.sum(-1)
+        ah[:, t] = a / c[:, None]
+        lc[:, t] = np.log(c) + mx[:, t]
+    bh = np.empty((B, T, K)); ld = np.zeros((B, T))
+    bh[:, T - 1] = 1.
+    for t in range(T - 2, -1, -1):
+        u = (bh[:, t + 1] * b[:, t + 1]).dot(P.T)
+        d = u.sum(-1)
+        bh[:, t] = u / d[:, None]
+        ld[:, t] = np.log(d) + mx[:, t + 1]
+    with np.errstate(divide='ignore'):
+        lalpha = np.log(ah) + np.cumsum(lc, axis=1)[..., None]
+        lbeta = np.log(bh) + np.cumsum(ld[:, ::-1], axis=1)[:, ::-1][..., None]
+    return lalpha, lbeta
+
+
 def marginals(lalpha, lbeta):
     """hmmsgd_metaobs.py:516-519 / hmmbase.py:226-229."""
     v = lalpha + lbeta
@@ -247,13 +284,17 @@ def marginals(lalpha, lbeta):
     return v / np.sum(v, axis=-1, keepdims=True)
 
 
-def local_update(xw, var_init, var_tran, emit):
+def local_update(xw, var_init, var_tran, emit, scaled=False):
     """hmmsgd_metaobs.py:487-519 on a batch of windows xw (B,T,D).
-    Returns dict(ll, lalpha, lbeta, var_x)."""
+    Returns dict(ll, lalpha, lbeta, var_x).  scaled=True: the same tables through
+    messages_scaled (large cases)."""
     mod_init, mod_tran = mod_params(var_init, var_tran)
     ll = lliks_gaussian(xw, emit)
-    lalpha = forward_msgs(ll, mod_init, mod_tran)
-    lbeta = backward_msgs(ll, mod_tran)
+    if scaled:
+        lalpha, lbeta = messages_scaled(ll, mod_init, mod_tran)
+    else:
+        lalpha = forward_msgs(ll, mod_init, mod_tran)
+        lbeta = backward_msgs(ll, mod_tran)
     return dict(ll=ll, lalpha=lalpha, lbeta=lbeta, var_x=marginals(lalpha, lbeta),
                 mod_init=mod_init, mod_tran=mod_tran)
 
@@ -374,7 +415,7 @@ def svi_global_update(var_tran, emit, prior_emit, A_inter, emit_inter, lrate, T_
 
 
 def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_emit,
-                       lrate, L, S=None, wrap=True, mask_ll=False, ada_G=None):
+                       lrate, L, S=None, wrap=True, mask_ll=False, ada_G=None, scaled=False):
     """One global step of hmmsgd_metaobs.VBHMM.infer (:396-439) given the window
     start indices `starts` (window b = obs[starts[b] : starts[b]+T]).
     Returns dict with var_x (B,T,K), A_inter, emit_inter, lb, var_tran_new, emit_new."""
@@ -391,7 +432,7 @@ def svi_minibatch_step(obs, mask, starts, T, var_tran, emit, prior_tran, prior_e
     if 'alpha' in emit[0]:
         return _svi_minibatch_step_cat(xw[..., 0], mw, var_init, var_tran, emit, prior_tran, prior_emit,
                                        lrate, L, S, T_full, wrap)
-    res = local_update(xw, var_init, var_tran, emit)
+    res = local_update(xw, var_init, var_tran, emit, scaled=scaled)
     A_inter = np.zeros_like(var_tran)
     emit_inter = None
     for b in range(len(starts)):

@@ -16,6 +16,7 @@
 #include "wide64.cuh"
 #include "ffbs.cuh"
 #include "dense.cuh"
+#include "batch16.cuh"
 
 static thread_local std::string g_err;
 
@@ -102,6 +103,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
   c->C = C; c->KE = K * C;
+  c->b16_min_B = 1;
   const size_t KE = (size_t)c->KE;
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : (kind == SVIHMM_EMIT_NIW_DIAG ? D : 0);
   c->OD = kind == SVIHMM_EMIT_CATEGORICAL ? 1 : D;
@@ -151,7 +153,8 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->stage_mask, c->stage_src, c->stage_starts, c->stage_stats, c->ll_ws, c->mx_ws, c->lt_ws, c->e_ws,
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
-                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
+                  c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->beta_ws, c->sb_ws,
+                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -387,7 +390,7 @@ static int ensure_ws(svihmm_ctx* c, int B, int T, bool need_r) {
 }
 
 template <int KP>
-static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStream_t st) {
+static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStream_t st, float* beta_out, float* sb_out) {
   const int G = 32 / KP;
   const int warps = (B + G - 1) / G;
   // few chains: one warp per CTA so that every chain gets a scheduler of its own
@@ -398,7 +401,7 @@ static void launch_fb(svihmm_ctx* c, int B, int T, float* q, float* r, cudaStrea
     k_forward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs);
     c->launches++; }
   { PhaseTimer pt(c, PH_BACKWARD, st);
-    k_backward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->b_ws, c->alpha_ws, q, r);
+    k_backward<KP><<<grid, wpb * 32, 0, st>>>(B, T, c->K, c->Pt, c->b_ws, c->alpha_ws, q, r, beta_out, sb_out);
     c->launches++; }
 }
 
@@ -708,7 +711,8 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
     // the feature rows fit one operand slot (k_emit_stats_dense), else by k_stats
     const int KPd = (K + 63) / 64 * 64, tiles = (B + DN_M - 1) / DN_M;
     const int NB = c->nfeat - K;
-    const bool tc_emit = !a.cat && NB <= ESD_NB && !getenv("SVIHMM_DENSE_FFMA_EMIT_STATS");
+    static const bool ffma_emit_stats = getenv("SVIHMM_DENSE_FFMA_EMIT_STATS") != nullptr;   // A/B switch, read once
+    const bool tc_emit = !a.cat && NB <= ESD_NB && !ffma_emit_stats;
     if (tc_emit) {
       const size_t needf = (size_t)tiles * T * NB * DN_M;
       if (needf > c->cap_dnf) {
@@ -759,6 +763,79 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
   return SVIHMM_OK;
 }
 
+// Batched tensor-core E-step (batch16.cuh): the diagonal model with K <= 16, D <= 16; sixteen windows
+// per chain warp, so it is the path for minibatches (the pipelined one-CTA-per-window kernel remains for
+// callers that set the threshold above their B through svihmm_set_tuning).
+static bool b16_eligible(const svihmm_ctx* c, int B, unsigned flags) {
+  return c->b16_min_B > 0 && B >= c->b16_min_B && c->K <= 16 && c->C == 1 && c->kind == SVIHMM_EMIT_NIW_DIAG &&
+         c->D <= 16 && !(flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS));
+}
+
+static int estep_b16(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask, const int64_t* starts,
+                     int B, int T, float* var_x_out, double* stats_out, unsigned flags, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  const size_t rows = (size_t)B * T;
+  if (rows > c->cap_b16) {
+    void* olds[] = {c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx};
+    for (void* p : olds) if (p) CU(cudaFree(p));
+    c->b16_b = c->b16_a = c->b16_c = nullptr; c->b16_E = nullptr; c->b16_mx = nullptr; c->cap_b16 = 0;
+    CU(dalloc(&c->b16_b, rows * B16_KS)); CU(dalloc(&c->b16_a, rows * B16_KS)); CU(dalloc(&c->b16_c, rows * B16_KS));
+    CU(dalloc(&c->b16_E, rows)); CU(dalloc(&c->b16_mx, rows));
+    c->cap_b16 = rows;
+  }
+  if ((size_t)B > c->cap_B) {
+    if (c->seq_ws) CU(cudaFree(c->seq_ws));
+    c->seq_ws = nullptr; c->cap_B = 0;
+    CU(dalloc(&c->seq_ws, 2 * (size_t)B));
+    c->cap_B = B;
+  }
+  B16Args a;
+  a.B = B; a.T = T; a.K = K; a.D = D;
+  a.wrap = (flags & SVIHMM_WRAP) ? 1 : 0; a.add_prior = (flags & SVIHMM_ADD_PRIOR) ? 1 : 0;
+  a.mask_ll = (flags & SVIHMM_MASK_LL) ? 1 : 0;
+  a.obs = obs; a.dtype = dtype; a.mask = mask; a.starts = starts;
+  a.P = c->Pt; a.PT = c->PtT; a.pi0 = c->pi0; a.par2 = c->par2; a.ckp = c->ckp; a.prior_tran = c->prior_tran;
+  a.bt = c->b16_b; a.at = c->b16_a; a.ct = c->b16_c; a.Et = c->b16_E; a.mx = c->b16_mx;
+  a.var_x_out = var_x_out; a.stats_out = stats_out; a.seq = c->seq_ws;
+  a.o_n = (size_t)K * K; a.o_sx = a.o_n + K; a.o_sxx = a.o_sx + (size_t)K * D;
+  a.o_q0 = a.o_sxx + (size_t)K * c->DD; a.o_tail = a.o_q0 + K; a.slen = c->slen;
+  static const bool dbg = getenv("SVIHMM_B16_DBG") != nullptr;
+#define B16_DBG(what) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); \
+    fprintf(stderr, "[b16 dbg] %s done: %s (B=%d T=%d K=%d D=%d)\n", what, cudaGetErrorString(e_), B, T, K, D); fflush(stderr); } } while (0)
+  {
+    PhaseTimer pt(c, PH_EMIT, st);
+    const unsigned grid = (unsigned)std::min<size_t>((rows + 255) / 256, 148 * 16);
+    const int KPe = K <= 4 ? 4 : (K <= 8 ? 8 : 16);
+    const size_t smem = (size_t)(2 * KPe * D + KPe) * sizeof(double);
+    if (KPe == 4) k_b16_emit<4><<<grid, 256, smem, st>>>(a);
+    else if (KPe == 8) k_b16_emit<8><<<grid, 256, smem, st>>>(a);
+    else k_b16_emit<16><<<grid, 256, smem, st>>>(a);
+    LAUNCHED(c);
+  }
+  B16_DBG("emit");
+  {
+    PhaseTimer pt(c, PH_FORWARD, st);
+    const int ngroups = (B + 15) / 16, nwarps = 2 * ngroups;
+    // few chain warps: one per CTA so that each has an SM (scheduler, tensor pipe) to itself
+    const int wpb = nwarps <= 148 ? 1 : 4;
+    k_b16_chain<<<(nwarps + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, ngroups);
+    LAUNCHED(c);
+  }
+  B16_DBG("chain");
+  {
+    PhaseTimer pt(c, PH_STATS, st);
+    const int64_t nunits = (int64_t)B * ((T + 7) / 8);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(2 * 148, (nunits + 7) / 8));
+    if (D <= 8) k_b16_post<3><<<grid, 256, 0, st>>>(a);
+    else k_b16_post<5><<<grid, 256, 0, st>>>(a);
+    LAUNCHED(c);
+  }
+  B16_DBG("post");
+#undef B16_DBG
+  c->last_B = B; c->last_T = T; c->last_fused = 1;
+  return SVIHMM_OK;
+}
+
 static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                       const int64_t* starts, int B, int T, float* var_x_out, double* stats_out,
                       unsigned flags, cudaStream_t st, int trim = 0) {
@@ -768,6 +845,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   if (trim > 0 && xi) return fail(SVIHMM_EUNSUPPORTED, "SVIHMM_EXACT_XI with buffered windows");
   size_t fsmem = 0;
   if (trim > 0) {}    // buffered windows: per-phase kernels (the statistics see the compacted inner rows)
+  else if (b16_eligible(c, B, flags))
+    return estep_b16(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, st);
   else if (pipe_eligible(c, T, flags, &fsmem))
     return estep_fused(c, obs, dtype, mask, starts, B, T, var_x_out, stats_out, flags, fsmem, st, true);
   else if (fused_eligible(c, T, flags, &fsmem))
@@ -894,7 +973,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     const int KPd = (K + 63) / 64 * 64;
     const size_t smem = (size_t)DN_M * KPd * 2 + (size_t)KPd * KPd * 2 + 1024;
     const int tiles = (B + DN_M - 1) / DN_M;
-    const bool tc_tran = trim == 0 && !mix && !getenv("SVIHMM_DENSE_FFMA_STATS");   // transition statistic on tcgen05
+    static const bool ffma_tran_stats = getenv("SVIHMM_DENSE_FFMA_STATS") != nullptr;         // A/B switch, read once
+    const bool tc_tran = trim == 0 && !mix && !ffma_tran_stats;   // transition statistic on tcgen05
     const size_t need = (size_t)tiles * DN_M * T * K;
     if (need > c->cap_dn) {
       void* olds[] = {c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16};
@@ -925,13 +1005,26 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     return stats_generic_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, false, st,
                                tc_tran ? c->dn_q16 : nullptr);
   }
+  // KEEP_LOCALS: also keep the normalised backward messages + their scale factors (self.lbeta)
+  float* beta_out = nullptr; float* sb_out = nullptr;
+  c->last_beta = 0;
+  if (flags & SVIHMM_KEEP_LOCALS) {
+    if ((size_t)R > c->cap_beta) {
+      if (c->beta_ws) CU(cudaFree(c->beta_ws));
+      if (c->sb_ws) CU(cudaFree(c->sb_ws));
+      c->beta_ws = c->sb_ws = nullptr; c->cap_beta = 0;
+      CU(dalloc(&c->beta_ws, (size_t)R * K)); CU(dalloc(&c->sb_ws, (size_t)R));
+      c->cap_beta = (size_t)R;
+    }
+    beta_out = c->beta_ws; sb_out = c->sb_ws; c->last_beta = 1;
+  }
   if (K <= 32) {
     switch (c->KP) {
-      case 2: launch_fb<2>(c, B, T, q, r, st); break;
-      case 4: launch_fb<4>(c, B, T, q, r, st); break;
-      case 8: launch_fb<8>(c, B, T, q, r, st); break;
-      case 16: launch_fb<16>(c, B, T, q, r, st); break;
-      default: launch_fb<32>(c, B, T, q, r, st); break;
+      case 2: launch_fb<2>(c, B, T, q, r, st, beta_out, sb_out); break;
+      case 4: launch_fb<4>(c, B, T, q, r, st, beta_out, sb_out); break;
+      case 8: launch_fb<8>(c, B, T, q, r, st, beta_out, sb_out); break;
+      case 16: launch_fb<16>(c, B, T, q, r, st, beta_out, sb_out); break;
+      default: launch_fb<32>(c, B, T, q, r, st, beta_out, sb_out); break;
     }
   } else {
     const int KT = (K + 31) / 32 * 32;
@@ -946,7 +1039,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       k_forward_wide<<<B, KT, smem, st>>>(B, T, K, c->Pt, c->pi0, c->b_ws, c->alpha_ws, cs, p_smem);
       c->launches++; }
     { PhaseTimer pt(c, PH_BACKWARD, st);
-      k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r, p_smem);
+      k_backward_wide<<<B, KT, smem, st>>>(B, T, K, c->PtT, c->b_ws, c->alpha_ws, q, r, p_smem, beta_out, sb_out);
       c->launches++; }
   }
   CU(cudaGetLastError());
@@ -1435,4 +1528,53 @@ extern "C" int svihmm_get_locals(svihmm_ctx* c, double* lliks, float* alpha, dou
   if (logz) CU(cudaMemcpyAsync(logz, c->seq_ws, sizeof(double) * 2 * c->last_B, kd, st));
   if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
   return SVIHMM_OK;
+}
+
+/* Normalised backward messages of the last KEEP_LOCALS E-step (see include/svihmm.h). */
+extern "C" int svihmm_get_locals_beta(svihmm_ctx* c, float* beta, float* sb, int loc, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  if (c->last_B == 0 || c->last_fused || !c->last_beta)
+    return fail(SVIHMM_ESTATE, "beta/sb need the last E-step to run with SVIHMM_KEEP_LOCALS");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const cudaMemcpyKind kd = loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  const size_t bt = (size_t)c->last_B * c->last_T;
+  if (beta) CU(cudaMemcpyAsync(beta, c->beta_ws, sizeof(float) * bt * c->K, kd, st));
+  if (sb) CU(cudaMemcpyAsync(sb, c->sb_ws, sizeof(float) * bt, kd, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+/* nsteps global steps of hmmsgd_metaobs.VBHMM.infer (:396-439) in one call: the minibatches are
+ * given up front (the samplers do not depend on the globals), every step = E-step over its B windows +
+ * natural-gradient update with lrate = (it0 + i + tau)^-kappa (:351); with peers != 0 the statistics
+ * are summed over the ranks inside the update kernel (svihmm_global_update_peers). */
+extern "C" int svihmm_svi_run(svihmm_ctx* c, const int64_t* starts_all, int nsteps, int B, int T,
+                              float* var_x_out, double* stats_out, unsigned flags, double tau, double kappa,
+                              int64_t it0, double bA, double bE, int peers, void* stream) {
+  int rc = check_estep_args(c, starts_all, B, T, stats_out, flags);
+  if (rc) return rc;
+  if (nsteps < 1) return fail(SVIHMM_EINVAL, "nsteps = %d", nsteps);
+  if (!c->obs) return fail(SVIHMM_ESTATE, "svihmm_set_series has not been called");
+  if (!c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  if (T > c->T_full) return fail(SVIHMM_EINVAL, "T (%d) exceeds the series length (%lld)", T, (long long)c->T_full);
+  if (peers && c->comm_world < 2) return fail(SVIHMM_ESTATE, "svihmm_comm_attach has not been called with world >= 2");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < nsteps; ++i) {
+    if ((rc = estep_impl(c, c->obs, c->obs_dtype, c->mask, starts_all + (size_t)i * B, B, T, var_x_out, stats_out,
+                         flags, st))) return rc;
+    const double lrate = pow((double)(it0 + i) + tau, -kappa);
+    if ((rc = run_global(c, GM_SVI, stats_out, lrate, bA, bE, st, peers != 0))) return rc;
+  }
+  return SVIHMM_OK;
+}
+
+/* Tuning knobs (see include/svihmm.h). */
+extern "C" int svihmm_set_tuning(svihmm_ctx* c, int key, int value) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  switch (key) {
+    case SVIHMM_TUNE_B16_MIN_B: c->b16_min_B = value; return SVIHMM_OK;
+    default: return fail(SVIHMM_EINVAL, "unknown tuning key %d", key);
+  }
 }

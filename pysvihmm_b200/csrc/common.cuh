@@ -62,7 +62,10 @@ struct svihmm_ctx {
   int* e_ws;
   float *dn_b, *dn_a, *dn_r; int* dn_e; uint16_t *dn_q16, *dn_fhi, *dn_flo; size_t cap_dn, cap_dnf;   // dense (tcgen05) recursion tables, tile layout
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
+  float *beta_ws, *sb_ws; size_t cap_beta; int last_beta;   // KEEP_LOCALS: normalised backward messages + scale factors
   size_t hostq_cap;
+  // batched tensor-core path for K <= 16 (batch16.cuh): (rows, 16) float tables, exponents, row maxima
+  float *b16_b, *b16_a, *b16_c; int* b16_E; double* b16_mx; size_t cap_b16; int b16_min_B;
   int last_B, last_T, last_fused;
   int max_smem_optin, fused_attr_set;
   int64_t launches;

@@ -77,7 +77,8 @@ k_forward(int B, int T, int K, const float* __restrict__ Pt, const float* __rest
 template <int KP>
 __global__ void __launch_bounds__(128)
 k_backward(int B, int T, int K, const float* __restrict__ Pt, const float* __restrict__ b,
-           const float* __restrict__ alpha, float* __restrict__ q, float* __restrict__ r_out) {
+           const float* __restrict__ alpha, float* __restrict__ q, float* __restrict__ r_out,
+           float* __restrict__ beta_out = nullptr, float* __restrict__ sb_out = nullptr) {
   constexpr int G = 32 / KP;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -96,6 +97,11 @@ k_backward(int B, int T, int K, const float* __restrict__ Pt, const float* __res
   float* rp = r_out ? r_out + base : nullptr;
   float beta = act ? 1.f : 0.f;
   if (act) qp[(size_t)(T - 1) * K] = ap[(size_t)(T - 1) * K];
+  // KEEP_LOCALS: the normalised backward messages and their scale factors (self.lbeta, :828-855)
+  float* bop = beta_out ? beta_out + base : nullptr;
+  float* sbp = sb_out ? sb_out + (size_t)s * T : nullptr;
+  if (bop && act) bop[(size_t)(T - 1) * K] = 1.f;
+  if (sbp && i == 0) sbp[T - 1] = 1.f;
   for (int t0 = T - 2; t0 >= 0; t0 -= FB_U) {
     float bb[FB_U], aa[FB_U];
 #pragma unroll
@@ -126,7 +132,9 @@ k_backward(int B, int T, int K, const float* __restrict__ Pt, const float* __res
         if (act) {
           qp[(size_t)t * K] = qv * (1.f / S2);
           if (rp) rp[(size_t)(t + 1) * K] = uu * (1.f / S2);
+          if (bop) bop[(size_t)t * K] = beta;
         }
+        if (sbp && i == 0) sbp[t] = S1;
       }
     }
   }
@@ -197,7 +205,8 @@ __global__ void k_forward_wide(int B, int T, int K, const float* __restrict__ Pt
 // dynamic smem as k_forward_wide; PtT is the transposed transition matrix
 __global__ void k_backward_wide(int B, int T, int K, const float* __restrict__ PtT,
                                 const float* __restrict__ b, const float* __restrict__ alpha,
-                                float* __restrict__ q, float* __restrict__ r_out, int p_smem) {
+                                float* __restrict__ q, float* __restrict__ r_out, int p_smem,
+                                float* __restrict__ beta_out = nullptr, float* __restrict__ sb_out = nullptr) {
   extern __shared__ float smf[];
   const int KT = blockDim.x, nw = KT >> 5, i = threadIdx.x, s = blockIdx.x;
   float* ub = smf + (p_smem ? K * K : 0); float* red = ub + 2 * KT;
@@ -209,6 +218,10 @@ __global__ void k_backward_wide(int B, int T, int K, const float* __restrict__ P
   float* qp = q + base; float* rp = r_out ? r_out + base : nullptr;
   float beta = act ? 1.f : 0.f;
   if (act) qp[(size_t)(T - 1) * K] = ap[(size_t)(T - 1) * K];
+  float* bop = beta_out ? beta_out + base : nullptr;
+  float* sbp = sb_out ? sb_out + (size_t)s * T : nullptr;
+  if (bop && act) bop[(size_t)(T - 1) * K] = 1.f;
+  if (sbp && i == 0) sbp[T - 1] = 1.f;
   for (int t = T - 2; t >= 0; --t) {
     float* uv = ub + (t & 1) * KT;
     const float uu = act ? beta * bp[(size_t)(t + 1) * K] : 0.f;
@@ -234,7 +247,9 @@ __global__ void k_backward_wide(int B, int T, int K, const float* __restrict__ P
     if (act) {
       qp[(size_t)t * K] = qv * (1.f / S2);
       if (rp) rp[(size_t)(t + 1) * K] = uu * (1.f / S2);
+      if (bop) bop[(size_t)t * K] = beta;
     }
+    if (sbp && i == 0) sbp[t] = S1;
   }
   if (rp && act) rp[0] = 0.f;
 }

@@ -177,8 +177,14 @@ class EStepEngine(object):
         keep_locals: keep the lliks/alpha/scale tables for get_locals (unfused kernels)."""
         if keep_locals:
             flags = int(flags) | L.KEEP_LOCALS
-        if not isinstance(starts, torch.Tensor):
-            starts = torch.as_tensor(np.asarray(starts, dtype=np.int64))
+        if not (isinstance(starts, torch.Tensor) and starts.is_cuda):
+            # host-side window starts are validated here (the kernels index the resident series
+            # unchecked); device-resident starts are the caller's responsibility (no sync on the hot path)
+            sh = np.asarray(starts.numpy() if isinstance(starts, torch.Tensor) else starts, dtype=np.int64).ravel()
+            if self.T_full is not None and sh.size and (sh.min() < 0 or sh.max() + int(T) > self.T_full):
+                raise L.SvihmmError("window [%d, +%d) outside the series of length %d" % (
+                    int(sh.min() if sh.min() < 0 else sh.max()), int(T), self.T_full))
+            starts = torch.from_numpy(np.ascontiguousarray(sh))
         starts = starts.to(device=self.device, dtype=torch.int64).contiguous()
         B = int(starts.numel())
         if var_x is None and want_var_x:
@@ -273,7 +279,25 @@ class EStepEngine(object):
         mx = np.empty((B, T)); cs = np.empty((B, T), dtype=np.float32)
         L.check(self.lib.svihmm_get_locals(self._h, _ptr(ll), _ptr(al), _ptr(mx), _ptr(cs), _ptr(lz),
                                            L.LOC_HOST, self._stream()))
-        return dict(lliks=ll, alpha=al, mx=mx, cs=cs, logZ=lz[:, 0], lb_q4=lz[:, 1])
+        be = np.empty((B, T, self.K), dtype=np.float32); sb = np.empty((B, T), dtype=np.float32)
+        L.check(self.lib.svihmm_get_locals_beta(self._h, _ptr(be), _ptr(sb), L.LOC_HOST, self._stream()))
+        return dict(lliks=ll, alpha=al, mx=mx, cs=cs, beta=be, sb=sb, logZ=lz[:, 0], lb_q4=lz[:, 1])
+
+    @staticmethod
+    def log_tables(loc, b=0):
+        """The reference's unnormalised log-domain tables of window b from the scaled ones:
+        lalpha[t] = log alpha[t] + sum_{u<=t}(log cs[u] + mx[u])          (hmmsgd_metaobs.py:775-803)
+        lbeta[t]  = log beta[t]  + sum_{u=t}^{T-2}(log sb[u] + mx[u+1])   (:828-855)
+        (float64 sums of the float32 scale factors; an entry whose normalised message is below the
+        float32 range comes back as -inf)."""
+        with np.errstate(divide='ignore'):
+            cum = np.cumsum(np.log(loc["cs"][b].astype(np.float64)) + loc["mx"][b])
+            lalpha = np.log(loc["alpha"][b].astype(np.float64)) + cum[:, None]
+            d = np.log(loc["sb"][b].astype(np.float64))
+            d[:-1] += loc["mx"][b][1:]
+            d[-1] = 0.
+            lbeta = np.log(loc["beta"][b].astype(np.float64)) + np.cumsum(d[::-1])[::-1][:, None]
+        return lalpha, lbeta
 
     def ffbs(self, var_init, T=None, start=0, nsamples=1, seed=0):
         """hmm_fast.FFBS (hmm_fast.pyx:43-124): nsamples state paths (nsamples, T) int32 for the window
@@ -284,6 +308,27 @@ class EStepEngine(object):
         L.check(self.lib.svihmm_ffbs(self._h, _ptr(vi), int(start), T, int(nsamples), int(seed), _ptr(z),
                                      L.LOC_HOST, self._stream()))
         return z
+
+    def svi_run(self, starts_all, T, tau, kappa, it0, bfact_A, bfact_E, flags=0, var_x=None, stats=None,
+                peers=False):
+        """nsteps global steps (E-step + natural-gradient update, hmmsgd_metaobs.py:396-439) enqueued by
+        one C call.  starts_all: (nsteps, B) int64 CUDA tensor of window starts, drawn up front.
+        Returns the stats tensor of the last step (device)."""
+        assert isinstance(starts_all, torch.Tensor) and starts_all.is_cuda and starts_all.dtype == torch.int64
+        starts_all = starts_all.contiguous()
+        nsteps, B = int(starts_all.shape[0]), int(starts_all.shape[1])
+        if stats is None:
+            stats = self.new_stats()
+        L.check(self.lib.svihmm_svi_run(self._h, _ptr(starts_all), nsteps, B, int(T), _ptr(var_x), _ptr(stats),
+                                        int(flags), float(tau), float(kappa), int(it0), float(bfact_A),
+                                        float(bfact_E), int(bool(peers)), self._stream()))
+        self._keep["starts_all"] = starts_all
+        return stats
+
+    def set_tuning(self, key, value):
+        """svihmm_set_tuning (e.g. L.TUNE_B16_MIN_B: minibatch size from which the batched tensor-core
+        path for K <= 16 is used; 0 = never)."""
+        L.check(self.lib.svihmm_set_tuning(self._h, int(key), int(value)))
 
     def launch_count(self):
         return int(self.lib.svihmm_launch_count(self._h))

@@ -215,11 +215,7 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
         loc = eng.get_locals(B, T)
         self.var_x = vx[B - 1].double().cpu().numpy()
         self.lliks = loc["lliks"][B - 1]
-        with np.errstate(divide='ignore'):
-            cum = np.cumsum(np.log(loc["cs"][B - 1].astype(np.float64)) + loc["mx"][B - 1])
-            self.lalpha = np.log(loc["alpha"][B - 1].astype(np.float64)) + cum[:, None]
-            # alpha_t(k) beta_t(k) sums to Z for every t  =>  lbeta = log q + logZ - lalpha
-            self.lbeta = np.log(self.var_x) + loc["logZ"][B - 1] - self.lalpha
+        self.lalpha, self.lbeta = eng.log_tables(loc, B - 1)
         self.mod_init = digamma(self.var_init + eps) - digamma(np.sum(self.var_init) + eps)
         tran_sum = np.sum(self.var_tran, axis=1)
         self.mod_tran = digamma(self.var_tran + eps) - digamma(tran_sum[:, None] + eps)

@@ -14,7 +14,7 @@ import numpy.random as npr
 
 from . import _lib as L
 from .hmmbase import VariationalHMMBase
-from .sharding import allreduce_stats, dist_or_none as _dist, shard_starts
+from .sharding import allreduce_stats, broadcast_minibatch, dist_or_none as _dist, shard_starts
 
 eps = 1e-9
 tau0 = 1.
@@ -84,6 +84,7 @@ class VBHMM(VariationalHMMBase):
         if metaobs_half is not None and metaobs_half < 1:
             raise RuntimeError("metaobs (%d) must be >= 1." % (metaobs_half,))
         self.metaobs_half = metaobs_half
+        self._ctor_half = metaobs_half
         self.mb_sz = mb_sz
         self.cur_mo = None
         self.batchfactor = 1.
@@ -148,10 +149,19 @@ class VBHMM(VariationalHMMBase):
         eng = self._ensure_engine()
         starts = np.array([m.i1 for m in minibatch], dtype=np.int64)
         T = int(minibatch[0].i2 - minibatch[0].i1 + 1)
+        self._check_windows(starts, T)
         dist = _dist()
         if dist is not None:
+            # every rank must work on the SAME minibatch and window length (a rank-local RNG draw in
+            # select_L / the sampler would silently de-synchronise the replicas): rank 0's wins
+            starts, T = broadcast_minibatch(starts, T, dist, eng.device)
             starts = shard_starts(starts, dist.get_rank(), dist.get_world_size())
-        vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x, trim=trim)
+        if len(starts) == 0:
+            # more ranks than windows (e.g. mb_sz = 1): this rank contributes zero statistics but
+            # still takes part in the sum over ranks below
+            vx, stats = None, eng.new_stats().zero_()
+        else:
+            vx, stats = eng.estep(starts, T, flags=self._flags(), want_var_x=want_var_x, trim=trim)
         if dist is not None and self.peer_allreduce and dist.get_backend() == "nccl":
             if self._px is None:            # the sum over ranks happens inside global_update (P2P over NVLink)
                 from .sharding import PeerExchange
@@ -161,7 +171,16 @@ class VBHMM(VariationalHMMBase):
             allreduce_stats(stats, dist)    # one sum all-reduce of the packed statistics per step
         self._var_x_batch = vx
         self._last_B, self._last_T = len(starts), T
+        self._last_B_global = len(minibatch)
         return stats
+
+    def _check_windows(self, starts, T):
+        """Window starts handed to the device are validated on the host (the kernels index the
+        resident series without bounds checks)."""
+        starts = np.asarray(starts, dtype=np.int64)
+        if T < 1 or T > self.T or (starts.size and (starts.min() < 0 or starts.max() + T > self.T)):
+            raise RuntimeError("meta-observation outside the series: starts in [%d, %d], length %d, T = %d" % (
+                int(starts.min()) if starts.size else 0, int(starts.max()) if starts.size else 0, T, self.T))
 
     def infer(self, adaptive=False, perIter=10, epsilon=1e-6, minHalfL=1, avgResidual=False,
               Lincrement=1, Lcutoff=1000):
@@ -178,8 +197,9 @@ class VBHMM(VariationalHMMBase):
         if (Lh is None or adaptive) and growBuffer:
             raise RuntimeError("Cannot specify both adaptive and buffer simultaneously!")   # :344
         eng = self._ensure_engine()
-        if self.adagrad:
-            eng.set_adagrad(True)
+        if self.adagrad and not getattr(self, "_ada_started", False):
+            eng.set_adagrad(True)          # ada_G = ones once (constructor, :183); kept across infer() calls
+            self._ada_started = True
         track_init = adaptive or Lh is None or growBuffer       # select_* read the previous var_init
         for it in range(maxit):
             start_time = time.time()
@@ -187,7 +207,11 @@ class VBHMM(VariationalHMMBase):
             if Lh is None or (adaptive and it % perIter == 0):            # :354-369
                 Lh = self.select_L(mb_sz, epsilon=epsilon, minHalfL=minHalfL, avgResidual=avgResidual,
                                    Lincrement=Lincrement, Lcutoff=Lcutoff)
-                self.metaobs_half = Lh        # global_update scales by the current L (:1033,1048)
+                # L stays local as in the reference: global_update keeps scaling with the constructor's
+                # metaobs_half (:340,355,1021).  metaobs_half=None (an extension: the reference's
+                # constructor raises for it) has no such value, so there the selected L is used.
+                if self._ctor_half is None:
+                    self.metaobs_half = Lh
                 self._resize_locals(2 * Lh + 1)
                 miniL = Lh
             if growBuffer and it % perIter == 0:                          # :372-393
@@ -234,6 +258,7 @@ class VBHMM(VariationalHMMBase):
         instead of the reference's per-index get_local_messages calls (:663-700)."""
         eng = self._ensure_engine()
         inds = np.asarray(inds, dtype=np.int64)
+        self._check_windows(inds - halflength, 2 * halflength + 1)
         vx, _ = eng.estep(inds - halflength, 2 * halflength + 1, flags=0)
         return vx.double().cpu().numpy()
 
@@ -390,19 +415,44 @@ class VBHMM(VariationalHMMBase):
         if isinstance(A_inter, torch.Tensor):
             stats = A_inter
         else:
-            K, D = self.K, self.D
-            parts = [np.asarray(A_inter, dtype=float).ravel(),
-                     np.array([e[1] for e in emit_inter], dtype=float),
-                     np.concatenate([np.asarray(e[0], dtype=float).ravel() for e in emit_inter]),
-                     np.concatenate([np.asarray(e[2], dtype=float).ravel() for e in emit_inter]),
-                     np.zeros(K + 4)]
-            stats = torch.from_numpy(np.concatenate(parts)).to(eng.device)
+            stats = torch.from_numpy(self._pack_inter(A_inter, emit_inter)).to(eng.device)
+            if stats.numel() != eng.slen:
+                raise RuntimeError("packed statistics have %d entries, the engine expects %d" % (
+                    stats.numel(), eng.slen))
         if self._px is not None and isinstance(A_inter, torch.Tensor):
             self._px.global_update(stats, self.lrate, bfact_A, bfact_E)
             self._px.reduced_stats(stats)   # callers read the all-reduced statistics from `stats`
         else:
             eng.global_update(stats, self.lrate, bfact_A, bfact_E)
         self._host_stale = True
+
+    def _pack_inter(self, A_inter, emit_inter):
+        """The reference's (A_inter, emit_inter) pair -> packed statistics of include/svihmm.h
+        [A | n | sx | sxx | q0 | logZ, Q4, B, 0].  A_inter already holds the per-window prior terms
+        (quirk Q5), so the tail carries the number of windows they stand for only where the device
+        update needs it (Categorical: alpha_0 - 1 per window, :925-926)."""
+        K = self.K
+        A = np.asarray(A_inter, dtype=float).ravel()
+        if A.size != K * K:
+            raise RuntimeError("A_inter must be (K, K)")
+        tail = np.zeros(K + 4)
+        if self.emission_kind == "categorical":
+            # emit_inter[k] = sum over windows of (alphav_0 + counts - 1)  (:925-926)
+            nwin = float(getattr(self, "_last_B_global", self.mb_sz))
+            a0 = np.array([np.asarray(self.prior_emit[k].alphav_0, dtype=float) for k in range(K)])
+            counts = np.array([np.asarray(e, dtype=float).ravel() for e in emit_inter]) - nwin * (a0 - 1.)
+            tail[K + 2] = nwin
+            return np.concatenate([A, counts.sum(1), counts.ravel(), tail])
+        if self.emission_kind not in ("niw_full", "niw_diag"):
+            raise RuntimeError("global_update(A_inter, emit_inter): unsupported emission kind %r" % (
+                self.emission_kind,))
+        KE = len(emit_inter)
+        if KE != self._ensure_engine().KE:
+            raise RuntimeError("emit_inter has %d entries, expected %d" % (KE, self._ensure_engine().KE))
+        return np.concatenate([A, np.array([float(e[1]) for e in emit_inter]),
+                               np.concatenate([np.asarray(e[0], dtype=float).ravel() for e in emit_inter]),
+                               np.concatenate([np.asarray(e[2], dtype=float).ravel() for e in emit_inter]),
+                               tail])
 
     def pred_logprob(self, metaobs=None):
         """hmmsgd_metaobs.py:1086-1119: mean over the masked rows of the meta-observation of

@@ -22,6 +22,23 @@ def shard_starts(starts, rank, world):
     return np.ascontiguousarray(np.asarray(starts, dtype=np.int64)[rank::world])
 
 
+def broadcast_minibatch(starts, T, dist, device):
+    """Rank 0's window starts and window length on every rank (one small broadcast per step).  The
+    samplers draw from the process-local legacy numpy RNG; with different seeds (or seed=None) the
+    ranks would otherwise shard DIFFERENT minibatches and the replicated globals would drift apart."""
+    import torch
+    n = torch.tensor([len(starts), int(T)], dtype=torch.int64)
+    dev = device if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = n.to(dev)
+    dist.broadcast(n, src=0)
+    nb, T = int(n[0].item()), int(n[1].item())
+    buf = torch.zeros(nb, dtype=torch.int64, device=dev)
+    if dist.get_rank() == 0:
+        buf.copy_(torch.as_tensor(np.asarray(starts, dtype=np.int64)))
+    dist.broadcast(buf, src=0)
+    return buf.cpu().numpy(), T
+
+
 def allreduce_stats(stats, dist=None):
     """Sum the packed statistics tensor (include/svihmm.h layout) over ranks, in place."""
     dist = dist_or_none() if dist is None else dist

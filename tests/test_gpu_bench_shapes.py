@@ -1,0 +1,186 @@
+"""Parity of exactly the code paths bench.py times, at the BASELINE shapes and dtypes, against the
+float64 oracle (scaled-domain form, held to the reference-made fixtures in test_oracle_golden).
+
+  c2  K16 D8 T512, float32 series, B = 256 and B > CTAs in flight   -> k_estep_pipe (vecx branch) /
+                                                                        the batched tensor-core path
+  c3  K64 D32 T1024 full covariance, float32 series, B = 64          -> wide64 kernels
+  c4  K256 D64 T256 B = 256, SVIHMM_BF16_DENSE                        -> tcgen05 recursion + statistics
+  c5  K32 x 4 components D16, T = 256 and T = 2048                    -> mixture path
+
+A float32 series is the benchmark's input: the oracle then sees obs.astype(float32).astype(float64),
+i.e. the SAME numbers, and the 1e-5 bound applies unchanged (tolerances as in test_gpu_parity).
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import frac_soft, make_random_problem, pack_emit_np
+from tests.test_gpu_parity import Q_ATOL, Q_RTOL, S_RTOL, assert_block, assert_q
+
+pytestmark = pytest.mark.gpu
+
+
+def _stats_from_q(q, obs, mask, starts, T, wrap, prior_tran, full):
+    """Summed minibatch statistics (Q1 product of marginals, Q2 wrap, Q5 prior per window;
+    hmmsgd_metaobs.py:873-904) from oracle marginals q (B,T,K), vectorised over the minibatch."""
+    B, _, K = q.shape
+    idx = np.asarray(starts)[:, None] + np.arange(T)[None]
+    x = obs[idx]
+    keep = ~(mask[idx].astype(bool)) & ~np.isnan(x).any(-1)
+    x = np.nan_to_num(x)
+    A = np.einsum("bti,btj->ij", q[:, :-1], q[:, 1:])
+    if wrap:
+        A += np.einsum("bi,bj->ij", q[:, -1], q[:, 0])
+        A += B * (prior_tran - 1.)
+    w = q * keep[..., None]
+    n = w.sum((0, 1))
+    sx = np.einsum("btk,btd->kd", w, x)
+    sxx = np.einsum("btk,bti,btj->kij", w, x, x) if full else np.einsum("btk,btd->kd", w, x * x)
+    return A, n, sx, sxx
+
+
+def _run_case(K, D, T, B, kind, dtype, flags_extra=0, q_check=None, seed_off=0, sep=0.4, miss=0.05,
+              q_abs=None, s_rtol=S_RTOL, lz_rtol=3e-6, onecta=False):
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    p = make_random_problem(seed=K * 1000 + T + seed_off, K=K, D=D, T_full=max(8 * T, 4000), kind=kind,
+                            miss=miss, sep=sep)
+    obs = p["obs"]
+    if dtype == "f32":
+        obs = obs.astype(np.float32).astype(np.float64)          # the numbers the engine is given
+    starts = np.random.RandomState(5).randint(0, obs.shape[0] - T + 1, B)
+    eng = EStepEngine(K, D, kind)
+    if onecta:                                  # the one-CTA-per-window kernels instead of the batched path
+        eng.set_tuning(L.TUNE_B16_MIN_B, 0)
+    eng.set_series(obs, p["mask"], dtype=dtype)
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    fl = L.WRAP | L.ADD_PRIOR | flags_extra
+    vx, stats = eng.estep(starts, T, flags=fl)
+    r = O.svi_minibatch_step(obs, p["mask"], starts, T, p["var_tran"], p["emit"], p["prior_tran"],
+                             p["prior_emit"], 0.37, max(T // 2, 1), wrap=True, scaled=True)
+    q = vx.cpu().numpy()
+    assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+    if q_abs is None:
+        assert_q(q, r["var_x"])
+    else:
+        assert np.isfinite(q).all() and float(np.max(np.abs(q - r["var_x"]))) < q_abs
+    s = eng.unpack_stats(stats)
+    A, n, sx, sxx = _stats_from_q(r["var_x"], obs, p["mask"], starts, T, True, p["prior_tran"],
+                                  kind == "niw_full")
+    assert_block(s["A"], A, s_rtol, "A")
+    assert_block(s["n"], n, s_rtol, "n")
+    assert_block(s["sx"], sx, s_rtol, "sx")
+    assert_block(s["sxx"], sxx, s_rtol, "sxx")
+    assert_block(s["q0"], r["var_x"][:, 0].sum(0), s_rtol, "q0")
+    np.testing.assert_allclose(s["logZ"], r["logZ"].sum(), rtol=lz_rtol)
+    np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=lz_rtol)
+    assert s["B"] == B
+    # the natural-gradient step from those statistics (hmmsgd_metaobs.py:1010-1069)
+    Lh, Tf = max(T // 2, 1), obs.shape[0]
+    eng.global_update(stats, 0.37, (Tf - 2 * Lh - 1) / (2. * Lh * B), (Tf - 2 * Lh - 1) / ((2. * Lh + 1.) * B))
+    vt, vi, em = eng.get_globals()
+    e = eng.unpack_emit(em)
+    g_rtol = max(s_rtol, S_RTOL)
+    assert_block(vt, r["var_tran_new"], g_rtol, "var_tran")
+    for key in ("mu", "sigma", "kappa", "nu"):
+        ref = np.array([np.broadcast_to(x[key], e[key][0].shape) for x in r["emit_new"]])
+        assert_block(e[key], ref, g_rtol, key)
+    eng.close()
+
+
+@pytest.mark.parametrize("onecta", [False, True])
+@pytest.mark.parametrize("B", [256, 700, 5000])
+def test_c2_bench_shape_float32_series(B, onecta):
+    """BASELINE configs[1] as bench.py runs it: float32 series (128-bit vector loads of the window
+    rows), B = 256 windows, B = 700 > the 296 CTAs the GPU holds at once and B = 5000 (several waves
+    accumulating into the same statistics; the batched path's float32 -> float64 accumulator flushes),
+    through the batched tensor-core path (the default) and the one-CTA-per-window pipelined kernel."""
+    _run_case(16, 8, 512, B, "niw_diag", "f32", onecta=onecta)
+
+
+@pytest.mark.parametrize("onecta", [False, True])
+def test_c2_bench_shape_float64_series(onecta):
+    _run_case(16, 8, 512, 300, "niw_diag", "f64", seed_off=1, onecta=onecta)
+
+
+def test_c3_bench_shape_float32_series():
+    """BASELINE configs[2] window (K64, D32, T1024, full covariance), float32 series, 64 windows."""
+    _run_case(64, 32, 1024, 64, "niw_full", "f32", sep=0.3)
+
+
+def test_c4_bench_shape_bf16_dense_against_oracle():
+    """BASELINE configs[3] as bench.py --config c4 runs it (K256, D64 diagonal, T256, bf16 tensor-core
+    recursion), 256 windows = 2 tiles of 128, against the ORACLE: marginals 3e-2 absolute, statistics
+    and updated globals 3e-2 relative to the largest entry, log normalisers 1e-2 (restated tolerance
+    of the opt-in bf16 path; the reference is float64 only)."""
+    from pysvihmm_b200 import _lib as L
+    _run_case(256, 64, 256, 256, "niw_diag", "f32", flags_extra=L.BF16_DENSE, sep=0.25, q_abs=3e-2, s_rtol=3e-2,
+              lz_rtol=1e-2)
+
+
+def test_c4_bench_shape_float32_recursions():
+    """The same shape without the flag (float32 recursions, generic kernels) meets the 1e-5 bound."""
+    _run_case(256, 64, 256, 130, "niw_diag", "f32", sep=0.25, seed_off=3)
+
+
+@pytest.mark.parametrize("T,B,sep", [(256, 3, 0.8), (256, 3, 0.2), (2048, 2, 0.8)])
+def test_c5_bench_shape_gmm(T, B, sep):
+    """BASELINE configs[4] (32 states x 4 full-covariance components, D16) at T = 256 with weakly and
+    strongly overlapping components (sep 0.8 / 0.2 sigma) and at the benchmark's T = 2048."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    K, C, D, kind = 32, 4, 16, "niw_full"
+    p = make_random_problem(seed=K * 100 + C + T, K=K * C, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1, sep=sep)
+    rs = np.random.RandomState(K + C)
+    emit = [dict(omega=1. + 3. * rs.rand(C), comps=p["emit"][k * C:(k + 1) * C]) for k in range(K)]
+    prior = [dict(omega=0.5 + rs.rand(C), comps=p["prior_emit"][k * C:(k + 1) * C]) for k in range(K)]
+    var_tran, prior_tran = 1. + 5. * rs.rand(K, K), np.ones((K, K))
+    obs = p["obs"].astype(np.float32).astype(np.float64)
+    starts = rs.randint(0, obs.shape[0] - T + 1, B)
+    eng = EStepEngine(K, D, kind, components=C)
+    eng.set_series(obs, p["mask"], dtype="f32")
+    eng.set_prior(prior_tran, pack_emit_np(p["prior_emit"]))
+    eng.set_mix_weights(np.array([e["omega"] for e in emit]), np.array([e["omega"] for e in prior]))
+    eng.set_globals(var_tran, pack_emit_np(p["emit"]))
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
+    r = O.gmm_minibatch_step(obs, p["mask"], starts, T, var_tran, emit, prior_tran, prior, 0.37, T // 2,
+                             scaled=True)
+    assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+    assert_q(vx.cpu().numpy(), r["var_x"])
+    s = eng.unpack_stats(stats)
+    assert_block(s["A"], r["A_inter"], S_RTOL, "A")
+    flat = [r["stats"][k][c] for k in range(K) for c in range(C)]
+    assert_block(s["n"], np.array([e[1] for e in flat]), S_RTOL, "n")
+    assert_block(s["sx"], np.array([e[0] for e in flat]), S_RTOL, "sx")
+    assert_block(s["sxx"], np.array([e[2] for e in flat]), S_RTOL, "sxx")
+    np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=3e-6)
+    eng.close()
+
+
+def test_log_domain_tables_match_reference_golden():
+    """self.lalpha / self.lbeta (hmmsgd_metaobs.py:775-803, :828-855) rebuilt from the engine's scaled
+    tables (svihmm_get_locals + svihmm_get_locals_beta) against the reference's own tables: 1e-6
+    relative (+2e-6 absolute: lbeta[T-1] = 0), every entry finite."""
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    from tests.helpers import SVI_CASES, emit_list, load_golden
+    for name in SVI_CASES:
+        g = load_golden(name)
+        K, D = g["init_tran"].shape[0], g["obs"].shape[1]
+        T = 2 * int(g["L"]) + 1
+        eng = EStepEngine(K, D)
+        eng.set_series(g["obs"], g["mask"], dtype="f64")
+        eng.set_globals(g["init_tran"], pack_emit_np(emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"],
+                                                               g["init_nu"])))
+        starts = g["w_starts"][0]
+        eng.estep(starts, T, flags=L.WRAP, keep_locals=True)
+        loc = eng.get_locals(len(starts), T)
+        for b in range(len(starts)):
+            la, lb = eng.log_tables(loc, b)
+            assert np.isfinite(la).all() and np.isfinite(lb).all()
+            np.testing.assert_allclose(la, g["w_lalpha"][0][b], rtol=1e-6, atol=2e-6)
+            np.testing.assert_allclose(lb, g["w_lbeta"][0][b], rtol=1e-6, atol=2e-6)
+        eng.close()
+    assert Q_RTOL == 1e-5 and Q_ATOL == 2e-7

@@ -53,7 +53,16 @@ def oracle_stats(O, r, obs, mask, starts, T, wrap):
     return A, n, sx, sxx
 
 
-PATHS = ["fused", "unfused"]     # single-kernel path (fused.cuh) / per-phase kernels (KEEP_LOCALS)
+# "fused": the engine's default choice (batched tensor-core path batch16.cuh where eligible, else the
+# one-CTA-per-window kernels); "onecta": the batched path switched off (fused.cuh / fused_pipe.cuh);
+# "unfused": per-phase kernels (KEEP_LOCALS)
+PATHS = ["fused", "onecta", "unfused"]
+
+
+def _apply_path(eng, path):
+    from pysvihmm_b200 import _lib as L
+    if path == "onecta":
+        eng.set_tuning(L.TUNE_B16_MIN_B, 0)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -68,7 +77,10 @@ def test_svi_step_matches_reference_golden(name, obs_dtype, path):
     Lh, S = int(g["L"]), int(g["mb_sz"])
     T = 2 * Lh + 1
     K, D = g["init_tran"].shape[0], obs.shape[1]
+    if path == "onecta":
+        pytest.skip("full-covariance fixtures never take the batched path: same kernels as 'fused'")
     eng = _engine(K, D)
+    _apply_path(eng, path)
     eng.set_series(obs, mask, dtype=obs_dtype)
     pe = golden_prior_emit(g, K)
     eng.set_prior(g["prior_tran"], pack_emit_np(pe))
@@ -179,6 +191,11 @@ ORACLE_CASES = [
     (4, 12, 40, 3, "niw_diag"),        # fused path, D > K: observation staging in several tiles
     (5, 9, 23, 2, "niw_full"),
     (2, 2, 20000, 1, "niw_full"),      # too long for shared memory: per-phase kernels either way
+    (16, 8, 257, 37, "niw_diag"),      # batched path: 3 groups of 16 windows (last one partial), T % 8 = 1
+    (11, 5, 40, 17, "niw_diag"),       # batched path: K, D not multiples of anything, one window in the 2nd group
+    (3, 13, 9, 2, "niw_diag"),         # batched path: D > 8 (two feature tiles), T barely over one unit
+    (16, 16, 1, 5, "niw_diag"),        # batched path: T = 1
+    (2, 1, 3000, 3, "niw_diag"),       # batched path: long windows
 ]
 
 
@@ -187,9 +204,13 @@ ORACLE_CASES = [
 def test_estep_matches_oracle(K, D, T, B, kind, path):
     from oracle import svihmm_oracle as O
     from pysvihmm_b200 import _lib as L
+    if path == "onecta" and not (kind == "niw_diag" and K <= 16 and D <= 16):
+        pytest.skip("the batched path does not take this shape: same kernels as 'fused'")
+    big = K >= 64            # log-domain recursions cost B*K*K logaddexp per step: use the pinned scaled form
     p = make_random_problem(seed=K * 1000 + T, K=K, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1)
     starts = np.random.RandomState(5).randint(0, p["obs"].shape[0] - T + 1, B)
     eng = _engine(K, D, kind)
+    _apply_path(eng, path)
     eng.set_series(p["obs"], p["mask"], dtype="f64")
     eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
     eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
@@ -198,7 +219,7 @@ def test_estep_matches_oracle(K, D, T, B, kind, path):
         vx, stats = eng.estep(starts, T, flags=flags, keep_locals=unf)
         r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"],
                                  p["prior_tran"], p["prior_emit"], 0.5, max(T // 2, 1), wrap=wrap,
-                                 mask_ll=mask_ll)
+                                 mask_ll=mask_ll, scaled=big)
         q = vx.cpu().numpy()
         assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
         assert_q(q, r["var_x"])
@@ -224,7 +245,7 @@ def test_estep_matches_oracle(K, D, T, B, kind, path):
     # natural-gradient step from the (WRAP|ADD_PRIOR) statistics
     vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR)
     r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"],
-                             p["prior_tran"], p["prior_emit"], 0.37, max(T // 2, 1), wrap=True)
+                             p["prior_tran"], p["prior_emit"], 0.37, max(T // 2, 1), wrap=True, scaled=big)
     Lh, Tf = max(T // 2, 1), p["obs"].shape[0]
     eng.global_update(stats, 0.37, (Tf - 2 * Lh - 1) / (2. * Lh * B), (Tf - 2 * Lh - 1) / ((2. * Lh + 1.) * B))
     vt, vi, em = eng.get_globals()
@@ -533,6 +554,38 @@ def test_streamed_step_equals_device_step():
     for a, b in zip(eng.get_globals(), ref_glob):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
     eng.close()
+
+
+@pytest.mark.parametrize("K,D,kind", [(16, 8, "niw_diag"), (5, 3, "niw_full")])
+def test_svi_run_equals_step_by_step(K, D, kind):
+    """svihmm_svi_run (nsteps global steps enqueued by one call, hmmsgd_metaobs.py:396-439) follows the
+    trajectory of svihmm_estep + svihmm_global_update called step by step."""
+    import torch
+    from pysvihmm_b200 import _lib as L
+    T, B, n = 64, 40, 5
+    p = make_random_problem(seed=21, K=K, D=D, T_full=3000, kind=kind, miss=0.05)
+    starts = torch.from_numpy(np.random.RandomState(2).randint(0, 3000 - T + 1, (n, B))).cuda()
+    flags = L.WRAP | L.ADD_PRIOR
+
+    def fresh():
+        eng = _engine(K, D, kind)
+        eng.set_series(p["obs"], p["mask"], dtype="f32")
+        eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        return eng
+    a = fresh()
+    for i in range(n):
+        vxa, st = a.estep(starts[i], T, flags=flags)
+        a.global_update(st, (3 + i + 1.0) ** -0.7, 2.0, 1.5)
+    b = fresh()
+    vxb = torch.empty((B, T, K), dtype=torch.float32, device="cuda")
+    stb = b.svi_run(starts, T, 1.0, 0.7, 3, 2.0, 1.5, flags=flags, var_x=vxb)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(stb.cpu().numpy(), st.cpu().numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(vxb.cpu().numpy(), vxa.cpu().numpy(), rtol=1e-6, atol=1e-9)
+    for x, y in zip(a.get_globals(), b.get_globals()):
+        np.testing.assert_allclose(x, y, rtol=1e-9, atol=1e-12)
+    a.close(); b.close()
 
 
 def test_error_paths():

@@ -51,6 +51,25 @@ def test_svi_minibatch_matches_reference(name):
         var_tran, emit = r["var_tran_new"], r["emit_new"]
 
 
+@pytest.mark.parametrize("name", SVI_CASES)
+def test_scaled_form_matches_reference(name):
+    """messages_scaled (the matrix-product form used for the BASELINE-size GPU parity cases) against
+    the reference's own lalpha / lbeta / var_x tables and against the log-domain restatement."""
+    g = load_golden(name)
+    L, T = int(g["L"]), 2 * int(g["L"]) + 1
+    emit = emit_list(g["init_mu"], g["init_sigma"], g["init_kappa"], g["init_nu"])
+    starts = g["w_starts"][0]
+    xw = g["obs"][np.asarray(starts)[:, None] + np.arange(T)[None]]
+    vi = O.stationary_init(g["init_tran"])
+    rs = O.local_update(xw, vi, g["init_tran"], emit, scaled=True)
+    np.testing.assert_allclose(rs["lalpha"], g["w_lalpha"][0], rtol=RT, atol=1e-9)
+    np.testing.assert_allclose(rs["lbeta"], g["w_lbeta"][0], rtol=RT, atol=1e-9)
+    np.testing.assert_allclose(rs["var_x"], g["w_var_x"][0], rtol=1e-9, atol=AT)
+    rl = O.local_update(xw, vi, g["init_tran"], emit)
+    np.testing.assert_allclose(O.local_lower_bound(rs["lalpha"]), O.local_lower_bound(rl["lalpha"]), rtol=RT)
+    np.testing.assert_allclose(O.log_Z(rs["lalpha"]), O.log_Z(rl["lalpha"]), rtol=RT)
+
+
 def test_wrap_quirk_is_needed():
     """Q2: without the wrap-around term the statistic differs by O(1)."""
     g = load_golden("svi_k3_d2_l5")

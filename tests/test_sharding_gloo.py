@@ -57,6 +57,34 @@ def test_two_rank_sharding_and_allreduce():
     assert out.get(0) is True and out.get(1) is True
 
 
+def _worker_bcast(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pysvihmm_b200.sharding import broadcast_minibatch, shard_starts
+    # each rank drew its OWN minibatch and window length (seed=None case): rank 0's must win
+    mine = np.random.RandomState(100 + rank).randint(0, 1000, 5 + rank)
+    starts, T = broadcast_minibatch(mine, 21 + 2 * rank, dist, torch.device("cpu"))
+    ref = np.random.RandomState(100).randint(0, 1000, 5)
+    ok = T == 21 and np.array_equal(starts, ref)
+    # a minibatch smaller than the world: the last rank's shard is empty, the others are not
+    one, _ = broadcast_minibatch(ref[:1], 21, dist, torch.device("cpu"))
+    sh = shard_starts(one, rank, world)
+    out[rank] = bool(ok) and len(sh) == (1 if rank == 0 else 0)
+    dist.destroy_process_group()
+
+
+def test_broadcast_minibatch_and_empty_shard():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker_bcast, args=(r, 2, port, out)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert out.get(0) is True and out.get(1) is True
+
+
 def test_shard_starts_partitions():
     from pysvihmm_b200.sharding import shard_starts
     s = np.arange(13)
