@@ -247,7 +247,8 @@ int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B
 
 /* Tuning knobs.  SVIHMM_TUNE_B16_MIN_B: smallest minibatch (windows per call) that takes the batched
  * tensor-core path for K <= 16 diagonal models (sixteen windows per chain warp, batch16.cuh); smaller
- * calls use the one-CTA-per-window pipelined kernel.  0 disables the batched path. */
+ * calls use the one-CTA-per-window pipelined kernel (default 4096: the measured crossover at the c2
+ * shape).  0 disables the batched path, 1 forces it for every eligible call. */
 enum { SVIHMM_TUNE_B16_MIN_B = 1 };
 int svihmm_set_tuning(svihmm_ctx* ctx, int key, int value);
 

@@ -103,7 +103,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
   c->C = C; c->KE = K * C;
-  c->b16_min_B = 1;
+  c->b16_min_B = 4096;     // measured crossover with the one-CTA-per-window kernel at K16/D8/T512
   const size_t KE = (size_t)c->KE;
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : (kind == SVIHMM_EMIT_NIW_DIAG ? D : 0);
   c->OD = kind == SVIHMM_EMIT_CATEGORICAL ? 1 : D;

@@ -65,8 +65,10 @@ __global__ void __launch_bounds__(256) k_b16_emit(const B16Args a) {
   for (int64_t i = gtid; i < 2 * (int64_t)a.B; i += nth) a.seq[i] = 0.0;
   __syncthreads();
   const bool vecx = a.dtype == SVIHMM_F32 && (D & 3) == 0 && ((((uintptr_t)a.obs) & 15) == 0);
+  const bool small = R < (int64_t)0x7fffffff;                 // 32-bit divisions where the row index fits
   for (int64_t r = gtid; r < R; r += nth) {
-    const int w = (int)(r / T); const int t = (int)(r - (int64_t)w * T);
+    const int w = small ? (int)((unsigned)r / (unsigned)T) : (int)(r / T);
+    const int t = (int)(r - (int64_t)w * T);
     const int64_t gi = a.starts[w] + t, e0 = gi * D;
     bool bad = false;
     double ll[KP];
@@ -154,7 +156,13 @@ __device__ __forceinline__ void b16_chain_run(const B16Args& a, const int grp, c
   float* op1 = out + (rb1 + tb) * B16_KS + 2 * c;
   int* ep0 = a.Et + rb0 + tb; int* ep1 = a.Et + rb1 + tb;
   const int stp = dt * B16_KS;
-  auto ldb = [&](const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); };
+  // asm volatile: the compiler must leave these loads where they are written (B16_PF steps ahead of
+  // their use); as plain __ldg it sank all refills of an unrolled block to the block's end
+  auto ldb = [&](const float* p) {
+    float2 r;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+  };
   auto stv = [&](float* p, const float x, const float y, const bool ok) {
     if (ok) *reinterpret_cast<float2*>(p) = make_float2(x, y);
   };
@@ -200,8 +208,15 @@ __device__ __forceinline__ void b16_chain_run(const B16Args& a, const int grp, c
     m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, 2)); m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
     m[0] = m0; m[1] = m1;
   };
+  // hi/lo split of the carried vector by truncation: hi = top 11 mantissa bits (exact in TF32), lo = v - hi
+  // exactly; the tensor core reads the top 11 bits of lo, so v is represented to 2^-22 (the constant
+  // matrix P is split with round-to-nearest once, above)
+  auto split_trunc = [](const float x, unsigned& hi, unsigned& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+  };
   auto step = [&](const int s, float2 (&bb)[2][2]) {
-    // ---- off the dependent chain: exponent shift of this step, scaled b, operand split of v
+    // ---- off the dependent chain: exponent shift of this step, scaled b
     int d[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -209,34 +224,38 @@ __device__ __forceinline__ void b16_chain_run(const B16Args& a, const int grp, c
       if (xm[r] == 0u) dd = 0;                            // all-zero row (cannot happen with pi0, P > 0; padding safety)
       d[r] = max(-60, min(60, dd));
     }
-    const float r0 = __uint_as_float((unsigned)(127 - d[0]) << 23), r1 = __uint_as_float((unsigned)(127 - d[1]) << 23);
+    const float r0 = __uint_as_float(0x3f800000u - ((unsigned)d[0] << 23)), r1 = __uint_as_float(0x3f800000u - ((unsigned)d[1] << 23));
+    float br[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      br[nt][0] = bb[0][nt].x * r0; br[nt][1] = bb[0][nt].y * r0;
+      br[nt][2] = bb[1][nt].x * r1; br[nt][3] = bb[1][nt].y * r1;
+    }
+    // ---- on the chain: operand split of v, 12 MMAs (two accumulator chains of 6, small terms first)
     unsigned ah[2][4], al[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      split_tf32(v[ks][0], ah[ks][0], al[ks][0]); split_tf32(v[ks][2], ah[ks][1], al[ks][1]);
-      split_tf32(v[ks][1], ah[ks][2], al[ks][2]); split_tf32(v[ks][3], ah[ks][3], al[ks][3]);
+      split_trunc(v[ks][0], ah[ks][0], al[ks][0]); split_trunc(v[ks][2], ah[ks][1], al[ks][1]);
+      split_trunc(v[ks][1], ah[ks][2], al[ks][2]); split_trunc(v[ks][3], ah[ks][3], al[ks][3]);
     }
     rowmax(xm);                                           // of v[s-1]: consumed by step s+1
-    float acc[2][2][4];
+    float acc[2][4];
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
+    for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        acc[ks][nt][0] = acc[ks][nt][1] = acc[ks][nt][2] = acc[ks][nt][3] = 0.f;
-        mma_tf32(acc[ks][nt], al[ks], ph[ks][nt]);
-        mma_tf32(acc[ks][nt], ah[ks], pl[ks][nt]);
-        mma_tf32(acc[ks][nt], ah[ks], ph[ks][nt]);
-      }
+    for (int ks = 0; ks < 2; ++ks) {
+      mma_tf32(acc[0], al[ks], ph[ks][0]); mma_tf32(acc[1], al[ks], ph[ks][1]);
+      mma_tf32(acc[0], ah[ks], pl[ks][0]); mma_tf32(acc[1], ah[ks], pl[ks][1]);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) { mma_tf32(acc[0], ah[ks], ph[ks][0]); mma_tf32(acc[1], ah[ks], ph[ks][1]); }
     float* o0 = op0 + s * stp; float* o1 = op1 + s * stp;
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      const float m0 = acc[0][nt][0] + acc[1][nt][0], m1 = acc[0][nt][1] + acc[1][nt][1];
-      const float m2 = acc[0][nt][2] + acc[1][nt][2], m3 = acc[0][nt][3] + acc[1][nt][3];
-      const float2 b0 = bb[0][nt], b1 = bb[1][nt];
-      v[nt][0] = m0 * (b0.x * r0); v[nt][1] = m1 * (b0.y * r0);
-      v[nt][2] = m2 * (b1.x * r1); v[nt][3] = m3 * (b1.y * r1);
+      v[nt][0] = acc[nt][0] * br[nt][0]; v[nt][1] = acc[nt][1] * br[nt][1];
+      v[nt][2] = acc[nt][2] * br[nt][2]; v[nt][3] = acc[nt][3] * br[nt][3];
       if (FWD) { stv(o0 + 8 * nt, v[nt][0], v[nt][1], ok0); stv(o1 + 8 * nt, v[nt][2], v[nt][3], ok1); }
-      else { stv(o0 + 8 * nt, m0 * r0, m1 * r0, ok0); stv(o1 + 8 * nt, m2 * r1, m3 * r1, ok1); }
+      else { stv(o0 + 8 * nt, acc[nt][0] * r0, acc[nt][1] * r0, ok0); stv(o1 + 8 * nt, acc[nt][2] * r1, acc[nt][3] * r1, ok1); }
     }
     E[0] += d[0]; E[1] += d[1];
     dprev[0] = d[0]; dprev[1] = d[1];
@@ -273,6 +292,14 @@ __global__ void __launch_bounds__(128) k_b16_chain(const B16Args a, const int ng
 #define B16_QS 20            // floats per row of the per-warp q tile (16 + 4: conflict-free fragment reads)
 #define B16_FLUSH 32         // units between float32 -> float64 flushes of the accumulators
 
+// hi/lo split by truncation (v = hi + lo exactly, the tensor core keeps the top 11 bits of lo): 2
+// instructions per value against ~8 for two round-to-nearest conversions; the operands of the
+// statistics are sums of thousands of terms, a 2^-22 relative truncation is far below their 1e-5 bound
+__device__ __forceinline__ void b16_split(const float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 template <int NTE>
 __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
   __shared__ __align__(16) float qs_all[8][9][B16_QS];
@@ -302,8 +329,11 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
   double lzs = 0.0, q4s = 0.0;
   int since = 0;
   const bool vec_out = a.var_x_out && K == 16 && ((((uintptr_t)a.var_x_out) & 15) == 0);
+  const bool small = nunits < (int64_t)0x7fffffff;
+  const bool f32x = a.dtype == SVIHMM_F32;
   for (int64_t u = wglob; u < nunits; u += nwarps) {
-    const int w = (int)(u / ngw); const int t0 = (int)(u - (int64_t)w * ngw) * 8;
+    const int w = small ? (int)((unsigned)u / (unsigned)ngw) : (int)(u / ngw);
+    const int t0 = (int)(u - (int64_t)w * ngw) * 8;
     const size_t rbase = (size_t)w * T;
     // ---- marginals of rows t0 .. t0+7 (4 lanes per row, one float4 each) and of the next row
     {
@@ -331,16 +361,21 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
         }
       }
       if (t == 0) { q0a.x += p.x; q0a.y += p.y; q0a.z += p.z; q0a.w += p.w; }
-      double lz = 0.0, q4 = 0.0;
+      // per-row log normalisers; the 8 rows of the unit are summed in float32 (|terms| <~ 1e4: the
+      // rounding is ~1e-9 of a window's total), windows and the minibatch in float64
+      float lz = 0.f, q4 = 0.f;
       if (valid && c == 0) {
-        const double lt = (double)logf(sa) + (double)a.Et[rbase + t] * M_LN2;
-        const double mxv = a.mx[rbase + t];
-        lz = (t == T - 1 ? lt : 0.0) + mxv;
-        q4 = lt + (double)(T - t) * mxv;
+        const float lt = fmaf((float)a.Et[rbase + t], 0.69314718056f, __logf(sa));
+        const float mxv = (float)a.mx[rbase + t];
+        lz = (t == T - 1 ? lt : 0.f) + mxv;
+        q4 = fmaf((float)(T - t), mxv, lt);
       }
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) { lz += __shfl_xor_sync(0xffffffffu, lz, o); q4 += __shfl_xor_sync(0xffffffffu, q4, o); }
-      if (lane == 0) { atomicAdd(a.seq + 2 * (size_t)w, lz); atomicAdd(a.seq + 2 * (size_t)w + 1, q4); lzs += lz; q4s += q4; }
+      if (lane == 0) {
+        atomicAdd(a.seq + 2 * (size_t)w, (double)lz); atomicAdd(a.seq + 2 * (size_t)w + 1, (double)q4);
+        lzs += (double)lz; q4s += (double)q4;
+      }
       // the row after the unit: t0 + 8, or row 0 for the wrap-around pair of the window's last unit
       int tn = t0 + 8;
       if (tn >= T) tn = (a.wrap && t0 + 8 >= T) ? 0 : -1;
@@ -367,8 +402,8 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
     __syncwarp();
     // ---- A fragments: Q^T of local rows c and c+4 (states g and g+8), split hi/lo
     unsigned ah[4], al_[4];
-    split_tf32(qs[c][g], ah[0], al_[0]); split_tf32(qs[c][g + 8], ah[1], al_[1]);
-    split_tf32(qs[c + 4][g], ah[2], al_[2]); split_tf32(qs[c + 4][g + 8], ah[3], al_[3]);
+    b16_split(qs[c][g], ah[0], al_[0]); b16_split(qs[c][g + 8], ah[1], al_[1]);
+    b16_split(qs[c + 4][g], ah[2], al_[2]); b16_split(qs[c + 4][g + 8], ah[3], al_[3]);
     // ---- transition pairs (local row k -> k+1), k = c and c+4; rows past the unit hold zeros
     {
       const int nloc = min(8, T - t0);                     // rows nloc+1 .. 8 of the tile are stale: mask them
@@ -377,7 +412,7 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
         const float x0 = (c + 1 <= nloc) ? qs[c + 1][8 * nt + g] : 0.f;
         const float x1 = (c + 5 <= nloc) ? qs[c + 5][8 * nt + g] : 0.f;
         unsigned bh[2], bl[2];
-        split_tf32(x0, bh[0], bl[0]); split_tf32(x1, bh[1], bl[1]);
+        b16_split(x0, bh[0], bl[0]); b16_split(x1, bh[1], bl[1]);
         mma_tf32(accT[nt], al_, bh); mma_tf32(accT[nt], ah, bl); mma_tf32(accT[nt], ah, bh);
       }
     }
@@ -391,8 +426,8 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
 #pragma unroll
       for (int j = 0; j < ND8; ++j) {
         const int d = 8 * j + g;
-        xa[j] = (va && d < D) ? (float)ld_obs(a.obs, a.dtype, ga * D + d) : 0.f;
-        xb[j] = (vb && d < D) ? (float)ld_obs(a.obs, a.dtype, gb * D + d) : 0.f;
+        xa[j] = (va && d < D) ? (f32x ? __ldg((const float*)a.obs + ga * D + d) : (float)__ldg((const double*)a.obs + ga * D + d)) : 0.f;
+        xb[j] = (vb && d < D) ? (f32x ? __ldg((const float*)a.obs + gb * D + d) : (float)__ldg((const double*)a.obs + gb * D + d)) : 0.f;
         na |= isnan(xa[j]); nb |= isnan(xb[j]);
       }
       const unsigned rowbits = 0x11111111u << c;            // the 8 lanes that hold columns of the same two rows
@@ -404,9 +439,9 @@ __global__ void __launch_bounds__(256) k_b16_post(const B16Args a) {
       for (int j = 0; j < ND8; ++j) {
         const float x0 = dropa ? 0.f : xa[j], x1 = dropb ? 0.f : xb[j];
         unsigned bh[2], bl[2];
-        split_tf32(x0, bh[0], bl[0]); split_tf32(x1, bh[1], bl[1]);
+        b16_split(x0, bh[0], bl[0]); b16_split(x1, bh[1], bl[1]);
         mma_tf32(accE[j], al_, bh); mma_tf32(accE[j], ah, bl); mma_tf32(accE[j], ah, bh);
-        split_tf32(x0 * x0, bh[0], bl[0]); split_tf32(x1 * x1, bh[1], bl[1]);
+        b16_split(x0 * x0, bh[0], bl[0]); b16_split(x1 * x1, bh[1], bl[1]);
         mma_tf32(accE[ND8 + j], al_, bh); mma_tf32(accE[ND8 + j], ah, bl); mma_tf32(accE[ND8 + j], ah, bh);
       }
       unsigned bo[2];

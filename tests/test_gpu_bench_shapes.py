@@ -50,8 +50,9 @@ def _run_case(K, D, T, B, kind, dtype, flags_extra=0, q_check=None, seed_off=0, 
         obs = obs.astype(np.float32).astype(np.float64)          # the numbers the engine is given
     starts = np.random.RandomState(5).randint(0, obs.shape[0] - T + 1, B)
     eng = EStepEngine(K, D, kind)
-    if onecta:                                  # the one-CTA-per-window kernels instead of the batched path
-        eng.set_tuning(L.TUNE_B16_MIN_B, 0)
+    # the one-CTA-per-window kernels, or the batched tensor-core path forced (the engine's own choice
+    # switches between them at the measured crossover, B = 4096)
+    eng.set_tuning(L.TUNE_B16_MIN_B, 0 if onecta else 1)
     eng.set_series(obs, p["mask"], dtype=dtype)
     eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
     eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))

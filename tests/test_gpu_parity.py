@@ -53,16 +53,15 @@ def oracle_stats(O, r, obs, mask, starts, T, wrap):
     return A, n, sx, sxx
 
 
-# "fused": the engine's default choice (batched tensor-core path batch16.cuh where eligible, else the
-# one-CTA-per-window kernels); "onecta": the batched path switched off (fused.cuh / fused_pipe.cuh);
-# "unfused": per-phase kernels (KEEP_LOCALS)
-PATHS = ["fused", "onecta", "unfused"]
+# "fused": the one-CTA-per-window kernels (fused.cuh / fused_pipe.cuh: the engine's choice for the small
+# minibatches of these cases); "batched": the batched tensor-core path (batch16.cuh) forced for every
+# eligible call; "unfused": per-phase kernels (KEEP_LOCALS)
+PATHS = ["fused", "batched", "unfused"]
 
 
 def _apply_path(eng, path):
     from pysvihmm_b200 import _lib as L
-    if path == "onecta":
-        eng.set_tuning(L.TUNE_B16_MIN_B, 0)
+    eng.set_tuning(L.TUNE_B16_MIN_B, 1 if path == "batched" else 0)
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -77,8 +76,8 @@ def test_svi_step_matches_reference_golden(name, obs_dtype, path):
     Lh, S = int(g["L"]), int(g["mb_sz"])
     T = 2 * Lh + 1
     K, D = g["init_tran"].shape[0], obs.shape[1]
-    if path == "onecta":
-        pytest.skip("full-covariance fixtures never take the batched path: same kernels as 'fused'")
+    if path == "batched":
+        pytest.skip("full-covariance fixtures never take the batched path")
     eng = _engine(K, D)
     _apply_path(eng, path)
     eng.set_series(obs, mask, dtype=obs_dtype)
@@ -204,8 +203,8 @@ ORACLE_CASES = [
 def test_estep_matches_oracle(K, D, T, B, kind, path):
     from oracle import svihmm_oracle as O
     from pysvihmm_b200 import _lib as L
-    if path == "onecta" and not (kind == "niw_diag" and K <= 16 and D <= 16):
-        pytest.skip("the batched path does not take this shape: same kernels as 'fused'")
+    if path == "batched" and not (kind == "niw_diag" and K <= 16 and D <= 16):
+        pytest.skip("the batched path does not take this shape")
     big = K >= 64            # log-domain recursions cost B*K*K logaddexp per step: use the pinned scaled form
     p = make_random_problem(seed=K * 1000 + T, K=K, D=D, T_full=max(4 * T, 300), kind=kind, miss=0.1)
     starts = np.random.RandomState(5).randint(0, p["obs"].shape[0] - T + 1, B)
