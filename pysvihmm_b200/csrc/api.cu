@@ -17,6 +17,8 @@
 #include "ffbs.cuh"
 #include "dense.cuh"
 #include "batch16.cuh"
+#include "stats_tc.cuh"
+#include <cudaTypedefs.h>
 
 static thread_local std::string g_err;
 
@@ -666,6 +668,78 @@ static int stats_sym_phase(svihmm_ctx* c, const void* obs, int dtype, const uint
   return SVIHMM_OK;
 }
 
+// ---- tensor-core statistics with TMA-fed operands (stats_tc.cuh) ------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+// row-major (rows, cols) float32 matrix, box = (box_rows, cols), no swizzle, out-of-bounds rows read as zero
+static bool tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool stats_tc_eligible(const svihmm_ctx* c, int T, int dtype, const void* obs, const float* q, int64_t series_rows) {
+  static const bool off = getenv("SVIHMM_NO_STATS_TC") != nullptr;       // A/B switch, read once
+  return !off && c->K > 16 && c->K <= 64 && (c->K & 3) == 0 && c->C == 1 && c->D <= 32 && (c->D & 3) == 0 &&
+         c->kind != SVIHMM_EMIT_CATEGORICAL && dtype == SVIHMM_F32 && T >= 32 && ((uintptr_t)obs & 15) == 0 &&
+         ((uintptr_t)q & 15) == 0 && series_rows < (int64_t)0x7fffffff && c->K + 1 + c->D + (c->kind == SVIHMM_EMIT_NIW_DIAG ? c->D : c->D * (c->D + 1) / 2) <= 640 &&
+         tmap_encoder() != nullptr;
+}
+
+static int stats_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, const uint8_t* mask, const int64_t* starts,
+                          int B, int T, const float* q, double* stats_out, unsigned flags, cudaStream_t st) {
+  const int K = c->K, D = c->D;
+  StcArgs a;
+  a.B = B; a.T = T; a.K = K; a.D = D; a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
+  a.NF = K + 1 + D + (a.diag ? D : D * (D + 1) / 2);
+  a.wrap = (flags & SVIHMM_WRAP) ? 1 : 0;
+  a.ntpw = (T + STC_R - 1) / STC_R; a.nmt = (a.NF + 127) / 128;
+  const int64_t nt = (int64_t)B * a.ntpw;
+  if (nt >= (int64_t)0x7fffffff || (int64_t)B * T >= (int64_t)0x7fffffff) return fail(SVIHMM_EUNSUPPORTED, "minibatch too large for the tensor-core statistics");
+  a.ntiles = (int)nt;
+  a.q = q; a.mask = mask; a.starts = starts;
+  const int grid = (int)std::min<int64_t>(148, nt);
+  const size_t need_part = (size_t)grid * K * a.NF;
+  if (need_part > c->cap_part) {
+    if (c->part_ws) CU(cudaFree(c->part_ws));
+    c->part_ws = nullptr; c->cap_part = 0;
+    CU(dalloc(&c->part_ws, need_part));
+    c->cap_part = need_part;
+  }
+  a.part = c->part_ws;
+  CUtensorMap tm_x, tm_q;
+  if (!tmap_2d_f32(&tm_x, obs, (uint64_t)series_rows, (uint64_t)D, STC_R) ||
+      !tmap_2d_f32(&tm_q, q, (uint64_t)B * T, (uint64_t)K, STC_R + 1))
+    return fail(SVIHMM_ECUDA, "cuTensorMapEncodeTiled failed");
+  const StcSmem L = stc_layout(K, D);
+  static bool attr_set = false;
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_set = true; }
+  k_stats_tc<<<grid, STC_NT, L.total, st>>>(tm_x, tm_q, a);
+  LAUNCHED(c);
+  k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+      B, T, K, D, c->DD, a.NF, a.diag, grid, c->part_ws, q, c->seq_ws, c->prior_tran,
+      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
 // generic statistics contraction (stats.cuh) of a dense (B, T, K) table of marginals
 static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                                const int64_t* starts, int B, int T, const float* q, double* stats_out,
@@ -841,6 +915,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
                       unsigned flags, cudaStream_t st, int trim = 0) {
   const int K = c->K, D = c->D;
   const bool xi = flags & SVIHMM_EXACT_XI;
+  // rows behind `obs`: the resident series, or the B*T gathered rows of a staging buffer
+  const int64_t series_rows = obs == c->obs ? c->T_full : (int64_t)B * T;
   if (trim < 0 || 2 * trim >= T) return fail(SVIHMM_EINVAL, "trim = %d leaves no inner rows of T = %d", trim, T);
   if (trim > 0 && xi) return fail(SVIHMM_EUNSUPPORTED, "SVIHMM_EXACT_XI with buffered windows");
   size_t fsmem = 0;
@@ -966,6 +1042,8 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
       return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
     }
     c->last_B = B; c->last_T = T; c->last_fused = 1;     // no lliks/alpha/cs tables in the classic form
+    if (stats_tc_eligible(c, Ts, dtype, obs, qs, series_rows))
+      return stats_tc_phase(c, obs, series_rows, mask, starts_s, B, Ts, qs, stats_out, flags, st);
     return stats_sym_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, st);
   }
   if ((flags & SVIHMM_BF16_DENSE) && K > 64 && K <= 256 && (K & 3) == 0 && !xi && !(flags & SVIHMM_KEEP_LOCALS)) {

@@ -1,0 +1,264 @@
+// Sufficient statistics of a minibatch on the 5th-generation tensor cores, operands fed by TMA
+// (16 < K <= 64; BASELINE config 3): replaces k_stats_mma (Ampere-style mma.sync, 1.49 ms at c3).
+//
+//   S[f][k] = sum over the rows r of the minibatch of  F[r][f] * q[r][k]
+//   F[r] = [ q[r+1] (K: the transition statistic, quirks Q1/Q2, hmmsgd_metaobs.py:873-881)
+//          | w_r | w_r x_r (D) | w_r x_r,i x_r,j, i <= j  (util.py:73-83; w_r = 0 on masked / NaN rows) ]
+// is ONE contraction over the rows.  A CTA walks tiles of 128 consecutive rows of one window:
+//   TMA       cp.async.bulk.tensor.2d brings the 129 x K block of marginals (one halo row: the "next"
+//             side of the last pair) and the 128 x D block of observations of the tile into shared
+//             memory (tensor maps over the (B*T, K) marginals and over the (T_full, D) series; the
+//             window start is a runtime coordinate), completion on mbarriers
+//   operands  all 256 threads turn them into bf16 hi + lo pairs (v = hi + lo to 2^-17) in the K-major
+//             SWIZZLE_128B layout of tcgen05: B operand = q^T (64 states x 128 rows), A operand = one
+//             M-tile of 128 feature rows x 128 rows; two A buffers, so the generation of the next M-tile
+//             overlaps the MMAs of the current one
+//   MMA       one thread issues, per M-tile, 8 k-steps x 3 terms (lo.hi, hi.lo, hi.hi) of
+//             tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 64, float32 accumulators in TENSOR
+//             MEMORY: nmt x 64 columns, kept across all tiles of the CTA; tcgen05.commit -> mbarriers
+//   epilogue  tcgen05.ld of the accumulators, one partial [K][NF] per CTA; k_stats_sym_finalize sums the
+//             partials in float64 (deterministic: no atomics anywhere)
+// Only q and the features carry rounding: each to 2^-17 relative, independent across rows.
+#pragma once
+#include <cuda.h>
+#include "dense.cuh"
+
+#define STC_R 128
+#define STC_NT 256
+#define STC_N 64
+
+struct StcArgs {
+  int B, T, K, D, NF, diag, wrap, ntpw, nmt, ntiles;
+  const float* q; const uint8_t* mask; const int64_t* starts;
+  float* part;               // [gridDim.x][K][NF]
+};
+
+struct StcSmem { size_t Bh, Bl, A, xs, qst, wrow, qwrap, fa, fb, bars, total; };
+__host__ __device__ inline StcSmem stc_layout(int K, int D) {
+  StcSmem s;
+  s.Bh = 0; s.Bl = 16384; s.A = 32768;                  // A: [buf][hi, lo] x 32 KB
+  s.xs = s.A + 4 * 32768;
+  s.qst = s.xs + (size_t)STC_R * D * 4;
+  s.qst = (s.qst + 127) & ~(size_t)127;
+  s.wrow = s.qst + (size_t)(STC_R + 1) * K * 4;
+  s.wrow = (s.wrow + 127) & ~(size_t)127;
+  s.qwrap = s.wrow + STC_R * 4;
+  s.fa = s.qwrap + STC_N * 4;
+  s.fb = s.fa + 640;
+  s.bars = (s.fb + 640 + 7) & ~(size_t)7;
+  s.total = s.bars + 8 * 8 + 1024;                      // + slack for the 1024-byte alignment of the base
+  return s;
+}
+
+__device__ __forceinline__ void stc_wait(unsigned long long* bar, const unsigned parity) {
+  unsigned ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(dn_smem(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void stc_tma_2d(const CUtensorMap* tm, void* dst, unsigned long long* bar, const int c0, const int c1,
+                                           const unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dn_smem(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dn_smem(dst)), "l"(tm), "r"(dn_smem(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// 8 consecutive K-elements (rows of the minibatch) of one operand row -> bf16 hi and lo chunks
+__device__ __forceinline__ void stc_pack(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * p], v[2 * p + 1]);
+    const float2 hf = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * p] - hf.x, v[2 * p + 1] - hf.y);
+    h[p] = *reinterpret_cast<const uint32_t*>(&h2); l[p] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(STC_NT, 1)
+k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const StcArgs a) {
+  extern __shared__ __align__(1024) uint8_t stc_raw[];
+  uint8_t* sm = stc_raw + ((1024u - (dn_smem(stc_raw) & 1023u)) & 1023u);
+  const int K = a.K, D = a.D, T = a.T, NF = a.NF;
+  const StcSmem L = stc_layout(K, D);
+  uint8_t* sBh = sm + L.Bh; uint8_t* sBl = sm + L.Bl; uint8_t* sA = sm + L.A;
+  float* xs = reinterpret_cast<float*>(sm + L.xs);
+  float* qst = reinterpret_cast<float*>(sm + L.qst);
+  float* wrow = reinterpret_cast<float*>(sm + L.wrow);
+  float* qwrap = reinterpret_cast<float*>(sm + L.qwrap);
+  uint8_t* fa = sm + L.fa; uint8_t* fb = sm + L.fb;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm + L.bars);
+  unsigned long long* full_q = bars; unsigned long long* full_x = bars + 1;
+  unsigned long long* mma_done = bars + 2;              // [2]: the MMAs that read A buffer 0 / 1
+  unsigned long long* mma_all = bars + 4;               // all MMAs of a tile (B operand free again)
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  // feature table: fa = 255 "next q" column fb; 254 zero row; else value = w * xe[fa] * xe[fb], xe[D] = 1
+  for (int f = tid; f < 640; f += STC_NT) {
+    int ia = 254, ib = 0;
+    if (f < K) { ia = 255; ib = f; }
+    else if (f == K) { ia = D; ib = D; }
+    else if (f < K + 1 + D) { ia = f - K - 1; ib = D; }
+    else if (f < NF) {
+      int e = f - (K + 1 + D);
+      if (a.diag) { ia = e; ib = e; }
+      else { int i = 0; while (e >= D - i) { e -= D - i; ++i; } ia = i; ib = i + e; }
+    }
+    fa[f] = (uint8_t)ia; fb[f] = (uint8_t)ib;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(bars + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+  }
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dn_smem(&tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(STC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const unsigned qbytes = (unsigned)(STC_R + 1) * K * 4, xbytes = (unsigned)STC_R * D * 4;
+  auto tile_w = [&](const int tau) { return tau / a.ntpw; };
+  auto tile_t0 = [&](const int tau) { return (tau - (tau / a.ntpw) * a.ntpw) * STC_R; };
+  int tau = blockIdx.x;
+  if (tid == 0 && tau < a.ntiles) {
+    const int w = tile_w(tau), t0 = tile_t0(tau);
+    stc_tma_2d(&tm_q, qst, full_q, 0, w * T + t0, qbytes);
+    stc_tma_2d(&tm_x, xs, full_x, 0, (int)(a.starts[w] + t0), xbytes);
+  }
+  unsigned it = 0, gen = 0;                             // tiles done by this CTA, A-operand generations so far
+  for (; tau < a.ntiles; tau += gridDim.x, ++it) {
+    const int w = tile_w(tau), t0 = tile_t0(tau);
+    const int nrow = min(STC_R, T - t0);                // real rows of the tile
+    stc_wait(full_q, it & 1);
+    if (it > 0) stc_wait(mma_all, (it - 1) & 1);        // the B operand is free again
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- B operand: q^T, hi and lo.  thread = (state n, 4 chunks of 8 rows)
+    {
+      const int n = tid & 63, cq = tid >> 6;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int c = cq * 4 + c4;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int r = 8 * c + j; v[j] = (r < nrow && n < K) ? qst[r * K + n] : 0.f; }
+        uint4 hi, lo;
+        stc_pack(v, hi, lo);
+        const uint32_t off = dn_chunk(n, c, STC_N);
+        *reinterpret_cast<uint4*>(sBh + off) = hi; *reinterpret_cast<uint4*>(sBl + off) = lo;
+      }
+      // the wrap-around partner of the window's last row (quirk Q2): q[w][0]
+      if (tid < STC_N) qwrap[tid] = (a.wrap && tid < K && t0 + STC_R >= T) ? __ldg(a.q + (size_t)w * T * K + tid) : 0.f;
+    }
+    // ---- row weights: 0 for masked rows, rows with a NaN, rows past the window end
+    stc_wait(full_x, it & 1);
+    {
+      const int64_t g0 = a.starts[w] + t0;
+      for (int r = wp * 16; r < wp * 16 + 16; ++r) {
+        const bool isn = lane < D ? isnan(xs[r * D + lane]) : false;
+        const unsigned any = __ballot_sync(0xffffffffu, isn);
+        if (lane == 0) wrow[r] = (r < nrow && !any && !(a.mask && a.mask[g0 + r])) ? 1.f : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int m = 0; m < a.nmt; ++m, ++gen) {
+      const unsigned ab = gen & 1, use = gen >> 1;
+      if (use > 0) { stc_wait(mma_done + ab, (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+      uint8_t* Ah = sA + (size_t)ab * 65536; uint8_t* Al = Ah + 32768;
+      // ---- A operand of M-tile m: thread = (feature row fl, 8 chunks of 8 rows)
+      {
+        const int fl = tid & 127, half = tid >> 7, f = 128 * m + fl;
+        const int ka = fa[f], kb = fb[f];
+#pragma unroll 2
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int c = half * 8 + c8;
+          float v[8];
+          if (ka == 255) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = 8 * c + j, tn = t0 + r + 1;
+              v[j] = tn < T ? qst[(r + 1) * K + kb] : (tn == T ? qwrap[kb] : 0.f);
+            }
+          } else if (ka == 254) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = 8 * c + j;
+              const float xa = ka < D ? xs[r * D + ka] : 1.f, xb = kb < D ? xs[r * D + kb] : 1.f;
+              v[j] = wrow[r] != 0.f ? xa * xb : 0.f;
+            }
+          }
+          uint4 hi, lo;
+          stc_pack(v, hi, lo);
+          const uint32_t off = dn_chunk(fl, c, 128);
+          *reinterpret_cast<uint4*>(Ah + off) = hi; *reinterpret_cast<uint4*>(Al + off) = lo;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tid == 0) {
+        const int taun = tau + gridDim.x;
+        if (taun < a.ntiles) {
+          // the staging buffers are free once their last readers are past the barrier above: the marginals
+          // after M-tile 0 (the "next q" features), the observations after the last M-tile
+          if (m == 0) stc_tma_2d(&tm_q, qst, full_q, 0, tile_w(taun) * T + tile_t0(taun), qbytes);
+          if (m == a.nmt - 1) stc_tma_2d(&tm_x, xs, full_x, 0, (int)(a.starts[tile_w(taun)] + tile_t0(taun)), xbytes);
+        }
+        const uint32_t aAh = dn_smem(Ah), aAl = dn_smem(Al), aBh = dn_smem(sBh), aBl = dn_smem(sBl);
+        const uint32_t dcol = tm + (uint32_t)m * STC_N;
+#pragma unroll 1
+        for (int ks = 0; ks < STC_R / 16; ++ks) {
+          const uint32_t oa = (ks >> 2) * (128 * 128) + (ks & 3) * 32, ob = (ks >> 2) * (STC_N * 128) + (ks & 3) * 32;
+          const uint64_t dah = dn_desc(aAh + oa), dal = dn_desc(aAl + oa), dbh = dn_desc(aBh + ob), dbl = dn_desc(aBl + ob);
+          const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(dcol), "l"(dal), "l"(dbh), "r"(idesc), "r"(acc0) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(dcol), "l"(dah), "l"(dbl), "r"(idesc), "r"(1u) : "memory");
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(dcol), "l"(dah), "l"(dbh), "r"(idesc), "r"(1u) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dn_smem(mma_done + ab)) : "memory");
+        if (m == a.nmt - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dn_smem(mma_all)) : "memory");
+      }
+    }
+  }
+  // ---- epilogue: accumulators -> this CTA's partial [K][NF]
+  if (it > 0) stc_wait(mma_all, (it - 1) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    float* part = a.part + (size_t)blockIdx.x * K * NF;
+    const int quarter = wp & 3, chalf = wp >> 2;
+    for (int m = 0; m < a.nmt; ++m) {
+      uint32_t v[32];
+      const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * STC_N + chalf * 32);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                     "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                     "=r"(v[30]), "=r"(v[31]) : "r"(ta) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int f = 128 * m + quarter * 32 + lane;
+      if (f < NF) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = chalf * 32 + j;
+          if (n < K) part[(size_t)n * NF + f] = it > 0 ? __uint_as_float(v[j]) : 0.f;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+}

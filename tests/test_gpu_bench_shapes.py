@@ -39,13 +39,21 @@ def _stats_from_q(q, obs, mask, starts, T, wrap, prior_tran, full):
 
 
 def _run_case(K, D, T, B, kind, dtype, flags_extra=0, q_check=None, seed_off=0, sep=0.4, miss=0.05,
-              q_abs=None, s_rtol=S_RTOL, lz_rtol=3e-6, onecta=False):
+              q_abs=None, s_rtol=S_RTOL, lz_rtol=3e-6, onecta=False, nan_frac=0.0):
     from oracle import svihmm_oracle as O
     from pysvihmm_b200 import _lib as L
     from pysvihmm_b200.engine import EStepEngine
     p = make_random_problem(seed=K * 1000 + T + seed_off, K=K, D=D, T_full=max(8 * T, 4000), kind=kind,
                             miss=miss, sep=sep)
     obs = p["obs"]
+    if nan_frac > 0:                                             # NaN entries: those rows carry no evidence
+        obs = obs.copy()
+        rsn = np.random.RandomState(77)
+        obs[rsn.rand(obs.shape[0]) < nan_frac, rsn.randint(0, D)] = np.nan
+        # the reference drops only MASKED rows from the emission statistics (a NaN observation would
+        # poison its sums, hmmsgd_metaobs.py:884-904); flag the NaN rows as masked so that the oracle's
+        # update stays finite - the engine drops them either way
+        p["mask"] = p["mask"] | np.isnan(obs).any(1)
     if dtype == "f32":
         obs = obs.astype(np.float32).astype(np.float64)          # the numbers the engine is given
     starts = np.random.RandomState(5).randint(0, obs.shape[0] - T + 1, B)
@@ -108,6 +116,15 @@ def test_c2_bench_shape_float64_series(onecta):
 def test_c3_bench_shape_float32_series():
     """BASELINE configs[2] window (K64, D32, T1024, full covariance), float32 series, 64 windows."""
     _run_case(64, 32, 1024, 64, "niw_full", "f32", sep=0.3)
+
+
+@pytest.mark.parametrize("K,D,T,B,kind", [(64, 32, 300, 5, "niw_full"), (32, 16, 200, 7, "niw_diag"),
+                                          (20, 4, 129, 3, "niw_full"), (48, 8, 33, 9, "niw_diag"),
+                                          (64, 32, 128, 160, "niw_full")])
+def test_tensor_core_statistics_path(K, D, T, B, kind):
+    """k_stats_tc (tcgen05 + TMA; 16 < K <= 64, float32 series): ragged last tiles (T % 128 != 0), masked
+    and NaN rows, more tiles than CTAs (160 windows x 1 tile > 148), full and diagonal second moments."""
+    _run_case(K, D, T, B, kind, "f32", sep=0.3, miss=0.1, nan_frac=0.02)
 
 
 def test_c4_bench_shape_bf16_dense_against_oracle():
