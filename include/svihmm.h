@@ -249,7 +249,10 @@ int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B
  * tensor-core path for K <= 16 diagonal models (sixteen windows per chain warp, batch16.cuh); smaller
  * calls use the one-CTA-per-window pipelined kernel (default 4096: the measured crossover at the c2
  * shape).  0 disables the batched path, 1 forces it for every eligible call. */
-enum { SVIHMM_TUNE_B16_MIN_B = 1 };
+enum { SVIHMM_TUNE_B16_MIN_B = 1,
+       /* shortest window that takes the block-parallel scan (K <= 16, few long chains; scan16.cuh)
+        * instead of the sequential per-phase recursions; default 4096, 0 = never */
+       SVIHMM_TUNE_SCAN_MIN_T = 2 };
 int svihmm_set_tuning(svihmm_ctx* ctx, int key, int value);
 
 /* Backward table of the last SVIHMM_KEEP_LOCALS E-step (self.lbeta, hmmsgd_metaobs.py:828-855 /

@@ -13,6 +13,7 @@ LOC_DEVICE, LOC_HOST = 0, 1
 WRAP, ADD_PRIOR, MASK_LL, EXACT_XI, KEEP_LOCALS, BF16_DENSE = 1, 2, 4, 8, 16, 32
 N_PHASES = 8
 TUNE_B16_MIN_B = 1
+TUNE_SCAN_MIN_T = 2
 
 _vp, _i, _i64, _d, _u = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint
 # name -> (restype, argtypes); must list every symbol include/svihmm.h declares

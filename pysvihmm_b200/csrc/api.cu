@@ -18,6 +18,7 @@
 #include "dense.cuh"
 #include "batch16.cuh"
 #include "stats_tc.cuh"
+#include "scan16.cuh"
 #include <cudaTypedefs.h>
 
 static thread_local std::string g_err;
@@ -105,6 +106,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   c->ev_pool = new std::vector<cudaEvent_t>(); c->ev_phase = new std::vector<int>();
   c->device = device; c->K = K; c->D = D; c->kind = kind; c->KP = next_pow2(K);
   c->C = C; c->KE = K * C;
+  c->scan_min_T = 4096;
   c->b16_min_B = 4096;     // measured crossover with the one-CTA-per-window kernel at K16/D8/T512
   const size_t KE = (size_t)c->KE;
   c->DD = kind == SVIHMM_EMIT_NIW_FULL ? D * D : (kind == SVIHMM_EMIT_NIW_DIAG ? D : 0);
@@ -156,7 +158,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
                   c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->beta_ws, c->sb_ws,
-                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
+                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -1096,7 +1098,30 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     }
     beta_out = c->beta_ws; sb_out = c->sb_ws; c->last_beta = 1;
   }
-  if (K <= 32) {
+  static const bool no_scan = getenv("SVIHMM_NO_SCAN") != nullptr;         // A/B switch, read once
+  if (K <= 16 && !xi && !no_scan && c->scan_min_T > 0 && T >= c->scan_min_T && (int64_t)B * ((T + 255) / 256) >= 64) {
+    // few LONG chains: block-parallel scan (scan16.cuh) instead of T sequential steps on one warp
+    ScanArgs sa;
+    sa.B = B; sa.T = T; sa.K = K; sa.Lc = T >= (1 << 19) ? 512 : 256; sa.C = (T + sa.Lc - 1) / sa.Lc;
+    sa.P = c->Pt; sa.PT = c->PtT; sa.pi0 = c->pi0; sa.b = c->b_ws; sa.alpha = c->alpha_ws; sa.cs = cs;
+    sa.q = q; sa.beta = beta_out; sa.sb = sb_out;
+    const size_t nch = (size_t)B * sa.C;
+    if (nch > c->cap_scan) {
+      if (c->scan_ops) CU(cudaFree(c->scan_ops));
+      if (c->scan_bound) CU(cudaFree(c->scan_bound));
+      c->scan_ops = c->scan_bound = nullptr; c->cap_scan = 0;
+      CU(dalloc(&c->scan_ops, nch * 2 * SC_OP)); CU(dalloc(&c->scan_bound, nch * 2 * 16));
+      c->cap_scan = nch;
+    }
+    sa.ops = c->scan_ops; sa.bound = c->scan_bound;
+    const int ngroups = (int)((nch + 15) / 16);
+    { PhaseTimer pt(c, PH_FORWARD, st);
+      k_scan_ops<<<(unsigned)((2 * nch + 3) / 4), 128, 0, st>>>(sa); LAUNCHED(c);
+      k_scan_combine<<<B, 64, 0, st>>>(sa); LAUNCHED(c);
+      k_scan_pass<<<(ngroups + 3) / 4, 128, 0, st>>>(sa, ngroups, 1); LAUNCHED(c); }
+    { PhaseTimer pt(c, PH_BACKWARD, st);
+      k_scan_pass<<<(ngroups + 3) / 4, 128, 0, st>>>(sa, ngroups, 0); LAUNCHED(c); }
+  } else if (K <= 32) {
     switch (c->KP) {
       case 2: launch_fb<2>(c, B, T, q, r, st, beta_out, sb_out); break;
       case 4: launch_fb<4>(c, B, T, q, r, st, beta_out, sb_out); break;
@@ -1122,7 +1147,12 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   }
   CU(cudaGetLastError());
   PhaseTimer pt_stats(c, PH_STATS, st);
-  k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
+  if (T >= 8192) {                    // long chains: split the rows of a sequence over CTAs
+    CU(cudaMemsetAsync(c->seq_ws, 0, sizeof(double) * 2 * B, st));
+    k_seq_logz_split<<<dim3(B, (unsigned)std::min(256, T / 4096)), 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
+  } else {
+    k_seq_logz<<<(B * 32 + 255) / 256, 256, 0, st>>>(B, T, cs, c->mx_ws, c->seq_ws);
+  }
   LAUNCHED(c);
   if ((rc = trim_for_stats())) return rc;
   if (mix) {
@@ -1653,6 +1683,7 @@ extern "C" int svihmm_set_tuning(svihmm_ctx* c, int key, int value) {
   if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
   switch (key) {
     case SVIHMM_TUNE_B16_MIN_B: c->b16_min_B = value; return SVIHMM_OK;
+    case SVIHMM_TUNE_SCAN_MIN_T: c->scan_min_T = value; return SVIHMM_OK;
     default: return fail(SVIHMM_EINVAL, "unknown tuning key %d", key);
   }
 }

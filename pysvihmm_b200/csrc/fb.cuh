@@ -277,3 +277,33 @@ k_seq_logz(int B, int T, const float* __restrict__ cs, const double* __restrict_
   }
   if (lane == 0) { seq[2 * s] = lz; seq[2 * s + 1] = q4; }
 }
+
+// the same for LONG sequences: grid (B, nsplit), every CTA sums a slice of the rows and adds its two
+// partial sums to seq with float64 atomics (seq zeroed beforehand); one warp per sequence would walk
+// 1e6 rows alone
+__global__ void __launch_bounds__(256)
+k_seq_logz_split(int B, int T, const float* __restrict__ cs, const double* __restrict__ mx,
+                 double* __restrict__ seq) {
+  __shared__ double red[2][8];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int per = (T + gridDim.y - 1) / gridDim.y;
+  const int ta = blockIdx.y * per, tb = min(T, ta + per);
+  double lz = 0.0, q4 = 0.0;
+  for (int t = ta + tid; t < tb; t += 256) {
+    const double term = log((double)cs[(size_t)s * T + t]) + mx[(size_t)s * T + t];
+    lz += term;
+    q4 += (double)(T - t) * term;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lz += __shfl_xor_sync(0xffffffffu, lz, o);
+    q4 += __shfl_xor_sync(0xffffffffu, q4, o);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = lz; red[1][tid >> 5] = q4; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(seq + 2 * s, a); atomicAdd(seq + 2 * s + 1, b);
+  }
+}

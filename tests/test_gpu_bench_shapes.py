@@ -202,3 +202,43 @@ def test_log_domain_tables_match_reference_golden():
             np.testing.assert_allclose(lb, g["w_lbeta"][0][b], rtol=1e-6, atol=2e-6)
         eng.close()
     assert Q_RTOL == 1e-5 and Q_ATOL == 2e-7
+
+
+@pytest.mark.parametrize("K,D,T,B,kind,keep", [(16, 8, 300000, 1, "niw_diag", False), (16, 4, 70001, 1, "niw_full", True),
+                                               (5, 3, 6000, 4, "niw_full", True), (2, 2, 1000000, 1, "niw_full", False)])
+def test_long_chain_block_parallel_scan(K, D, T, B, kind, keep):
+    """full_local_update / batch drivers on ONE long chain (hmmsgd_metaobs.py:1147-1205,
+    hmmbase.py:266-320).  K <= 16 and T >= 4096 take the block-parallel scan (scan16.cuh: chunk transfer
+    operators on the tensor cores, boundary messages, per-chunk passes) instead of T sequential steps;
+    same outputs as the sequential kernels: marginals 1e-5, log normalisers, statistics and - with
+    KEEP_LOCALS - the reference's lalpha / lbeta tables at 1e-6 relative."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    Tf = B * T + 100
+    p = make_random_problem(seed=K * 7 + D, K=K, D=D, T_full=Tf, kind=kind, miss=0.05, sep=0.5)
+    starts = np.arange(B) * T + 50
+    eng = EStepEngine(K, D, kind)
+    eng.set_series(p["obs"], p["mask"], dtype="f64")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep(starts, T, flags=L.MASK_LL | L.ADD_PRIOR, keep_locals=keep)
+    r = O.svi_minibatch_step(p["obs"], p["mask"], starts, T, p["var_tran"], p["emit"], p["prior_tran"],
+                             p["prior_emit"], 0.5, T // 2, wrap=False, mask_ll=True, scaled=True)
+    assert frac_soft(r["var_x"]) > 0.2
+    assert_q(vx.cpu().numpy(), r["var_x"])
+    s = eng.unpack_stats(stats)
+    np.testing.assert_allclose(s["logZ"], r["logZ"].sum(), rtol=3e-6)
+    np.testing.assert_allclose(s["lb_q4"], r["lb"], rtol=3e-6)
+    A = O.tran_stat(r["var_x"], False).sum(0) + B * (p["prior_tran"] - 1.)
+    assert_block(s["A"], A, S_RTOL, "A")
+    assert_block(s["n"], np.array([e[1] for e in r["emit_inter"]]), S_RTOL, "n")
+    assert_block(s["sx"], np.array([e[0] for e in r["emit_inter"]]), S_RTOL, "sx")
+    if keep:
+        loc = eng.get_locals(B, T)
+        for b in range(B):
+            la, lb = eng.log_tables(loc, b)
+            assert np.isfinite(la).all() and np.isfinite(lb).all()
+            np.testing.assert_allclose(la, r["lalpha"][b], rtol=1e-6, atol=2e-5)
+            np.testing.assert_allclose(lb, r["lbeta"][b], rtol=1e-6, atol=2e-5)
+    eng.close()
