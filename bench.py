@@ -250,6 +250,108 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+
+def quick_record(name, cfg, world, rank, local, dev, dist, B_per_gpu, seconds, scaling, steps=4, t_full=1 << 21):
+    """A short (a few seconds) run of another BASELINE config beside the main one, so that the configs
+    north_star ties to several GPUs are on the driver's record: same step as the main line (E-step over
+    this rank's windows + sum over ranks inside the update + natural-gradient update), one
+    svihmm_svi_run call per block of `steps` steps, CUDA events, median block, max over ranks.  The series
+    is smaller than the main one (2M rows, still larger than L2)."""
+    import torch
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine, pack_emit_dicts as pack_emit_np
+    K, D, T, kind = cfg["K"], cfg["D"], cfg["T"], cfg["kind"]
+    B = int(B_per_gpu)
+    obs_host, mus = synthetic_series(K, D, t_full, seed=4242)
+    C_mix = int(cfg.get("components", 1))
+    var_tran, emit, prior = globals_for(K, D, kind, mus, seed=4242)
+    if C_mix > 1:
+        rsm = np.random.RandomState(7)
+        emit = [dict(e, mu=e["mu"] + 0.7 * rsm.randn(D)) for e in emit for _ in range(C_mix)]
+        prior = [p_ for p_ in prior for _ in range(C_mix)]
+    eng = EStepEngine(K, D, kind, device=local, components=C_mix)
+    eng.set_series(torch.from_numpy(obs_host).to(dev))
+    del obs_host
+    eng.set_prior(np.ones((K, K)), pack_emit_np(prior))
+    if C_mix > 1:
+        eng.set_mix_weights(2. * np.ones((K, C_mix)), np.ones((K, C_mix)))
+    eng.set_globals(var_tran, pack_emit_np(emit))
+    flags = L.WRAP | L.ADD_PRIOR | (L.BF16_DENSE if cfg.get("bf16_dense") else 0)
+    Lh, S = T // 2, B * world
+    bA = (t_full - 2 * Lh - 1) / (2. * Lh * S)
+    bE = (t_full - 2 * Lh - 1) / ((2. * Lh + 1.) * S)
+    px = None
+    if world > 1:
+        from pysvihmm_b200.sharding import PeerExchange
+        px = PeerExchange(eng, dist)
+    g = torch.Generator().manual_seed(77)
+    pool = 4 * steps
+    starts = torch.randint(0, t_full - T, (pool, world, B), generator=g)[:, rank].contiguous().to(dev)
+    var_x = torch.empty((B, T, K), dtype=torch.float32, device=dev)
+    stats = eng.new_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def block(i):
+        i0 = (i % 4) * steps
+        eng.svi_run(starts[i0:i0 + steps], T, 1.0, 0.7, i * steps, bA, bE, flags=flags, var_x=var_x, stats=stats,
+                    peers=px is not None)
+    block(0)
+    sync()
+    eng.set_profiling(True); eng.phase_ms()
+    out, tot, i = [], 0.0, 1
+    while True:
+        sync()
+        e0.record(); block(i); e1.record()
+        sync()
+        out.append(e0.elapsed_time(e1)); tot += out[-1]; i += 1
+        go = torch.tensor([1.0 if (tot < 1e3 * seconds and len(out) < 200) else 0.0], device=dev)
+        if world > 1:
+            dist.broadcast(go, src=0)
+        if go.item() < 0.5:
+            break
+    ph = eng.phase_ms()
+    eng.set_profiling(False)
+    tmax = torch.tensor([float(np.median(out))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item()) / steps
+    rec = {"config": name, "workload": cfg["workload"], "B_per_gpu": B, "global_B": B * world, "scaling": scaling,
+           "n_gpus": world, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "E-steps/s",
+           "blocks": len(out), "steps_per_block": steps,
+           "phases_ms_per_step": {k: v[0] / (len(out) * steps) for k, v in ph.items()}}
+    eng.close()
+    del eng, var_x, starts
+    torch.cuda.empty_cache()
+    return rec
+
+
+def xrank_check(eng, px, dist, starts_row, T, flags, bA, bE, dev):
+    """Outside the timed region: the sum over ranks taken inside the update kernel (P2P pushes over
+    NVLink) against an NCCL all-reduce of the same per-rank statistics, and bit-equality of the
+    replicated globals across ranks after the update."""
+    import torch
+    stats = eng.new_stats()
+    eng.estep(starts_row, T, flags=flags, want_var_x=False, stats=stats)
+    ref = stats.clone()
+    dist.all_reduce(ref)                                      # NCCL sum of the per-rank statistics
+    px.global_update(stats, 0.1, bA, bE)
+    red = px.reduced_stats()
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max().item())
+    err = float((red - ref).abs().max().item()) / max(scale, 1e-300)
+    vt, vi, em = eng.get_globals()
+    packed = torch.from_numpy(np.concatenate([vt.ravel(), vi.ravel(), em.ravel()])).to(dev).view(torch.int64)
+    lo, hi = packed.clone(), packed.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool((lo == hi).all().item())
+    ok = err < 1e-12 and same
+    return {"xrank_check": "ok" if ok else "FAILED", "peer_sum_vs_nccl_rel_err": err, "globals_bitwise_equal_across_ranks": same}
+
 def run_ours(args, cfg):
     # libraries (NCCL, symmetric memory) may print to stdout: keep fd 1 for the ONE JSON line
     json_fd = os.dup(1)
@@ -332,6 +434,11 @@ def run_ours(args, cfg):
     for i in range(args.warmup):
         step(i, i)
     sync()
+    xr = None
+    if px is not None:
+        xr = xrank_check(eng, px, dist, starts_dev[0], T, flags, bA, bE, dev)
+        eng.set_globals(var_tran, em0)
+        sync()
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
     eng.set_profiling(True)
     eng.phase_ms()
@@ -481,6 +588,24 @@ def run_ours(args, cfg):
     ms2 = float(tmax.item())
     e2e = world * B * args.steps / (ms2 * 1e-3)
 
+    # ---- the other BASELINE configs, briefly (driver-visible records for the multi-GPU configs) ----
+    extras = []
+    slen = eng.slen
+    if args.extras and args.config == "c2" and not args.B:
+        eng.close()
+        del eng, var_x, starts_dev
+        torch.cuda.empty_cache()
+        try:
+            # configs[2]: 4096 windows in all, sharded over the ranks (strong scaling)
+            extras.append(quick_record("c3", CONFIGS["c3"], world, rank, local, dev, dist, 4096 // world, 1.0, "strong"))
+            # configs[3]: 1024 windows per GPU (weak scaling sweep)
+            extras.append(quick_record("c4", CONFIGS["c4"], world, rank, local, dev, dist, 1024, 1.0, "weak"))
+            # configs[4]: 512 windows in all (strong scaling)
+            extras.append(quick_record("c5", CONFIGS["c5"], world, rank, local, dev, dist, max(512 // world, 1), 1.0, "strong"))
+        except Exception as e:          # noqa: BLE001
+            extras.append({"error": repr(e)})
+        eng = None
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg_bytes = T * (D * 4 + K * 4)                      # read window once, write var_x once
@@ -516,7 +641,7 @@ def run_ours(args, cfg):
                          "whole_step_achieved": step_ach, "whole_step_frac": step_ach / peak,
                          "phases_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}},
             "e2e": {"value": e2e, "unit": "E-steps/s", "ms_per_step": ms2 / args.steps,
-                    "h2d_bytes_per_step": B * T * D * 4 + B * 8, "d2h_bytes_per_step": eng.slen * 8,
+                    "h2d_bytes_per_step": B * T * D * 4 + B * 8, "d2h_bytes_per_step": slen * 8,
                     "phases_ms_per_call": {k: v[0] / max(v[1], 1) for k, v in phases2.items()},
                     "call": "svihmm_svi_step_host (one C-ABI call per global step: host windows in, statistics "
                             "out; the next step's windows are gathered over PCIe while this step computes)"
@@ -528,6 +653,10 @@ def run_ours(args, cfg):
         }
         if b_sweep is not None:
             line["b_sweep"] = b_sweep
+        if xr is not None:
+            line.update(xr)
+        if extras:
+            line["extra_configs"] = extras
         if cfg.get("bf16_dense"):
             # the dense K x K work (forward + backward matvecs + transition statistic =
             # 6 K^2 T flop per E-step) against the measured bf16 tensor peak, over the phases that hold it
@@ -562,6 +691,8 @@ def main():
     ap.add_argument("--nccl", action="store_true", help="N > 1: plain NCCL all-reduce instead of the fused peer sum")
     ap.add_argument("--min-seconds", type=float, default=2.0,
                     help="repeat the timed block of --steps steps until the timed region is at least this long")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the short records of configs c3 / c4 / c5 appended to the c2 line")
     ap.add_argument("--py-loop", action="store_true",
                     help="drive every global step from Python (svihmm_estep + svihmm_global_update per step) "
                          "instead of one svihmm_svi_run call per block")
