@@ -953,6 +953,9 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   float* b_out = mix ? nullptr : c->b_ws;
   if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {
     // register-blocked float64 kernel with the row maximum and b = exp(ll - max) fused in
+    // (a persistent-grid variant that kept the float64 log-likelihoods in per-CTA scratch slots, so that
+    // the 268 MB table of config 3 never reaches HBM, was measured SLOWER: 2.69 ms against 1.87 ms; the
+    // kernel is bound by the FP64 pipe, not by that write, and loses its CTA-level latency hiding)
     const unsigned grid = (unsigned)((R + 2 * ERB_NT - 1) / (2 * ERB_NT));
 #define ERB_LAUNCH(DV) do { \
       const size_t smem = (size_t)2 * ERB_KC * (erb_len(DV) + DV + (DV & 1)) * sizeof(double); \
