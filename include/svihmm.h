@@ -245,6 +245,14 @@ int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B
                    double* stats_out, unsigned flags, double tau, double kappa, int64_t it0, double bfact_A,
                    double bfact_E, int peers, void* stream);
 
+/* Global part of the variational lower bound from the device-resident parameters, one float64 at `loc`:
+ * hmmsgd_metaobs.VBHMM.global_lower_bound (hmmsgd_metaobs.py:273-296) = Dirichlet energy + entropy of the
+ * transition rows + sum over states of var_emit[k].get_vlb() (Gaussian: pybasicbayes/distributions.py:331-349,
+ * Categorical: :1372-1381; per dimension for the diagonal model; mixture weights as Categoricals);
+ * include_init != 0 adds the Dirichlet terms of the initial distribution (hmmbase.lower_bound,
+ * hmmbase.py:145-199).  The data term is the statistics tail [sum logZ, sum Q4] of the E-step. */
+int svihmm_global_bound(svihmm_ctx* ctx, double* out, int include_init, int loc, void* stream);
+
 /* Tuning knobs.  SVIHMM_TUNE_B16_MIN_B: smallest minibatch (windows per call) that takes the batched
  * tensor-core path for K <= 16 diagonal models (sixteen windows per chain warp, batch16.cuh); smaller
  * calls use the one-CTA-per-window pipelined kernel (default 4096: the measured crossover at the c2
@@ -252,7 +260,11 @@ int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B
 enum { SVIHMM_TUNE_B16_MIN_B = 1,
        /* shortest window that takes the block-parallel scan (K <= 16, few long chains; scan16.cuh)
         * instead of the sequential per-phase recursions; default 4096, 0 = never */
-       SVIHMM_TUNE_SCAN_MIN_T = 2 };
+       SVIHMM_TUNE_SCAN_MIN_T = 2,
+       /* != 0: svihmm_set_series_streamed does not page-lock the host series; the windows of every step are
+        * gathered by the CPU into pinned staging instead (for memory-mapped series larger than host memory,
+        * gen_synthetic.read_data_mmap, gen_synthetic.py:188-191).  Set before svihmm_set_series_streamed. */
+       SVIHMM_TUNE_NO_HOSTREG = 3 };
 int svihmm_set_tuning(svihmm_ctx* ctx, int key, int value);
 
 /* Backward table of the last SVIHMM_KEEP_LOCALS E-step (self.lbeta, hmmsgd_metaobs.py:828-855 /

@@ -14,6 +14,7 @@ WRAP, ADD_PRIOR, MASK_LL, EXACT_XI, KEEP_LOCALS, BF16_DENSE = 1, 2, 4, 8, 16, 32
 N_PHASES = 8
 TUNE_B16_MIN_B = 1
 TUNE_SCAN_MIN_T = 2
+TUNE_NO_HOSTREG = 3
 
 _vp, _i, _i64, _d, _u = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_uint
 # name -> (restype, argtypes); must list every symbol include/svihmm.h declares
@@ -49,6 +50,7 @@ SYMBOLS = {
     "svihmm_batchsgd_update": (_i, [_vp, _vp, _d, _vp]),
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_svi_run": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _u, _d, _d, _i64, _d, _d, _i, _vp]),
+    "svihmm_global_bound": (_i, [_vp, _vp, _i, _i, _vp]),
     "svihmm_set_tuning": (_i, [_vp, _i, _i]),
     "svihmm_get_locals_beta": (_i, [_vp, _vp, _vp, _i, _vp]),
     "svihmm_ffbs": (_i, [_vp, _vp, _i64, _i, _i, C.c_uint64, _vp, _i, _vp]),

@@ -19,6 +19,7 @@
 #include "batch16.cuh"
 #include "stats_tc.cuh"
 #include "scan16.cuh"
+#include "bound.cuh"
 #include <cudaTypedefs.h>
 
 static thread_local std::string g_err;
@@ -211,14 +212,18 @@ extern "C" int svihmm_set_series_streamed(svihmm_ctx* c, const void* obs_host, i
   // Page-lock + map the caller's buffer so the GPU gathers each step's windows itself.  If the
   // registration is refused (e.g. read-only mapping) the CPU-gather + pinned-staging path is used.
   const size_t nb = (size_t)T_full * c->OD * esize(dtype);
-  if (cudaHostRegister((void*)obs_host, nb, cudaHostRegisterMapped) == cudaSuccess) {
+  // (a read-only mapping, e.g. np.memmap(mode='r') of gen_synthetic.read_data_mmap, needs the ReadOnly flag)
+  if (c->no_hostreg) return SVIHMM_OK;        // tuning: CPU gather + pinned staging (series larger than host memory)
+  if (cudaHostRegister((void*)obs_host, nb, cudaHostRegisterMapped) == cudaSuccess ||
+      ((void)cudaGetLastError(), cudaHostRegister((void*)obs_host, nb, cudaHostRegisterMapped | cudaHostRegisterReadOnly) == cudaSuccess)) {
     c->h_reg_obs = 1;
     void* dp = nullptr;
     if (cudaHostGetDevicePointer(&dp, (void*)obs_host, 0) == cudaSuccess) c->hobs_dev = dp;
   }
   (void)cudaGetLastError();
   if (mask_host && c->hobs_dev) {
-    if (cudaHostRegister((void*)mask_host, (size_t)T_full, cudaHostRegisterMapped) == cudaSuccess) {
+    if (cudaHostRegister((void*)mask_host, (size_t)T_full, cudaHostRegisterMapped) == cudaSuccess ||
+        ((void)cudaGetLastError(), cudaHostRegister((void*)mask_host, (size_t)T_full, cudaHostRegisterMapped | cudaHostRegisterReadOnly) == cudaSuccess)) {
       c->h_reg_mask = 1;
       void* dp = nullptr;
       if (cudaHostGetDevicePointer(&dp, (void*)mask_host, 0) == cudaSuccess) c->hmask_dev = (const uint8_t*)dp;
@@ -1397,6 +1402,9 @@ static void sg_teardown(svihmm_ctx* c) {
     if (c->sg_src[i]) cudaFree(c->sg_src[i]);
     if (c->sg_dense[i]) cudaFree(c->sg_dense[i]);
     if (c->sg_pin_starts[i]) cudaFreeHost(c->sg_pin_starts[i]);
+    if (c->sg_pin_obs[i]) cudaFreeHost(c->sg_pin_obs[i]);
+    if (c->sg_pin_mask[i]) cudaFreeHost(c->sg_pin_mask[i]);
+    c->sg_pin_obs[i] = nullptr; c->sg_pin_mask[i] = nullptr; c->sg_pin_rows[i] = 0;
     cudaEventDestroy(c->ev_gathered[i]); cudaEventDestroy(c->ev_consumed[i]);
   }
   cudaEventDestroy(c->ev_stats); cudaEventDestroy(c->ev_read);
@@ -1433,6 +1441,31 @@ static int sg_gather(svihmm_ctx* c, int s, const int64_t* starts_host, int B, in
   const bool has_mask = c->hmask != nullptr;
   memcpy(c->sg_pin_starts[s], starts_host, sizeof(int64_t) * B);
   PhaseTimer pt(c, PH_GATHER, q);
+  if (!c->hobs_dev) {
+    // the series could not be page-locked (e.g. a memmap larger than host memory): the CPU gathers the
+    // windows into pinned staging of this slot (page faults served by the OS), one H2D copy per table
+    const size_t rows = (size_t)B * T;
+    if (rows > c->sg_pin_rows[s]) {
+      if (c->sg_pin_obs[s]) CU(cudaFreeHost(c->sg_pin_obs[s]));
+      if (c->sg_pin_mask[s]) CU(cudaFreeHost(c->sg_pin_mask[s]));
+      c->sg_pin_obs[s] = nullptr; c->sg_pin_mask[s] = nullptr; c->sg_pin_rows[s] = 0;
+      CU(cudaMallocHost(&c->sg_pin_obs[s], rows * rowbytes + sizeof(int64_t) * B));
+      CU(cudaMallocHost((void**)&c->sg_pin_mask[s], rows));
+      c->sg_pin_rows[s] = rows;
+    }
+    for (int b = 0; b < B; ++b) {
+      memcpy((uint8_t*)c->sg_pin_obs[s] + (size_t)b * T * rowbytes, (const uint8_t*)c->hobs + (size_t)starts_host[b] * rowbytes,
+             (size_t)T * rowbytes);
+      if (has_mask) memcpy(c->sg_pin_mask[s] + (size_t)b * T, c->hmask + starts_host[b], (size_t)T);
+    }
+    int64_t* ds = (int64_t*)((uint8_t*)c->sg_pin_obs[s] + rows * rowbytes);
+    for (int b = 0; b < B; ++b) ds[b] = (int64_t)b * T;
+    CU(cudaMemcpyAsync(c->sg_obs[s], c->sg_pin_obs[s], rows * rowbytes, cudaMemcpyHostToDevice, q));
+    if (has_mask) CU(cudaMemcpyAsync(c->sg_mask[s], c->sg_pin_mask[s], rows, cudaMemcpyHostToDevice, q));
+    CU(cudaMemcpyAsync(c->sg_dense[s], ds, sizeof(int64_t) * B, cudaMemcpyHostToDevice, q));
+    c->sg_valid[s] = 1; c->sg_T[s] = T; c->sg_nB[s] = B;
+    return SVIHMM_OK;
+  }
   // the GPU gathers the windows itself out of the mapped host series (one small persistent kernel)
   CU(cudaMemcpyAsync(c->sg_src[s], c->sg_pin_starts[s], sizeof(int64_t) * B, cudaMemcpyHostToDevice, q));
   const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
@@ -1475,7 +1508,6 @@ static int sg_checks(svihmm_ctx* c, const int64_t* starts_host, int B, int T) {
   if (!c || !starts_host) return fail(SVIHMM_EINVAL, "NULL argument");
   if (B < 1 || T < 1) return fail(SVIHMM_EINVAL, "B (%d) and T (%d) must be >= 1", B, T);
   if (!c->hobs) return fail(SVIHMM_ESTATE, "svihmm_set_series_streamed has not been called");
-  if (!c->hobs_dev) return fail(SVIHMM_EUNSUPPORTED, "the host series could not be page-locked: use svihmm_estep_host");
   return check_windows(c, starts_host, B, T);
 }
 
@@ -1687,6 +1719,30 @@ extern "C" int svihmm_set_tuning(svihmm_ctx* c, int key, int value) {
   switch (key) {
     case SVIHMM_TUNE_B16_MIN_B: c->b16_min_B = value; return SVIHMM_OK;
     case SVIHMM_TUNE_SCAN_MIN_T: c->scan_min_T = value; return SVIHMM_OK;
+    case SVIHMM_TUNE_NO_HOSTREG: c->no_hostreg = value ? 1 : 0; return SVIHMM_OK;
     default: return fail(SVIHMM_EINVAL, "unknown tuning key %d", key);
   }
+}
+
+/* Global part of the variational lower bound (see include/svihmm.h). */
+extern "C" int svihmm_global_bound(svihmm_ctx* c, double* out, int include_init, int loc, void* stream) {
+  if (!c || !out) return fail(SVIHMM_EINVAL, "NULL argument");
+  if (!c->have_globals || !c->have_prior) return fail(SVIHMM_ESTATE, "globals and priors must be set first");
+  if (c->C > 1 && !c->have_mix) return fail(SVIHMM_ESTATE, "svihmm_set_mix_weights has not been called");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  BoundArgs a;
+  a.K = c->K; a.D = c->D; a.KE = c->KE; a.C = c->C; a.kind = c->kind; a.include_init = include_init ? 1 : 0;
+  a.plen = c->plen;
+  a.W = c->W; a.vinit = c->vinit; a.emit = c->emit; a.prior_tran = c->prior_tran; a.prior_init = c->prior_init;
+  a.prior_emit = c->prior_emit; a.omega = c->omega; a.omega_prior = c->omega_prior;
+  a.out = c->rowsum;                                   // scratch double (rewritten by every global step)
+  CU(cudaMemsetAsync(a.out, 0, sizeof(double), st));
+  const size_t smem = c->kind == SVIHMM_EMIT_NIW_FULL ? (2 * (size_t)c->D * c->D + 2 * (size_t)c->D) * sizeof(double) : 0;
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_bound, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_global_bound<<<1 + c->KE + (c->C > 1 ? 1 : 0), 256, smem, st>>>(a);
+  LAUNCHED(c);
+  CU(cudaMemcpyAsync(out, a.out, sizeof(double), loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
 }

@@ -46,6 +46,7 @@ struct svihmm_ctx {
   void* sg_obs[SVIHMM_NSLOT]; uint8_t* sg_mask[SVIHMM_NSLOT]; int64_t* sg_src[SVIHMM_NSLOT]; int64_t* sg_dense[SVIHMM_NSLOT];
   size_t sg_rows[SVIHMM_NSLOT], sg_B[SVIHMM_NSLOT];
   int64_t* sg_pin_starts[SVIHMM_NSLOT];               // pinned copies of the window starts
+  void* sg_pin_obs[SVIHMM_NSLOT]; uint8_t* sg_pin_mask[SVIHMM_NSLOT]; size_t sg_pin_rows[SVIHMM_NSLOT];   // CPU-gather staging (series that cannot be page-locked: read-only memmaps larger than host memory)
   cudaStream_t cstream, dstream;                      // gather / result read-back streams
   cudaEvent_t ev_gathered[SVIHMM_NSLOT], ev_consumed[SVIHMM_NSLOT], ev_stats, ev_read;
   int sg_valid[SVIHMM_NSLOT], sg_T[SVIHMM_NSLOT], sg_nB[SVIHMM_NSLOT], sg_init, sg_ring;
@@ -64,7 +65,7 @@ struct svihmm_ctx {
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
   float *beta_ws, *sb_ws; size_t cap_beta; int last_beta;   // KEEP_LOCALS: normalised backward messages + scale factors
   size_t hostq_cap;
-  float *scan_ops, *scan_bound; size_t cap_scan; int scan_min_T;          // block-parallel scan for long chains (scan16.cuh)
+  float *scan_ops, *scan_bound; size_t cap_scan; int scan_min_T; int no_hostreg;          // block-parallel scan for long chains (scan16.cuh)
   // batched tensor-core path for K <= 16 (batch16.cuh): (rows, 16) float tables, exponents, row maxima
   float *b16_b, *b16_a, *b16_c; int* b16_E; double* b16_mx; size_t cap_b16; int b16_min_B;
   int last_B, last_T, last_fused;

@@ -130,6 +130,18 @@ class EStepEngine(object):
             self._h, _ptr(obs_host), self.hT_full, L.F32 if obs_host.dtype == np.float32 else L.F64,
             _ptr(m)))
 
+    def set_series_memmap(self, fname, T, D=None, mask_host=None, page_lock=True):
+        """The on-disk series of gen_synthetic.generate_data_mmap / read_data_mmap (gen_synthetic.py:158-191:
+        a float64 memmap of shape (T, D)) as the streamed series: windows are gathered per step by
+        prefetch_windows / estep_streamed / svi_step_host, so the series may be larger than HBM.
+        page_lock=False: never page-lock the mapping (series larger than host memory): the CPU gathers
+        each minibatch's windows into pinned staging, the OS pages the file in on demand."""
+        mm = np.memmap(fname, dtype=np.float64, mode="r", shape=(int(T), int(self.OD if D is None else D)))
+        if not page_lock:
+            self.set_tuning(L.TUNE_NO_HOSTREG, 1)
+        self.set_series_streamed(mm, mask_host)
+        return mm
+
     # ------------------------------------------------------------------ parameters
     def set_prior(self, prior_tran, prior_emit, prior_init=None):
         pt, pe = _f64(prior_tran), _f64(prior_emit)
@@ -324,6 +336,13 @@ class EStepEngine(object):
                                         float(bfact_E), int(bool(peers)), self._stream()))
         self._keep["starts_all"] = starts_all
         return stats
+
+    def global_bound(self, include_init=False):
+        """Global part of the lower bound from the device-resident parameters
+        (hmmsgd_metaobs.py:273-296; include_init: + the initial-distribution Dirichlet terms, hmmbase.py:145-199)."""
+        out = np.empty(1)
+        L.check(self.lib.svihmm_global_bound(self._h, _ptr(out), int(bool(include_init)), L.LOC_HOST, self._stream()))
+        return float(out[0])
 
     def set_tuning(self, key, value):
         """svihmm_set_tuning (e.g. L.TUNE_B16_MIN_B: minibatch size from which the batched tensor-core

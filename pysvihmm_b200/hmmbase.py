@@ -248,6 +248,10 @@ class VariationalHMMBase(object, metaclass=abc.ABCMeta):
     def lower_bound(self):
         """hmmbase.py:145-199; the data term lZ = sum_t logsumexp_k lalpha[t] comes from the
         engine (statistics tail)."""
+        return self._ensure_engine().global_bound(include_init=True) + float(np.sum(self._lb_q4))
+
+    def _lower_bound_host(self):
+        """The same from the host copies of the parameters (cross-check of svihmm_global_bound)."""
         self._pull_globals()
         elbo = self._dirichlet_bound(self.prior_init, self.var_init)
         elbo += self._dirichlet_bound(self.prior_tran, self.var_tran)

@@ -128,7 +128,13 @@ class VBHMM(VariationalHMMBase):
         return float(self._last_stats_host["lb_q4"])
 
     def global_lower_bound(self):
-        """hmmsgd_metaobs.py:273-296."""
+        """hmmsgd_metaobs.py:273-296, evaluated on the device from the resident parameters
+        (svihmm_global_bound): no per-iteration read-back of the globals."""
+        return self._ensure_engine().global_bound(include_init=False)
+
+    def _global_lower_bound_host(self):
+        """The same from the host copies of the parameters (the classes' get_vlb); kept as the
+        cross-check of the device kernel."""
         self._pull_globals()
         out = self._dirichlet_bound(self.prior_tran, self.var_tran)
         for k in range(self.K):

@@ -41,6 +41,9 @@ def test_vbhmm_infer_follows_reference_trajectory(name):
     assert _rel(np.array([e.nu_mf for e in hmm.var_emit]), g["g_nu"][-1]) < 1e-4
     assert hmm.cur_mo.i1 == g["w_starts"][-1][-1]
     assert hmm.metaobs_fun is None                      # hmmsgd_metaobs.py:485
+    # hmmsgd_metaobs.py:273-296 on the device against the host classes' formulas (Dirichlet terms follow
+    # the reference line by line; the inverse-Wishart terms are restated on both sides)
+    np.testing.assert_allclose(hmm.global_lower_bound(), hmm._global_lower_bound_host(), rtol=1e-10)
     # per-window call path of the reference: local_update(metaobs) + intermediate_pars
     hmm2 = H.VBHMM(g["obs"].copy(), np.ones(K), np.ones((K, K)), _emit_objs(g, K),
                    metaobs_half=int(g["L"]), mb_sz=int(g["mb_sz"]), mask=g["mask"],
@@ -75,6 +78,7 @@ def test_hmmbatchcd_two_cluster_demo():
     hmm = HCD.VBHMM(obs, np.ones(K), np.ones((K, K)), emit, maxit=20, sts=sts)
     hmm.infer()
     assert hmm.hamming == 0.0
+    np.testing.assert_allclose(hmm.lower_bound(), hmm._lower_bound_host(), rtol=1e-10)     # incl. the initial Dirichlet
     assert len(hmm.elbo_vec) >= 2 and np.all(np.isfinite(hmm.elbo_vec))
     assert np.all(np.diff(hmm.elbo_vec) > -1e-3 * np.abs(hmm.elbo_vec[:-1]))   # CAVI bound does not fall
     assert abs(hmm.var_tran.sum() - (K * K + T - 1)) < 1e-2
@@ -175,6 +179,8 @@ def test_vbhmm_categorical_emissions_follow_oracle_trajectory():
     assert _rel(hmm.var_tran, var_tran) < 1e-4
     assert _rel(np.array([g._alpha_mf for g in hmm.var_emit]), np.array([e["alpha"] for e in emit])) < 1e-4
     assert abs(sum(hmm.var_emit[0].weights) - 1.) < 1e-12
+    # global bound on the device (svihmm_global_bound) against the host classes' formulas
+    np.testing.assert_allclose(hmm.global_lower_bound(), hmm._global_lower_bound_host(), rtol=1e-10)
 
 
 def test_vbhmm_gmm_emissions_follow_oracle_trajectory():
@@ -213,6 +219,7 @@ def test_vbhmm_gmm_emissions_follow_oracle_trajectory():
     assert _rel(np.array([m.weights._alpha_mf for m in hmm.var_emit]), np.array([e["omega"] for e in emit])) < 1e-4
     assert _rel(np.array([g.mu_mf for m in hmm.var_emit for g in m.components]),
                 np.array([g["mu"] for e in emit for g in e["comps"]])) < 1e-4
+    np.testing.assert_allclose(hmm.global_lower_bound(), hmm._global_lower_bound_host(), rtol=1e-10)
 
 
 def _adaptive_problem():
@@ -370,3 +377,27 @@ def test_pred_logprob_matches_oracle():
     ref_full = np.mean(np.logaddexp.reduce(np.log(rf["var_x"][0][mm] + 1e-9) + ll[mm], axis=1))
     got_full = hmm.pred_logprob_full()
     assert abs(got_full - ref_full) < 1e-5 * max(1., abs(ref_full))
+
+
+def test_global_bound_on_device_matches_host_classes():
+    """svihmm_global_bound (hmmsgd_metaobs.py:273-296, hmmbase.py:145-199) for the diagonal model and for
+    full covariances at D = 32 against the host classes' get_vlb + the Dirichlet terms."""
+    from pysvihmm_b200.distributions import DiagonalGaussian, Gaussian
+    from pysvihmm_b200.engine import EStepEngine
+    from pysvihmm_b200.hmmbase import VariationalHMMBase as Base
+    from tests.helpers import make_random_problem, pack_emit_np
+    for K, D, kind in [(5, 7, "niw_diag"), (6, 32, "niw_full")]:
+        p = make_random_problem(seed=K + D, K=K, D=D, T_full=50, kind=kind)
+        prior_init, var_init = 1. + np.random.RandomState(1).rand(K), 0.5 + 3. * np.random.RandomState(2).rand(K)
+        eng = EStepEngine(K, D, kind)
+        eng.set_prior(p["prior_tran"] + 0.3, pack_emit_np(p["prior_emit"]), prior_init)
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]), var_init)
+        cls = DiagonalGaussian if kind == "niw_diag" else Gaussian
+        vlb = sum(cls(mu=e["mu"], sigma=e["sigma"], mu_0=pe["mu"], sigma_0=pe["sigma"], kappa_0=pe["kappa"],
+                      nu_0=pe["nu"], kappa_mf=e["kappa"], nu_mf=e["nu"]).get_vlb()
+                  for e, pe in zip(p["emit"], p["prior_emit"]))
+        tran = Base._dirichlet_bound(None, p["prior_tran"] + 0.3, p["var_tran"])
+        init = Base._dirichlet_bound(None, prior_init, var_init)
+        np.testing.assert_allclose(eng.global_bound(False), tran + vlb, rtol=1e-10)
+        np.testing.assert_allclose(eng.global_bound(True), tran + init + vlb, rtol=1e-10)
+        eng.close()

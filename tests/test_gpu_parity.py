@@ -587,6 +587,43 @@ def test_svi_run_equals_step_by_step(K, D, kind):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("page_lock", [True, False])
+def test_memmap_series_streamed_equals_resident(tmp_path, page_lock):
+    """gen_synthetic.read_data_mmap's on-disk series (gen_synthetic.py:158-191) as the streamed series:
+    read-only mapping page-locked and gathered by the GPU, or (page_lock=False, for files larger than host
+    memory) gathered by the CPU into pinned staging; both follow the resident-series trajectory."""
+    from pysvihmm_b200 import _lib as L
+    K, D, T, B, n, Tf = 6, 4, 48, 13, 4, 3000
+    p = make_random_problem(seed=31, K=K, D=D, T_full=Tf, kind="niw_full", miss=0.05)
+    fname = str(tmp_path / "obs.dat")
+    mm = np.memmap(fname, dtype="float64", mode="w+", shape=(Tf, D))
+    mm[:] = p["obs"]; mm.flush(); del mm
+    starts = np.random.RandomState(3).randint(0, Tf - T + 1, (n, B))
+    flags = L.WRAP | L.ADD_PRIOR
+
+    def fresh():
+        eng = _engine(K, D, "niw_full")
+        eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+        eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+        return eng
+    ref = fresh(); ref.set_series(p["obs"], p["mask"], dtype="f64")
+    ref_stats = []
+    for i in range(n):
+        _, st = ref.estep(starts[i], T, flags=flags, want_var_x=False)
+        ref_stats.append(st.cpu().numpy())
+        ref.global_update(st, (i + 1.) ** -0.7, 2.0, 1.5)
+    ref_glob = ref.get_globals(); ref.close()
+    eng = fresh()
+    eng.set_series_memmap(fname, Tf, D, mask_host=p["mask"], page_lock=page_lock)
+    for i in range(n):
+        sh = eng.svi_step_host(starts[i], T, (i + 1.) ** -0.7, 2.0, 1.5, next_starts=starts[i + 1] if i + 1 < n else None,
+                               flags=flags)
+        np.testing.assert_allclose(sh, ref_stats[i], rtol=1e-9, atol=1e-9)
+    for a, b in zip(eng.get_globals(), ref_glob):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12)
+    eng.close()
+
+
 def test_error_paths():
     from pysvihmm_b200 import SvihmmError
     eng = _engine(3, 2)
