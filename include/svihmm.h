@@ -253,6 +253,13 @@ int svihmm_svi_run(svihmm_ctx* ctx, const int64_t* starts_all, int nsteps, int B
  * hmmbase.py:145-199).  The data term is the statistics tail [sum logZ, sum Q4] of the E-step. */
 int svihmm_global_bound(svihmm_ctx* ctx, double* out, int include_init, int loc, void* stream);
 
+/* Health check of the device-resident parameters; synchronises.  SVIHMM_ESTATE (and the flag is cleared)
+ * if a global step met a non-positive pivot / variance in an emission scale: the emission statistics are
+ * accumulated from float32 products (the reference's util.NIW_suffstats is float64), so for a series whose
+ * mean is far from zero in units of its spread (|mean| / std >~ 1e3) Sigma = eta3 - kappa mu mu^T cancels.
+ * Centre such a series before handing it over. */
+int svihmm_check(svihmm_ctx* ctx, void* stream);
+
 /* Tuning knobs.  SVIHMM_TUNE_B16_MIN_B: smallest minibatch (windows per call) that takes the batched
  * tensor-core path for K <= 16 diagonal models (sixteen windows per chain warp, batch16.cuh); smaller
  * calls use the one-CTA-per-window pipelined kernel (default 4096: the measured crossover at the c2

@@ -51,6 +51,7 @@ SYMBOLS = {
     "svihmm_get_locals": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "svihmm_svi_run": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _u, _d, _d, _i64, _d, _d, _i, _vp]),
     "svihmm_global_bound": (_i, [_vp, _vp, _i, _i, _vp]),
+    "svihmm_check": (_i, [_vp, _vp]),
     "svihmm_set_tuning": (_i, [_vp, _i, _i]),
     "svihmm_get_locals_beta": (_i, [_vp, _vp, _vp, _i, _vp]),
     "svihmm_ffbs": (_i, [_vp, _vp, _i64, _i, _i, C.c_uint64, _vp, _i, _vp]),

@@ -127,6 +127,7 @@ static int create_impl(svihmm_ctx** out, int device, int K, int D, int kind, int
   CU(dalloc(&c->par2, 2 * KE * D)); CU(dalloc(&c->ckp, KE));
   CU(dalloc(&c->Rs, rs)); CU(dalloc(&c->gk, KE * D)); CU(dalloc(&c->ck, KE));
   CU(dalloc(&c->stage_stats, c->slen));
+  CU(dalloc(&c->status_dev, (size_t)1)); CU(cudaMemset(c->status_dev, 0, sizeof(int)));
   *out = c;
   return SVIHMM_OK;
 }
@@ -159,7 +160,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
                   c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->beta_ws, c->sb_ws,
-                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
+                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->status_dev, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -282,6 +283,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
   ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
   ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
+  ga.status = c->status_dev;
   ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck; ga.par2 = c->par2; ga.ckp = c->ckp;
   const int KE = c->KE;
   if (c->C > 1 && mode != GM_PREP && mode != GM_SVI) return fail(SVIHMM_EUNSUPPORTED, "mixture emissions support the SVI update only");
@@ -1744,5 +1746,21 @@ extern "C" int svihmm_global_bound(svihmm_ctx* c, double* out, int include_init,
   LAUNCHED(c);
   CU(cudaMemcpyAsync(out, a.out, sizeof(double), loc == SVIHMM_LOC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
   if (loc == SVIHMM_LOC_HOST) CU(cudaStreamSynchronize(st));
+  return SVIHMM_OK;
+}
+
+/* Health of the device-resident parameters (see include/svihmm.h). */
+extern "C" int svihmm_check(svihmm_ctx* c, void* stream) {
+  if (!c) return fail(SVIHMM_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int flags = 0;
+  CU(cudaMemcpyAsync(&flags, c->status_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (flags & 1) {
+    CU(cudaMemsetAsync(c->status_dev, 0, sizeof(int), st));
+    return fail(SVIHMM_ESTATE, "an emission scale matrix lost positive definiteness in a global step: the float32 "
+                "statistics cancel when |mean| >> spread (centre the series, or use a float64 series with the per-phase kernels)");
+  }
   return SVIHMM_OK;
 }

@@ -38,6 +38,7 @@ struct GlobalArgs {
   double *Rs, *gk, *ck;
   long long* dbg;                           // optional clock64 stamps (debug)
   double *par2, *ckp;                       // diagonal, fused-kernel form: [d][k] (-Rs, 2 Rs mu) and ck - sum Rs mu^2
+  int* status;                              // bit 0: a scale matrix lost positive definiteness (see svihmm_check)
 };
 
 // The global-step kernel runs each code path once per launch, so its time is dominated by cold
@@ -443,6 +444,9 @@ __device__ void global_emit_full_block(const GlobalArgs& a, const int k, double*
       double s = L[j * D + j];
 #pragma unroll 1
       for (int q = 0; q < j; ++q) s -= L[j * D + q] * L[j * D + q];
+      // sigma = eta3 - kappa mu mu^T cancels when |mean| >> spread and the float32 statistics lose the
+      // variance: flag it instead of propagating NaN silently (svihmm_check)
+      if (!(s > 0.0)) { atomicOr(a.status, 1); s = 1e-300; }
       L[j * D + j] = sqrt(s);
     }
     __syncthreads();
@@ -522,6 +526,7 @@ __device__ void global_emit_diag_block(const GlobalArgs& a, const int blk, const
       }
     }
     if (a.mode != GM_PREP) { p[d] = mu; p[D + d] = sg; p[2 * D + d] = ka; p[3 * D + d] = nu; }
+    if (!(sg > 0.0)) atomicOr(a.status, 1);                // variance lost to cancellation (see svihmm_check)
     // ll = ck - sum_d Rs (x_d - mu_d)^2 with Rs = nu / (2 sigma)
     const double rs = nu / (2.0 * sg);
     a.Rs[e] = rs;

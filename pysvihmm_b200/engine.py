@@ -155,7 +155,12 @@ class EStepEngine(object):
         vi = None if var_init is None else _f64(var_init)
         L.check(self.lib.svihmm_set_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
 
+    def check(self):
+        """svihmm_check: raises SvihmmError if a global step lost an emission scale to cancellation."""
+        L.check(self.lib.svihmm_check(self._h, self._stream()))
+
     def get_globals(self):
+        self.check()
         vt = np.empty((self.K, self.K)); vi = np.empty(self.K); em = np.empty((self.KE, self.plen))
         L.check(self.lib.svihmm_get_globals(self._h, _ptr(vt), _ptr(vi), _ptr(em), L.LOC_HOST, self._stream()))
         return vt, vi, em

@@ -624,6 +624,29 @@ def test_memmap_series_streamed_equals_resident(tmp_path, page_lock):
     eng.close()
 
 
+def test_uncentred_series_is_flagged_not_silent():
+    """the emission statistics are float32 products, so a series with |mean| >> std loses its
+    variance in eta3 - kappa mu mu^T; the global step flags the non-positive scale (svihmm_check /
+    get_globals raise) instead of handing back NaN silently.  The same series centred works."""
+    from pysvihmm_b200 import SvihmmError, _lib as L
+    K, D, T, B = 3, 2, 64, 20
+    p = make_random_problem(seed=5, K=K, D=D, T_full=2000, kind="niw_full", miss=0.0, sep=1.0)
+    starts = np.random.RandomState(1).randint(0, 2000 - T + 1, B)
+    for shift, ok in [(0.0, True), (3e4, False)]:
+        eng = _engine(K, D)
+        eng.set_series(p["obs"] + shift, None, dtype="f32")
+        eng.set_prior(p["prior_tran"], pack_emit_np([dict(e, mu=e["mu"] + shift) for e in p["prior_emit"]]))
+        eng.set_globals(p["var_tran"], pack_emit_np([dict(e, mu=e["mu"] + shift) for e in p["emit"]]))
+        _, st = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR, want_var_x=False)
+        eng.global_update(st, 0.9, 30.0, 30.0)
+        if ok:
+            eng.get_globals()
+        else:
+            with pytest.raises(SvihmmError):
+                eng.get_globals()
+        eng.close()
+
+
 def test_error_paths():
     from pysvihmm_b200 import SvihmmError
     eng = _engine(3, 2)
