@@ -160,7 +160,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
                   c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->beta_ws, c->sb_ws,
-                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->status_dev, c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
+                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->status_dev, c->acc_stats[0], c->acc_stats[1], c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -270,7 +270,7 @@ static int comm_blocks(const svihmm_ctx* c) {
   return 1 + nblk + (c->C > 1 ? 1 : 0);
 }
 static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate, double bA, double bE,
-                      cudaStream_t st, bool peers = false) {
+                      cudaStream_t st, bool peers = false, double* zero_buf = nullptr) {
   const int K = c->K, D = c->D;
   GlobalArgs ga;
   ga.K = K; ga.D = D; ga.DD = c->DD; ga.diag = c->kind == SVIHMM_EMIT_NIW_DIAG; ga.cat = c->kind == SVIHMM_EMIT_CATEGORICAL; ga.mode = mode;
@@ -283,7 +283,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   ga.stats = stats ? stats : c->stage_stats;      // unused in GM_PREP
   ga.lrate = lrate; ga.bA = bA; ga.bE = bE;
   ga.gth = c->lu; ga.rowsum = c->rowsum; ga.ckc = c->ckc;
-  ga.status = c->status_dev;
+  ga.status = c->status_dev; ga.zero_buf = zero_buf;
   ga.Pt = c->Pt; ga.PtT = c->PtT; ga.pi0 = c->pi0; ga.Rs = c->Rs; ga.gk = c->gk; ga.ck = c->ck; ga.par2 = c->par2; ga.ckp = c->ckp;
   const int KE = c->KE;
   if (c->C > 1 && mode != GM_PREP && mode != GM_SVI) return fail(SVIHMM_EUNSUPPORTED, "mixture emissions support the SVI update only");
@@ -306,7 +306,17 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
     // K*K digamma threads + one warp for the stationary vector
     // K*K digamma threads + one warp for the stationary vector
     const int nthr = std::min(512, ((K * K + 31) / 32) * 32 + 32);
-    k_global_step<<<1 + nblk + (c->C > 1 ? 1 : 0), std::max(nthr, 128), smem, st>>>(ga, nblk);
+    if (c->pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(1 + nblk + (c->C > 1 ? 1 : 0)); cfg.blockDim = dim3(std::max(nthr, 128));
+      cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CU(cudaLaunchKernelEx(&cfg, k_global_step, ga, nblk));
+    } else {
+      k_global_step<<<1 + nblk + (c->C > 1 ? 1 : 0), std::max(nthr, 128), smem, st>>>(ga, nblk);
+    }
     LAUNCHED(c);
   }
   if (gdbg) {
@@ -427,10 +437,18 @@ static cudaError_t launch_fused(const FusedArgs& fa, size_t smem, cudaStream_t s
 }
 
 template <int KP, int NTE>
-static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st, bool set_attr) {
+static cudaError_t launch_pipe(const FusedArgs& fa, size_t smem, cudaStream_t st, bool set_attr, bool pdl = false) {
   if (set_attr) {
     cudaError_t e = cudaFuncSetAttribute(k_estep_pipe<KP, NTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+  }
+  if (pdl) {                 // svihmm_svi_run: the prologue may overlap the preceding update kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(fa.B); cfg.blockDim = dim3(FP_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_estep_pipe<KP, NTE>, fa);
   }
   k_estep_pipe<KP, NTE><<<fa.B, FP_NT, smem, st>>>(fa);
   return cudaGetLastError();
@@ -477,7 +495,8 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
     c->cap_B = B;
   }
   PhaseTimer pt(c, PH_FUSED, st);
-  CU(cudaMemsetAsync(stats_out, 0, sizeof(double) * c->slen, st));
+  const bool pdl = pipe && c->pdl;      // svihmm_svi_run: the accumulator was zeroed by the previous update kernel
+  if (!pdl) CU(cudaMemsetAsync(stats_out, 0, sizeof(double) * c->slen, st));
   FusedArgs fa;
   fa.B = B; fa.T = T; fa.K = K; fa.D = D; fa.DD = c->DD;
   fa.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
@@ -498,10 +517,10 @@ static int estep_fused(svihmm_ctx* c, const void* obs, int dtype, const uint8_t*
     const bool wide = pipe_nte(c) > 3;                  // 8 < D <= 16
     switch (c->KP) {
       case 2:
-      case 4: e = wide ? launch_pipe<4, 5>(fa, smem, st, set_attr) : launch_pipe<4, 3>(fa, smem, st, set_attr); break;
-      case 8: e = wide ? launch_pipe<8, 5>(fa, smem, st, set_attr) : launch_pipe<8, 3>(fa, smem, st, set_attr); break;
-      case 16: e = wide ? launch_pipe<16, 5>(fa, smem, st, set_attr) : launch_pipe<16, 3>(fa, smem, st, set_attr); break;
-      default: e = launch_pipe<32, 3>(fa, smem, st, set_attr); break;
+      case 4: e = wide ? launch_pipe<4, 5>(fa, smem, st, set_attr, pdl) : launch_pipe<4, 3>(fa, smem, st, set_attr, pdl); break;
+      case 8: e = wide ? launch_pipe<8, 5>(fa, smem, st, set_attr, pdl) : launch_pipe<8, 3>(fa, smem, st, set_attr, pdl); break;
+      case 16: e = wide ? launch_pipe<16, 5>(fa, smem, st, set_attr, pdl) : launch_pipe<16, 3>(fa, smem, st, set_attr, pdl); break;
+      default: e = launch_pipe<32, 3>(fa, smem, st, set_attr, pdl); break;
     }
   } else {
     switch (c->KP) {
@@ -1706,6 +1725,29 @@ extern "C" int svihmm_svi_run(svihmm_ctx* c, const int64_t* starts_all, int nste
   if (peers && c->comm_world < 2) return fail(SVIHMM_ESTATE, "svihmm_comm_attach has not been called with world >= 2");
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
+  size_t fsmem = 0;
+  static const bool no_pdl = getenv("SVIHMM_NO_PDL") != nullptr;          // A/B switch, read once
+  if (!no_pdl && !c->profiling && !b16_eligible(c, B, flags) && pipe_eligible(c, T, flags, &fsmem)) {
+    // Pipelined kernel: the steps are chained with programmatic dependent launch and no memset node.
+    // E-step i accumulates into acc[i & 1]; update i consumes it and zeroes acc[(i + 1) & 1] for E-step
+    // i + 1 (its only writer, which cannot start its atomics before update i has finished).
+    for (int j = 0; j < 2; ++j) {
+      if (!c->acc_stats[j]) CU(dalloc(&c->acc_stats[j], c->slen));
+      CU(cudaMemsetAsync(c->acc_stats[j], 0, sizeof(double) * c->slen, st));
+    }
+    c->pdl = 1;
+    for (int i = 0; i < nsteps && !rc; ++i) {
+      rc = estep_impl(c, c->obs, c->obs_dtype, c->mask, starts_all + (size_t)i * B, B, T, var_x_out,
+                      c->acc_stats[i & 1], flags, st);
+      const double lrate = pow((double)(it0 + i) + tau, -kappa);
+      if (!rc) rc = run_global(c, GM_SVI, c->acc_stats[i & 1], lrate, bA, bE, st, peers != 0, c->acc_stats[(i + 1) & 1]);
+    }
+    c->pdl = 0;
+    if (rc) return rc;
+    // the last step's statistics (with peers: this rank's own; the sums are read with svihmm_get_reduced_stats)
+    CU(cudaMemcpyAsync(stats_out, c->acc_stats[(nsteps - 1) & 1], sizeof(double) * c->slen, cudaMemcpyDeviceToDevice, st));
+    return SVIHMM_OK;
+  }
   for (int i = 0; i < nsteps; ++i) {
     if ((rc = estep_impl(c, c->obs, c->obs_dtype, c->mask, starts_all + (size_t)i * B, B, T, var_x_out, stats_out,
                          flags, st))) return rc;

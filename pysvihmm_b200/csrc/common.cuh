@@ -66,6 +66,8 @@ struct svihmm_ctx {
   float *beta_ws, *sb_ws; size_t cap_beta; int last_beta;   // KEEP_LOCALS: normalised backward messages + scale factors
   size_t hostq_cap;
   float *scan_ops, *scan_bound; size_t cap_scan; int scan_min_T; int no_hostreg;
+  double* acc_stats[2];                                   // svihmm_svi_run: double-buffered E-step accumulators
+  int pdl;                                                // launches carry the programmatic-dependent-launch attribute
   int* status_dev;                                        // device flags raised by the global step (svihmm_check)          // block-parallel scan for long chains (scan16.cuh)
   // batched tensor-core path for K <= 16 (batch16.cuh): (rows, 16) float tables, exponents, row maxima
   float *b16_b, *b16_a, *b16_c; int* b16_E; double* b16_mx; size_t cap_b16; int b16_min_B;

@@ -166,19 +166,25 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)a.obs + (size_t)(s0 + row1) * D * (a.dtype == SVIHMM_F32 ? 4 : 8)));
   }
   // ---- setup: emission constants, barriers -----------------------------------------------------
+  // Programmatic dependent launch (svihmm_svi_run): everything above (window start, L2 prefetch of the
+  // first rows) does not depend on the global parameters and may overlap the update kernel; from here on
+  // the parameters it wrote are read.  They are loaded through L2 (ld.global.cg): a line of the PREVIOUS
+  // step's parameters may still sit in this SM's L1 when the CTA was scheduled before the update finished.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.diag) {
     for (int i = tid; i < KS * D; i += FP_NT) {                 // [d][KS], zero-padded columns
       const int d = i / KS, kk = i - d * KS;
       const bool in = kk < K;
-      parS[2 * i] = in ? a.Rs[2 * (d * K + kk)] : 0.0;
-      parS[2 * i + 1] = in ? a.Rs[2 * (d * K + kk) + 1] : 0.0;
+      parS[2 * i] = in ? __ldcg(a.Rs + 2 * (d * K + kk)) : 0.0;
+      parS[2 * i + 1] = in ? __ldcg(a.Rs + 2 * (d * K + kk) + 1) : 0.0;
     }
-    for (int kk = tid; kk < KS; kk += FP_NT) parS[2 * KS * D + kk] = kk < K ? a.ck[kk] : 0.0;
+    for (int kk = tid; kk < KS; kk += FP_NT) parS[2 * KS * D + kk] = kk < K ? __ldcg(a.ck + kk) : 0.0;
   } else {
     const int np = a.tri + D + 1;
     for (int i = tid; i < K * np; i += FP_NT) {
       const int kk = i / np, p = i - kk * np;
-      parS[i] = p < a.tri ? a.Rs[(size_t)kk * a.tri + p] : (p < a.tri + D ? a.gk[(size_t)kk * D + (p - a.tri)] : a.ck[kk]);
+      parS[i] = p < a.tri ? __ldcg(a.Rs + (size_t)kk * a.tri + p) : (p < a.tri + D ? __ldcg(a.gk + (size_t)kk * D + (p - a.tri)) : __ldcg(a.ck + kk));
     }
   }
   if (tid < nroundsA) mbar_init(barA + tid, NWK);
@@ -197,8 +203,8 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
     unsigned long long col2[KP / 2];
 #pragma unroll
     for (int i = 0; i < KP; i += 2) {
-      const float p0 = (ac && i < K) ? (fw ? __ldg(a.Pt + i * K + j) : __ldg(a.Pt + j * K + i)) : 0.f;
-      const float p1 = (ac && i + 1 < K) ? (fw ? __ldg(a.Pt + (i + 1) * K + j) : __ldg(a.Pt + j * K + i + 1)) : 0.f;
+      const float p0 = (ac && i < K) ? (fw ? __ldcg(a.Pt + i * K + j) : __ldcg(a.Pt + j * K + i)) : 0.f;
+      const float p1 = (ac && i + 1 < K) ? (fw ? __ldcg(a.Pt + (i + 1) * K + j) : __ldcg(a.Pt + j * K + i + 1)) : 0.f;
       col2[i / 2] = pack2(p0, p1);
     }
     // broadcast slots [parity][chain warp][32 lanes]
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(FP_NT, 2) k_estep_pipe(const FusedArgs a) {
     float* op = (fw ? aS : cS) + (size_t)tb * KS + jj;
     int* ep = ES + tb;
     const int de = fw ? 1 : 0;                                   // only the forward chain's exponents are kept
-    const float pi0j = (fw && ac) ? __ldg(a.pi0 + j) : 0.f;
+    const float pi0j = (fw && ac) ? __ldcg(a.pi0 + j) : 0.f;
     mbar_wait(barA, 0);                                          // round 0 of phase A: rows 0.. and T-1..
     PIPE_STAMP(1, 0);
     float v, pend;

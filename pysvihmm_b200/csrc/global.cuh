@@ -39,6 +39,7 @@ struct GlobalArgs {
   long long* dbg;                           // optional clock64 stamps (debug)
   double *par2, *ckp;                       // diagonal, fused-kernel form: [d][k] (-Rs, 2 Rs mu) and ck - sum Rs mu^2
   int* status;                              // bit 0: a scale matrix lost positive definiteness (see svihmm_check)
+  double* zero_buf;                         // non-NULL: slen doubles zeroed by block 0 (the NEXT E-step's accumulator, svihmm_svi_run)
 };
 
 // The global-step kernel runs each code path once per launch, so its time is dominated by cold
@@ -613,6 +614,13 @@ __device__ void global_mix_block(const GlobalArgs& a) {
 // grid: 1 + (diag ? nblk_diag : K) blocks.
 __global__ void __launch_bounds__(512) k_global_step(const GlobalArgs a, const int nblk_emit) {
   extern __shared__ double gsm[];
+  // programmatic dependent launch (svihmm_svi_run): let the next E-step's CTAs be scheduled as soon as
+  // there is room, then wait for the E-step whose statistics this update consumes (both are no-ops for a
+  // plain stream-ordered launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (a.zero_buf && blockIdx.x == 0)
+    for (size_t i = threadIdx.x; i < a.slen; i += blockDim.x) a.zero_buf[i] = 0.0;
   if (a.world > 1 && a.mode != GM_PREP) {
     const size_t KK = (size_t)a.K * a.K, o_n = KK, o_sx = o_n + a.KE, o_sxx = o_sx + (size_t)a.KE * a.D,
                  o_q0 = o_sxx + (size_t)a.KE * a.DD;
