@@ -367,7 +367,10 @@ def run_ours(args, cfg):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None
     if world > 1:
+        from pysvihmm_b200.sharding import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)      # before the host series is allocated (first touch)
         dist.init_process_group("nccl", device_id=dev)
     K, D, T, B, kind = cfg["K"], cfg["D"], cfg["T"], cfg["B"], cfg["kind"]
     obs_host, mus = synthetic_series(K, D, T_FULL, seed=8675309)       # same series on every rank
@@ -646,7 +649,7 @@ def run_ours(args, cfg):
                        "step": "E-step (B windows) + %sglobal natural-gradient update" % (
                            ("" if world == 1 else "NCCL all-reduce of packed statistics + " if px is None else
                             "sum over ranks by P2P pushes over NVLink inside the ")),
-                       "var_x_written": True},
+                       "var_x_written": True, "rank0_numa_node": numa_node},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom[0]) if args.config == "c2" else None, "kernel": dom[0], "kernel_ms": dom_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_estep": alg_bytes,

@@ -725,26 +725,34 @@ static bool tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64
 
 static bool stats_tc_eligible(const svihmm_ctx* c, int T, int dtype, const void* obs, const float* q, int64_t series_rows) {
   static const bool off = getenv("SVIHMM_NO_STATS_TC") != nullptr;       // A/B switch, read once
-  return !off && c->K > 16 && c->K <= 64 && (c->K & 3) == 0 && c->C == 1 && c->D <= 32 && (c->D & 3) == 0 &&
-         c->kind != SVIHMM_EMIT_CATEGORICAL && dtype == SVIHMM_F32 && T >= 32 && ((uintptr_t)obs & 15) == 0 &&
-         ((uintptr_t)q & 15) == 0 && series_rows < (int64_t)0x7fffffff && c->K + 1 + c->D + (c->kind == SVIHMM_EMIT_NIW_DIAG ? c->D : c->D * (c->D + 1) / 2) <= 640 &&
+  const int KEm = c->C > 1 ? c->KE : 0;
+  const int NF = c->K + 1 + c->D + (c->kind == SVIHMM_EMIT_NIW_DIAG ? c->D : c->D * (c->D + 1) / 2);
+  const int N = KEm ? (c->K + KEm + 15) / 16 * 16 : 64;
+  return !off && c->K > 16 && c->K <= 64 && (c->K & 3) == 0 && (KEm & 3) == 0 && N <= 256 && ((NF + 127) / 128) * N <= 512 &&
+         c->D <= 32 && (c->D & 3) == 0 && c->kind != SVIHMM_EMIT_CATEGORICAL && dtype == SVIHMM_F32 && T >= 32 &&
+         ((uintptr_t)obs & 15) == 0 && ((uintptr_t)q & 15) == 0 && series_rows < (int64_t)0x7fffffff && NF <= 640 &&
          tmap_encoder() != nullptr;
 }
 
+// wq: (B*T, KE) component weights q r (mixtures) or nullptr
 static int stats_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, const uint8_t* mask, const int64_t* starts,
-                          int B, int T, const float* q, double* stats_out, unsigned flags, cudaStream_t st) {
+                          int B, int T, const float* q, const float* wq, double* stats_out, unsigned flags, cudaStream_t st) {
   const int K = c->K, D = c->D;
   StcArgs a;
   a.B = B; a.T = T; a.K = K; a.D = D; a.diag = c->kind == SVIHMM_EMIT_NIW_DIAG;
   a.NF = K + 1 + D + (a.diag ? D : D * (D + 1) / 2);
   a.wrap = (flags & SVIHMM_WRAP) ? 1 : 0;
-  a.ntpw = (T + STC_R - 1) / STC_R; a.nmt = (a.NF + 127) / 128;
+  a.KE = wq ? c->KE : 0;
+  a.RT = wq ? 64 : 128;
+  a.N = wq ? (K + a.KE + 15) / 16 * 16 : 64;
+  a.ntpw = (T + a.RT - 1) / a.RT; a.nmt = (a.NF + 127) / 128;
   const int64_t nt = (int64_t)B * a.ntpw;
   if (nt >= (int64_t)0x7fffffff || (int64_t)B * T >= (int64_t)0x7fffffff) return fail(SVIHMM_EUNSUPPORTED, "minibatch too large for the tensor-core statistics");
   a.ntiles = (int)nt;
   a.q = q; a.mask = mask; a.starts = starts;
   const int grid = (int)std::min<int64_t>(148, nt);
-  const size_t need_part = (size_t)grid * K * a.NF;
+  const int Kout = K + a.KE;
+  const size_t need_part = (size_t)grid * Kout * a.NF;
   if (need_part > c->cap_part) {
     if (c->part_ws) CU(cudaFree(c->part_ws));
     c->part_ws = nullptr; c->cap_part = 0;
@@ -752,18 +760,26 @@ static int stats_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, c
     c->cap_part = need_part;
   }
   a.part = c->part_ws;
-  CUtensorMap tm_x, tm_q;
-  if (!tmap_2d_f32(&tm_x, obs, (uint64_t)series_rows, (uint64_t)D, STC_R) ||
-      !tmap_2d_f32(&tm_q, q, (uint64_t)B * T, (uint64_t)K, STC_R + 1))
+  CUtensorMap tm_x, tm_q, tm_w;
+  if (!tmap_2d_f32(&tm_x, obs, (uint64_t)series_rows, (uint64_t)D, a.RT) ||
+      !tmap_2d_f32(&tm_q, q, (uint64_t)B * T, (uint64_t)K, a.RT + 1) ||
+      !tmap_2d_f32(&tm_w, wq ? wq : q, (uint64_t)B * T, (uint64_t)(wq ? a.KE : K), a.RT))
     return fail(SVIHMM_ECUDA, "cuTensorMapEncodeTiled failed");
-  const StcSmem L = stc_layout(K, D);
+  const StcSmem L = stc_layout(K, D, a.KE, a.RT, a.N);
+  const int dyn_max = c->max_smem_optin - 2048;       // the kernel also has ~1 KB of static shared memory
+  if (L.total > (size_t)dyn_max) return fail(SVIHMM_EUNSUPPORTED, "tensor-core statistics: shared memory");
   static bool attr_set = false;
-  if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_set = true; }
-  k_stats_tc<<<grid, STC_NT, L.total, st>>>(tm_x, tm_q, a);
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_stats_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max)); attr_set = true; }
+  k_stats_tc<<<grid, STC_NT, L.total, st>>>(tm_x, tm_q, tm_w, a);
   LAUNCHED(c);
-  k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
-      B, T, K, D, c->DD, a.NF, a.diag, grid, c->part_ws, q, c->seq_ws, c->prior_tran,
-      (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+  if (wq)
+    k_stats_tc_finalize_mix<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+        B, T, K, a.KE, D, c->DD, a.NF, a.diag, grid, c->part_ws, q, c->seq_ws, c->prior_tran,
+        (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
+  else
+    k_stats_sym_finalize<<<(unsigned)((c->slen + 255) / 256), 256, 0, st>>>(
+        B, T, K, D, c->DD, a.NF, a.diag, grid, c->part_ws, q, c->seq_ws, c->prior_tran,
+        (flags & SVIHMM_ADD_PRIOR) ? 1 : 0, stats_out, c->slen);
   LAUNCHED(c);
   return SVIHMM_OK;
 }
@@ -1070,11 +1086,17 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     if ((rc = trim_for_stats())) return rc;
     if (mix) {
       c->last_B = B; c->last_T = T; c->last_fused = 1;
+      if (trim == 0 && stats_tc_eligible(c, Ts, dtype, obs, qs, series_rows)) {
+        // component weights q r, then ONE tensor-core contraction for transitions and component statistics
+        k_mix_weights<<<(unsigned)((R * c->KE + 255) / 256), 256, 0, st>>>(R * c->KE, c->C, qs, c->resp_ws, c->wq_ws);
+        LAUNCHED(c);
+        return stats_tc_phase(c, obs, series_rows, mask, starts_s, B, Ts, qs, c->wq_ws, stats_out, flags, st);
+      }
       return stats_mix(c, obs, dtype, mask, starts_s, B, Ts, qs, T, trim, stats_out, flags, st);
     }
     c->last_B = B; c->last_T = T; c->last_fused = 1;     // no lliks/alpha/cs tables in the classic form
     if (stats_tc_eligible(c, Ts, dtype, obs, qs, series_rows))
-      return stats_tc_phase(c, obs, series_rows, mask, starts_s, B, Ts, qs, stats_out, flags, st);
+      return stats_tc_phase(c, obs, series_rows, mask, starts_s, B, Ts, qs, nullptr, stats_out, flags, st);
     return stats_sym_phase(c, obs, dtype, mask, starts_s, B, Ts, qs, stats_out, flags, st);
   }
   if ((flags & SVIHMM_BF16_DENSE) && K > 64 && K <= 256 && (K & 3) == 0 && !xi && !(flags & SVIHMM_KEEP_LOCALS)) {

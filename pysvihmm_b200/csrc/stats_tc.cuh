@@ -19,31 +19,37 @@
 //   epilogue  tcgen05.ld of the accumulators, one partial [K][NF] per CTA; k_stats_sym_finalize sums the
 //             partials in float64 (deterministic: no atomics anywhere)
 // Only q and the features carry rounding: each to 2^-17 relative, independent across rows.
+// Mixture emissions (BASELINE config 5): the B operand gets KE more columns, the weights q[r][k] r[r][k][c]
+// of the K*C components (a third tensor map), so that one pass yields the transition statistic (feature
+// rows "next q" x state columns) and the component statistics (feature rows [1 | x | xx] x component
+// columns); tiles are 64 rows then, to fit shared memory.
 #pragma once
 #include <cuda.h>
 #include "dense.cuh"
 
-#define STC_R 128
 #define STC_NT 256
-#define STC_N 64
 
 struct StcArgs {
   int B, T, K, D, NF, diag, wrap, ntpw, nmt, ntiles;
+  int KE;                    // mixture components (0: plain emissions)
+  int RT;                    // rows per tile: 128, or 64 with mixture columns
+  int N;                     // columns of the accumulators = MMA N: K (+ KE) rounded up to 16 (64 when plain)
   const float* q; const uint8_t* mask; const int64_t* starts;
-  float* part;               // [gridDim.x][K][NF]
+  float* part;               // [gridDim.x][K + KE][NF]
 };
 
-struct StcSmem { size_t Bh, Bl, A, xs, qst, wrow, qwrap, fa, fb, bars, total; };
-__host__ __device__ inline StcSmem stc_layout(int K, int D) {
+struct StcSmem { size_t Bh, Bl, A, Asz, xs, qst, wst, wrow, qwrap, fa, fb, bars, total; };
+__host__ __device__ inline StcSmem stc_layout(int K, int D, int KE, int RT, int N) {
   StcSmem s;
-  s.Bh = 0; s.Bl = 16384; s.A = 32768;                  // A: [buf][hi, lo] x 32 KB
-  s.xs = s.A + 4 * 32768;
-  s.qst = s.xs + (size_t)STC_R * D * 4;
-  s.qst = (s.qst + 127) & ~(size_t)127;
-  s.wrow = s.qst + (size_t)(STC_R + 1) * K * 4;
-  s.wrow = (s.wrow + 127) & ~(size_t)127;
-  s.qwrap = s.wrow + STC_R * 4;
-  s.fa = s.qwrap + STC_N * 4;
+  const size_t bsz = (size_t)N * RT * 2;                // one B operand (hi or lo)
+  s.Asz = (size_t)128 * RT * 2;                         // one A operand (hi or lo) of one buffer
+  s.Bh = 0; s.Bl = bsz; s.A = 2 * bsz;                  // A: [buf][hi, lo]
+  s.xs = s.A + 4 * s.Asz;
+  s.qst = (s.xs + (size_t)RT * D * 4 + 127) & ~(size_t)127;
+  s.wst = (s.qst + (size_t)(RT + 1) * K * 4 + 127) & ~(size_t)127;
+  s.wrow = (s.wst + (size_t)RT * KE * 4 + 127) & ~(size_t)127;
+  s.qwrap = s.wrow + 128 * 4;
+  s.fa = s.qwrap + 64 * 4;
   s.fb = s.fa + 640;
   s.bars = (s.fb + 640 + 7) & ~(size_t)7;
   s.total = s.bars + 8 * 8 + 1024;                      // + slack for the 1024-byte alignment of the base
@@ -76,14 +82,16 @@ __device__ __forceinline__ void stc_pack(const float (&v)[8], uint4& hi, uint4& 
 }
 
 __global__ void __launch_bounds__(STC_NT, 1)
-k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q, const StcArgs a) {
+k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
+           const __grid_constant__ CUtensorMap tm_w, const StcArgs a) {
   extern __shared__ __align__(1024) uint8_t stc_raw[];
   uint8_t* sm = stc_raw + ((1024u - (dn_smem(stc_raw) & 1023u)) & 1023u);
-  const int K = a.K, D = a.D, T = a.T, NF = a.NF;
-  const StcSmem L = stc_layout(K, D);
+  const int K = a.K, D = a.D, T = a.T, NF = a.NF, KE = a.KE, RT = a.RT, N = a.N;
+  const StcSmem L = stc_layout(K, D, KE, RT, N);
   uint8_t* sBh = sm + L.Bh; uint8_t* sBl = sm + L.Bl; uint8_t* sA = sm + L.A;
   float* xs = reinterpret_cast<float*>(sm + L.xs);
   float* qst = reinterpret_cast<float*>(sm + L.qst);
+  float* wst = reinterpret_cast<float*>(sm + L.wst);
   float* wrow = reinterpret_cast<float*>(sm + L.wrow);
   float* qwrap = reinterpret_cast<float*>(sm + L.qwrap);
   uint8_t* fa = sm + L.fa; uint8_t* fb = sm + L.fb;
@@ -91,6 +99,7 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   unsigned long long* full_q = bars; unsigned long long* full_x = bars + 1;
   unsigned long long* mma_done = bars + 2;              // [2]: the MMAs that read A buffer 0 / 1
   unsigned long long* mma_all = bars + 4;               // all MMAs of a tile (B operand free again)
+  unsigned long long* full_w = bars + 5;                // mixture weights of the tile
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
   // feature table: fa = 255 "next q" column fb; 254 zero row; else value = w * xe[fa] * xe[fb], xe[D] = 1
@@ -107,10 +116,11 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     fa[f] = (uint8_t)ia; fb[f] = (uint8_t)ib;
   }
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(bars + i)) : "memory");
+    for (int i = 0; i < 6; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(bars + i)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
+    if (KE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   }
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dn_smem(&tmem_base)), "r"(512) : "memory");
@@ -121,45 +131,49 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_base;
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(STC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const unsigned qbytes = (unsigned)(STC_R + 1) * K * 4, xbytes = (unsigned)STC_R * D * 4;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const unsigned qbytes = (unsigned)(RT + 1) * K * 4, xbytes = (unsigned)RT * D * 4, wbytes = (unsigned)RT * KE * 4;
+  const int nchunk = RT / 8;                            // 16-byte chunks (8 rows) per operand row
   auto tile_w = [&](const int tau) { return tau / a.ntpw; };
-  auto tile_t0 = [&](const int tau) { return (tau - (tau / a.ntpw) * a.ntpw) * STC_R; };
+  auto tile_t0 = [&](const int tau) { return (tau - (tau / a.ntpw) * a.ntpw) * RT; };
   int tau = blockIdx.x;
   if (tid == 0 && tau < a.ntiles) {
     const int w = tile_w(tau), t0 = tile_t0(tau);
     stc_tma_2d(&tm_q, qst, full_q, 0, w * T + t0, qbytes);
     stc_tma_2d(&tm_x, xs, full_x, 0, (int)(a.starts[w] + t0), xbytes);
+    if (KE) stc_tma_2d(&tm_w, wst, full_w, 0, w * T + t0, wbytes);
   }
   unsigned it = 0, gen = 0;                             // tiles done by this CTA, A-operand generations so far
   for (; tau < a.ntiles; tau += gridDim.x, ++it) {
     const int w = tile_w(tau), t0 = tile_t0(tau);
-    const int nrow = min(STC_R, T - t0);                // real rows of the tile
+    const int nrow = min(RT, T - t0);                   // real rows of the tile
     stc_wait(full_q, it & 1);
+    if (KE) stc_wait(full_w, it & 1);
     if (it > 0) stc_wait(mma_all, (it - 1) & 1);        // the B operand is free again
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- B operand: q^T, hi and lo.  thread = (state n, 4 chunks of 8 rows)
+    // ---- B operand: [q | component weights]^T, hi and lo.  task = (column n, chunk of 8 rows)
     {
-      const int n = tid & 63, cq = tid >> 6;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int c = cq * 4 + c4;
+      for (int task = tid; task < N * nchunk; task += STC_NT) {
+        const int n = task % N, c = task / N;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const int r = 8 * c + j; v[j] = (r < nrow && n < K) ? qst[r * K + n] : 0.f; }
+        for (int j = 0; j < 8; ++j) {
+          const int r = 8 * c + j;
+          v[j] = r < nrow ? (n < K ? qst[r * K + n] : (n < K + KE ? wst[r * KE + (n - K)] : 0.f)) : 0.f;
+        }
         uint4 hi, lo;
         stc_pack(v, hi, lo);
-        const uint32_t off = dn_chunk(n, c, STC_N);
+        const uint32_t off = dn_chunk(n, c, N);
         *reinterpret_cast<uint4*>(sBh + off) = hi; *reinterpret_cast<uint4*>(sBl + off) = lo;
       }
       // the wrap-around partner of the window's last row (quirk Q2): q[w][0]
-      if (tid < STC_N) qwrap[tid] = (a.wrap && tid < K && t0 + STC_R >= T) ? __ldg(a.q + (size_t)w * T * K + tid) : 0.f;
+      if (tid < 64) qwrap[tid] = (a.wrap && tid < K && t0 + RT >= T) ? __ldg(a.q + (size_t)w * T * K + tid) : 0.f;
     }
     // ---- row weights: 0 for masked rows, rows with a NaN, rows past the window end
     stc_wait(full_x, it & 1);
     {
       const int64_t g0 = a.starts[w] + t0;
-      for (int r = wp * 16; r < wp * 16 + 16; ++r) {
+      for (int r = wp * (RT / 8); r < (wp + 1) * (RT / 8); ++r) {
         const bool isn = lane < D ? isnan(xs[r * D + lane]) : false;
         const unsigned any = __ballot_sync(0xffffffffu, isn);
         if (lane == 0) wrow[r] = (r < nrow && !any && !(a.mask && a.mask[g0 + r])) ? 1.f : 0.f;
@@ -169,14 +183,14 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     for (int m = 0; m < a.nmt; ++m, ++gen) {
       const unsigned ab = gen & 1, use = gen >> 1;
       if (use > 0) { stc_wait(mma_done + ab, (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-      uint8_t* Ah = sA + (size_t)ab * 65536; uint8_t* Al = Ah + 32768;
-      // ---- A operand of M-tile m: thread = (feature row fl, 8 chunks of 8 rows)
+      uint8_t* Ah = sA + (size_t)ab * 2 * L.Asz; uint8_t* Al = Ah + L.Asz;
+      // ---- A operand of M-tile m: thread = (feature row fl, half of the chunks of 8 rows)
       {
         const int fl = tid & 127, half = tid >> 7, f = 128 * m + fl;
         const int ka = fa[f], kb = fb[f];
 #pragma unroll 2
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const int c = half * 8 + c8;
+        for (int c8 = 0; c8 < nchunk / 2; ++c8) {
+          const int c = half * (nchunk / 2) + c8;
           float v[8];
           if (ka == 255) {
 #pragma unroll
@@ -210,14 +224,17 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (taun < a.ntiles) {
           // the staging buffers are free once their last readers are past the barrier above: the marginals
           // after M-tile 0 (the "next q" features), the observations after the last M-tile
-          if (m == 0) stc_tma_2d(&tm_q, qst, full_q, 0, tile_w(taun) * T + tile_t0(taun), qbytes);
+          if (m == 0) {
+            stc_tma_2d(&tm_q, qst, full_q, 0, tile_w(taun) * T + tile_t0(taun), qbytes);
+            if (KE) stc_tma_2d(&tm_w, wst, full_w, 0, tile_w(taun) * T + tile_t0(taun), wbytes);
+          }
           if (m == a.nmt - 1) stc_tma_2d(&tm_x, xs, full_x, 0, (int)(a.starts[tile_w(taun)] + tile_t0(taun)), xbytes);
         }
         const uint32_t aAh = dn_smem(Ah), aAl = dn_smem(Al), aBh = dn_smem(sBh), aBl = dn_smem(sBl);
-        const uint32_t dcol = tm + (uint32_t)m * STC_N;
+        const uint32_t dcol = tm + (uint32_t)m * N;
 #pragma unroll 1
-        for (int ks = 0; ks < STC_R / 16; ++ks) {
-          const uint32_t oa = (ks >> 2) * (128 * 128) + (ks & 3) * 32, ob = (ks >> 2) * (STC_N * 128) + (ks & 3) * 32;
+        for (int ks = 0; ks < RT / 16; ++ks) {
+          const uint32_t oa = (ks >> 2) * (128 * 128) + (ks & 3) * 32, ob = (ks >> 2) * (N * 128) + (ks & 3) * 32;
           const uint64_t dah = dn_desc(aAh + oa), dal = dn_desc(aAl + oa), dbh = dn_desc(aBh + ob), dbl = dn_desc(aBl + ob);
           const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -233,27 +250,30 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       }
     }
   }
-  // ---- epilogue: accumulators -> this CTA's partial [K][NF]
+  // ---- epilogue: accumulators -> this CTA's partial [K + KE][NF]
   if (it > 0) stc_wait(mma_all, (it - 1) & 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
-    float* part = a.part + (size_t)blockIdx.x * K * NF;
-    const int quarter = wp & 3, chalf = wp >> 2;
+    const int Kout = K + KE;
+    float* part = a.part + (size_t)blockIdx.x * Kout * NF;
+    const int quarter = wp & 3;
     for (int m = 0; m < a.nmt; ++m) {
-      uint32_t v[32];
-      const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * STC_N + chalf * 32);
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                     "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-                     "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                     "=r"(v[30]), "=r"(v[31]) : "r"(ta) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int f = 128 * m + quarter * 32 + lane;
-      if (f < NF) {
+      for (int cc = wp >> 2; cc < (N + 31) / 32; cc += 2) {       // 32-column chunks, two warps per lane quarter
+        uint32_t v[32];
+        const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * N + cc * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                       "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                       "=r"(v[30]), "=r"(v[31]) : "r"(ta) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int f = 128 * m + quarter * 32 + lane;
+        if (f < NF) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = chalf * 32 + j;
-          if (n < K) part[(size_t)n * NF + f] = it > 0 ? __uint_as_float(v[j]) : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            const int n = cc * 32 + j;
+            if (n < Kout) part[(size_t)n * NF + f] = it > 0 ? __uint_as_float(v[j]) : 0.f;
+          }
         }
       }
     }
@@ -261,4 +281,47 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+}
+
+// partials of k_stats_tc with mixture columns, [z][K + KE][NF] -> packed statistics
+// [ A (K*K) | n (KE) | sx (KE*D) | sxx (KE*DD) | q0 (K) | tail ]: the transition statistic from the state
+// columns x "next q" feature rows, the component statistics from the component columns x emission feature
+// rows (second moments stored as the upper triangle, mirrored here).  Float64 sums, fixed order.
+__global__ void __launch_bounds__(256)
+k_stats_tc_finalize_mix(int B, int T, int K, int KE, int D, int DD, int NF, int diag, int nsplit,
+                        const float* __restrict__ part, const float* __restrict__ q,
+                        const double* __restrict__ seq, const double* __restrict__ prior_tran, int add_prior,
+                        double* __restrict__ out, size_t slen) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= slen) return;
+  const int Kout = K + KE;
+  const size_t o_n = (size_t)K * K, o_sx = o_n + KE, o_sxx = o_sx + (size_t)KE * D,
+               o_q0 = o_sxx + (size_t)KE * DD, o_tail = o_q0 + K;
+  int m = -1, n = 0;
+  double v = 0.0;
+  if (idx < o_n) { m = (int)(idx / K); n = (int)(idx % K); }
+  else if (idx < o_sx) { m = K + (int)(idx - o_n); n = K; }
+  else if (idx < o_sxx) { const size_t e = idx - o_sx; m = K + (int)(e / D); n = K + 1 + (int)(e % D); }
+  else if (idx < o_q0) {
+    const size_t e = idx - o_sxx; m = K + (int)(e / DD);
+    const int c = (int)(e % DD);
+    if (diag) n = K + 1 + D + c;
+    else {
+      int i = c / D, j = c - i * D;
+      if (i > j) { const int tmp = i; i = j; j = tmp; }
+      n = K + 1 + D + i * D - i * (i - 1) / 2 + (j - i);
+    }
+  }
+  if (m >= 0) {
+    for (int z = 0; z < nsplit; ++z) v += (double)part[((size_t)z * Kout + m) * NF + n];
+    if (idx < o_n && add_prior) v += (double)B * (prior_tran[idx] - 1.0);
+  } else if (idx < o_tail) {
+    const int k = (int)(idx - o_q0);
+    for (int b = 0; b < B; ++b) v += (double)q[(size_t)b * T * K + k];
+  } else {
+    const int tt = (int)(idx - o_tail);
+    if (tt < 2) for (int b = 0; b < B; ++b) v += seq[2 * b + tt];
+    else if (tt == 2) v = (double)B;
+  }
+  out[idx] = v;
 }
