@@ -18,6 +18,7 @@
 #include "dense.cuh"
 #include "batch16.cuh"
 #include "stats_tc.cuh"
+#include "emit_tc.cuh"
 #include "scan16.cuh"
 #include "bound.cuh"
 #include <cudaTypedefs.h>
@@ -160,7 +161,7 @@ extern "C" int svihmm_destroy(svihmm_ctx* c) {
                   c->seq_ws, c->b_ws, c->alpha_ws, c->q_ws, c->r_ws, c->part_ws, c->hostq_ws,
                   c->omega, c->omega_prior, c->lw, c->ell_ws, c->resp_ws, c->wq_ws, c->part2_ws,
                   c->qin_ws, c->respin_ws, c->starts_in, c->ada_G, c->beta_ws, c->sb_ws,
-                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->status_dev, c->acc_stats[0], c->acc_stats[1], c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo};
+                  c->b16_b, c->b16_a, c->b16_c, c->b16_E, c->b16_mx, c->scan_ops, c->scan_bound, c->status_dev, c->acc_stats[0], c->acc_stats[1], c->dn_b, c->dn_a, c->dn_r, c->dn_e, c->dn_q16, c->dn_fhi, c->dn_flo, c->etc_blob};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->pin_obs) cudaFreeHost(c->pin_obs);
   if (c->pin_mask) cudaFreeHost(c->pin_mask);
@@ -784,6 +785,99 @@ static int stats_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, c
   return SVIHMM_OK;
 }
 
+// ---- tensor-core emissions (emit_tc.cuh) ---------------------------------------------------------------
+// row-major (rows, cols) float32 matrix, box = (box_rows, cols), hardware swizzle of the 16-byte chunks of a
+// row (cols * 4 = 128 or 64 bytes), out-of-bounds rows read as zero
+static bool tmap_2d_f32_sw(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = cols * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool emit_tc_eligible(const svihmm_ctx* c, int T, int dtype, const void* obs, int64_t series_rows, unsigned flags) {
+  static const bool off = getenv("SVIHMM_NO_EMIT_TC") != nullptr;        // A/B switch, read once
+  const bool mix = c->C > 1;
+  return !off && c->kind == SVIHMM_EMIT_NIW_FULL && (c->D == 16 || c->D == 32) && dtype == SVIHMM_F32 &&
+         ((uintptr_t)obs & 15) == 0 && series_rows < (int64_t)0x7fffffff && T >= 32 &&
+         (mix || (c->K <= 64 && (c->K & 7) == 0 && !(flags & SVIHMM_KEEP_LOCALS))) && tmap_encoder() != nullptr;
+}
+
+// K1 on the tensor cores: b / row maxima (plain emissions) or the component log-likelihoods (mixtures)
+static int emit_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, const uint8_t* mask, const int64_t* starts,
+                         int B, int T, int mask_ll, cudaStream_t st) {
+  const int D = c->D, Ke = c->KE;
+  const bool mix = c->C > 1;
+  const int spw = 32 / D;                               // states per chunk and warpgroup
+  EtcArgs a;
+  a.B = B; a.T = T; a.K = Ke; a.mask_ll = mask_ll; a.zero = 0;
+  a.ntpw = (T + ETC_RT - 1) / ETC_RT;
+  const int64_t nt = (int64_t)B * a.ntpw;
+  if (nt >= (int64_t)0x7fffffff || (int64_t)B * T >= (int64_t)0x7fffffff) return fail(SVIHMM_EUNSUPPORTED, "minibatch too large for the tensor-core emissions");
+  a.ntiles = (int)nt;
+  a.nchunks = ((Ke + 1) / 2 + spw - 1) / spw;
+  a.H = a.nchunks * spw;
+  const size_t need = (size_t)a.nchunks * etc_slot(D);
+  if (need > c->cap_etc) {
+    if (c->etc_blob) CU(cudaFree(c->etc_blob));
+    c->etc_blob = nullptr; c->cap_etc = 0;
+    CU(dalloc(&c->etc_blob, need));
+    c->cap_etc = need;
+  }
+  a.starts = starts; a.mask = mask; a.blob = c->etc_blob; a.ck = c->ck;
+  a.bout = mix ? nullptr : c->b_ws; a.mx = c->mx_ws; a.ll = mix ? c->ell_ws : nullptr;
+  static const bool dbg = getenv("SVIHMM_ETC_DBG") != nullptr;           // timeline probe (scripts/emit_tc_probe.py)
+  static long long* dbg_buf = nullptr;
+  a.dbg = nullptr;
+  if (dbg) {
+    if (!dbg_buf) CU(cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long)));
+    CU(cudaMemsetAsync(dbg_buf, 0, 256 * 8 * sizeof(long long), st));
+    a.dbg = dbg_buf;
+  }
+  CUtensorMap tm_x;
+  if (!tmap_2d_f32_sw(&tm_x, obs, (uint64_t)series_rows, (uint64_t)D, ETC_RT)) return fail(SVIHMM_ECUDA, "cuTensorMapEncodeTiled failed");
+  const EtcSmem L = etc_layout(D, Ke);
+  const int dyn_max = c->max_smem_optin - 1024;
+  if (L.total > (size_t)dyn_max) return fail(SVIHMM_EUNSUPPORTED, "tensor-core emissions: shared memory");
+  const int grid = (int)std::min<int64_t>(148, nt);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_emit_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    CU(cudaFuncSetAttribute(k_emit_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
+    attr_set = true;
+  }
+  if (D == 32) {
+    k_etc_prep<32><<<a.nchunks, ETC_NCOL, 0, st>>>(Ke, a.H, c->Rs, c->gk, c->etc_blob);
+    LAUNCHED(c);
+    k_emit_tc<32><<<grid, ETC_NT, L.total, st>>>(tm_x, a);
+  } else {
+    k_etc_prep<16><<<a.nchunks, ETC_NCOL, 0, st>>>(Ke, a.H, c->Rs, c->gk, c->etc_blob);
+    LAUNCHED(c);
+    k_emit_tc<16><<<grid, ETC_NT, L.total, st>>>(tm_x, a);
+  }
+  LAUNCHED(c);
+  if (dbg) {
+    std::vector<long long> h(256 * 8);
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const long long t0 = h[4];
+    fprintf(stderr, "k_emit_tc timeline (CTA 0, second tile; cycles since the epilogue reached chunk 0)\n"
+                    "chunk  tma_issue  mma_b_ready  mma_stage_free  mma_issued | epi_arrive  epi_tfull  epi_phase1  epi_phase2\n");
+    for (int ch = 0; ch < a.nchunks && ch < 256; ++ch) {
+      fprintf(stderr, "%5d", ch);
+      for (int i = 0; i < 8; ++i) fprintf(stderr, " %10lld%s", h[ch * 8 + i] ? h[ch * 8 + i] - t0 : 0, i == 3 ? " |" : "");
+      fprintf(stderr, "\n");
+    }
+  }
+  return SVIHMM_OK;
+}
+
 // generic statistics contraction (stats.cuh) of a dense (B, T, K) table of marginals
 static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                                const int64_t* starts, int B, int T, const float* q, double* stats_out,
@@ -993,7 +1087,10 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   const int Ke = c->KE;                                   // emission components (= K without mixtures)
   double* ll_out = mix ? c->ell_ws : c->ll_ws;
   float* b_out = mix ? nullptr : c->b_ws;
-  if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {
+  if (emit_tc_eligible(c, T, dtype, obs, series_rows, flags)) {
+    // exact sliced product on tcgen05, float64 square-and-sum epilogue (emit_tc.cuh)
+    if ((rc = emit_tc_phase(c, obs, series_rows, mask, starts, B, T, mask_ll, st))) return rc;
+  } else if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {
     // register-blocked float64 kernel with the row maximum and b = exp(ll - max) fused in
     // (a persistent-grid variant that kept the float64 log-likelihoods in per-CTA scratch slots, so that
     // the 268 MB table of config 3 never reaches HBM, was measured SLOWER: 2.69 ms against 1.87 ms; the

@@ -63,6 +63,7 @@ struct svihmm_ctx {
   int* e_ws;
   float *dn_b, *dn_a, *dn_r; int* dn_e; uint16_t *dn_q16, *dn_fhi, *dn_flo; size_t cap_dn, cap_dnf;   // dense (tcgen05) recursion tables, tile layout
   float *b_ws, *alpha_ws, *q_ws, *r_ws, *part_ws, *hostq_ws;
+  uint8_t* etc_blob; size_t cap_etc;                      // sliced emission factors for k_emit_tc (emit_tc.cuh)
   float *beta_ws, *sb_ws; size_t cap_beta; int last_beta;   // KEEP_LOCALS: normalised backward messages + scale factors
   size_t hostq_cap;
   float *scan_ops, *scan_bound; size_t cap_scan; int scan_min_T; int no_hostreg;
