@@ -804,7 +804,10 @@ static bool tmap_2d_f32_sw(CUtensorMap* tm, const void* base, uint64_t rows, uin
 static bool emit_tc_eligible(const svihmm_ctx* c, int T, int dtype, const void* obs, int64_t series_rows, unsigned flags) {
   static const bool off = getenv("SVIHMM_NO_EMIT_TC") != nullptr;        // A/B switch, read once
   const bool mix = c->C > 1;
-  return !off && c->kind == SVIHMM_EMIT_NIW_FULL && (c->D == 16 || c->D == 32) && dtype == SVIHMM_F32 &&
+  // D = 16 works (k_emit_tc<16>) but does not pay: the float64 kernel's work grows with D^2, this one's with D,
+  // and at D = 16 they meet (BASELINE config 5: 0.89 ms either way)
+  static const bool d16 = getenv("SVIHMM_EMIT_TC_D16") != nullptr;
+  return !off && c->kind == SVIHMM_EMIT_NIW_FULL && (c->D == 32 || (d16 && c->D == 16)) && dtype == SVIHMM_F32 &&
          ((uintptr_t)obs & 15) == 0 && series_rows < (int64_t)0x7fffffff && T >= 32 &&
          (mix || (c->K <= 64 && (c->K & 7) == 0 && !(flags & SVIHMM_KEEP_LOCALS))) && tmap_encoder() != nullptr;
 }
@@ -1441,6 +1444,75 @@ k_gather_windows(int B, int T, int rowbytes, const uint8_t* __restrict__ src, co
   }
   for (size_t b = tid; b < (size_t)B; b += nth) dense_starts[b] = (int64_t)b * T;
 }
+// The same gather on the bulk-copy engine: ONE thread per CTA moves 4 KB pieces host -> shared memory
+// (cp.async.bulk over PCIe, completion on an mbarrier) -> staging buffer (cp.async.bulk shared -> global),
+// two 4 KB slots per CTA (8 KB of shared memory: the CTAs fit beside two E-step CTAs on an SM), 32 CTAs.  46 GB/s with 8 threads in all against 36-44 GB/s for the
+// load/store kernel with 2048 threads (scripts/probes/tma_gather_probe.cu), and no thread slots or issue
+// bandwidth are taken from the E-step kernel running beside it.  Lanes 1..31 gather the mask bytes.
+#define GB_PIECE 4096
+#define GB_SLOTS 2
+#define GB_CTAS 32
+__global__ void __launch_bounds__(32)
+k_gather_bulk(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const uint8_t* __restrict__ msrc,
+              const int64_t* __restrict__ starts, uint8_t* __restrict__ dst, uint8_t* __restrict__ mdst,
+              int64_t* __restrict__ dense_starts) {
+  __shared__ __align__(128) uint8_t ring[GB_SLOTS * GB_PIECE];
+  __shared__ __align__(8) unsigned long long full[GB_SLOTS];
+  const size_t wbytes = (size_t)T * rowbytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GB_SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(full + s)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int ppw = (int)((wbytes + GB_PIECE - 1) / GB_PIECE);
+    const long long np = (long long)B * ppw;
+    const int mine = np > (long long)blockIdx.x ? (int)((np - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+    int issued = 0, done = 0;
+    while (done < mine) {
+      while (issued < mine && issued < done + GB_SLOTS) {
+        // slot reuse: every store issued so far has finished READING its slot
+        if (issued >= GB_SLOTS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        const long long p = blockIdx.x + (long long)issued * gridDim.x;
+        const int b = (int)(p / ppw), k = (int)(p - (long long)b * ppw), s = issued % GB_SLOTS;
+        const unsigned nb = (unsigned)min((size_t)GB_PIECE, wbytes - (size_t)k * GB_PIECE);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(full + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(ring + s * GB_PIECE)),
+                       "l"(src + (size_t)starts[b] * rowbytes + (size_t)k * GB_PIECE), "r"(nb), "r"(bar) : "memory");
+        ++issued;
+      }
+      const int s = done % GB_SLOTS; const unsigned par = (done / GB_SLOTS) & 1;
+      unsigned ok = 0;
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(full + s)), "r"(par) : "memory");
+      const long long p = blockIdx.x + (long long)done * gridDim.x;
+      const int b = (int)(p / ppw), k = (int)(p - (long long)b * ppw);
+      const unsigned nb = (unsigned)min((size_t)GB_PIECE, wbytes - (size_t)k * GB_PIECE);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                   ::"l"(dst + (size_t)b * wbytes + (size_t)k * GB_PIECE), "r"((uint32_t)__cvta_generic_to_shared(ring + s * GB_PIECE)), "r"(nb) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      ++done;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    const size_t tid = (size_t)blockIdx.x * 31 + (threadIdx.x - 1), nth = (size_t)gridDim.x * 31;
+    if (msrc) {
+      const size_t total = (size_t)B * T;
+      for (size_t i = tid; i < total; i += nth) { const size_t b = i / T; mdst[i] = msrc[starts[b] + (i - b * T)]; }
+    }
+    for (size_t b = tid; b < (size_t)B; b += nth) dense_starts[b] = (int64_t)b * T;
+  }
+}
+// windows out of the mapped host series: the bulk-copy engine when rows are 16-byte multiples, else loads/stores
+static void launch_gather(int B, int T, int rowbytes, const uint8_t* src, const uint8_t* msrc, const int64_t* starts,
+                          uint8_t* dst, uint8_t* mdst, int64_t* dense_starts, cudaStream_t st) {
+  static const bool zc = getenv("SVIHMM_GATHER_ZEROCOPY") != nullptr;    // A/B switch, read once
+  const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
+  if (vec16 && !zc && ((uintptr_t)dst % 16) == 0)
+    k_gather_bulk<<<GB_CTAS, 32, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts);
+  else
+    k_gather_windows<<<gather_ctas(), 256, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts, vec16);
+}
 
 extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int B, int T,
                                  float* var_x_host, double* stats_host, unsigned flags, void* stream) {
@@ -1473,11 +1545,9 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
   if (c->hobs_dev) {
     // GPU-side gather straight out of the page-locked host series
     CU(cudaMemcpyAsync(c->stage_src, starts_host, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
-    const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
     PhaseTimer pt(c, PH_GATHER, st);
-    k_gather_windows<<<gather_ctas(), 256, 0, st>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
-                                           has_mask ? c->hmask_dev : nullptr, c->stage_src,
-                                           (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, vec16);
+    launch_gather(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev, has_mask ? c->hmask_dev : nullptr, c->stage_src,
+                  (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, st);
     LAUNCHED(c);
   } else {
     // CPU gather into pinned staging, one H2D copy
@@ -1608,10 +1678,8 @@ static int sg_gather(svihmm_ctx* c, int s, const int64_t* starts_host, int B, in
   }
   // the GPU gathers the windows itself out of the mapped host series (one small persistent kernel)
   CU(cudaMemcpyAsync(c->sg_src[s], c->sg_pin_starts[s], sizeof(int64_t) * B, cudaMemcpyHostToDevice, q));
-  const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)c->hobs_dev) % 16 == 0);
-  k_gather_windows<<<gather_ctas(), 256, 0, q>>>(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev,
-                                               has_mask ? c->hmask_dev : nullptr, c->sg_src[s],
-                                               (uint8_t*)c->sg_obs[s], c->sg_mask[s], c->sg_dense[s], vec16);
+  launch_gather(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev, has_mask ? c->hmask_dev : nullptr, c->sg_src[s],
+                (uint8_t*)c->sg_obs[s], c->sg_mask[s], c->sg_dense[s], q);
   LAUNCHED(c);
   c->sg_valid[s] = 1; c->sg_T[s] = T; c->sg_nB[s] = B;
   return SVIHMM_OK;

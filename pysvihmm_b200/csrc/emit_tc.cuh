@@ -109,7 +109,10 @@ k_etc_prep(int K, int H, const double* __restrict__ Rs, const double* __restrict
       __half2 h2 = __halves2half2(dg[s][8 * c8 + 4], dg[s][8 * c8 + 5]), h3 = __halves2half2(dg[s][8 * c8 + 6], dg[s][8 * c8 + 7]);
       pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
       pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(img + dn_chunk(n, c, ETC_NCOL)) = pk;
+      if (D == 32)   // 128 operand rows: row (s & 1) 64 + n holds R_s in the K-half s >> 1 (see etc_mma_chunk32)
+        *reinterpret_cast<uint4*>(img + dn_chunk((s & 1) * ETC_NCOL + n, (s >> 1) * 4 + c8, 2 * ETC_NCOL)) = pk;
+      else
+        *reinterpret_cast<uint4*>(img + dn_chunk(n, c, ETC_NCOL)) = pk;
     }
   cst[0] = (k < K) ? sR * (1.0 / 8589934592.0) : 0.0;       // sR 2^-33 (see etc_combine)
   cst[1] = (k < K) ? gk[(size_t)k * D + i] : 0.0;
@@ -143,6 +146,14 @@ __device__ __forceinline__ void etc_wait_sleep(unsigned long long* bar, const un
     __nanosleep(40);
   }
 }
+// two barriers polled together (their latencies overlap)
+__device__ __forceinline__ void etc_wait2(unsigned long long* b0, const unsigned p0, unsigned long long* b1, const unsigned p1) {
+  unsigned ok = 0;
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p, q;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\tand.pred p, p, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(dn_smem(b0)), "r"(p0), "r"(dn_smem(b1)), "r"(p1) : "memory");
+}
 __device__ __forceinline__ void etc_ld8(const uint32_t ta, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(ta) : "memory");
@@ -152,23 +163,85 @@ __device__ __forceinline__ void etc_ld8(const uint32_t ta, uint32_t (&v)[8]) {
 // W = (512 L0 + L1) 256 + rint((L2 + 2^-9 L3) / 2):  sum_d x_d Rs_cd = sx sR 2^-33 W  (sx = 2^e).
 //   L0, L1 (|.| <= 2^22, exact integers): x + 1.5 * 2^23 has the integer in its mantissa;
 //   L2 + 2^-9 L3 (|.| < 2^23): + 1.5 * 2^24 leaves half of it, rounded - 2^-39 of the leading level;
-//   the 64-bit integer W + 2^23 >= 0 is added to the bit pattern of 1.5 * 2^(52+e) (hi word himag), which
-//   is the float64 number 1.5 * 2^(52+e) + (W + 2^23) 2^e exactly; negmag = -(1.5 * 2^(52+e) + 2^(23+e)).
+//   the 64-bit integer W + 0x4BC00000 (the float bias of the third term is left in) is added to the bit
+//   pattern of 1.5 * 2^(52+e) (hi word himag), which is the float64 number 1.5 * 2^(52+e) + (W + bias) 2^e
+//   exactly; negmag = -(1.5 * 2^(52+e) + bias 2^e), whose bit pattern is (himag, bias).
 // The FP64 pipe of this part does NOT run while tcgen05.mma is executing (scripts/microbench/ubench7.cu:
 // a DFMA loop and an MMA stream take the SUM of their times; FFMA is unaffected), and the MMAs of chunk
 // c + 1 start exactly when the epilogue of chunk c does.  So the epilogue of a chunk is two phases: all the
 // float32 / integer work first (under the MMAs), then all the float64 instructions; a data dependency
-// through the hi-word magic (`hm`) keeps ptxas from interleaving them.
+// through `negmag` keeps ptxas from interleaving them.
 __device__ __forceinline__ void etc_combine(const uint32_t a0, const uint32_t a1, const uint32_t a2, const uint32_t a3,
-                                            uint32_t& whi, uint32_t& wlo) {
+                                            const int himag, uint32_t& whi, uint32_t& wlo) {
   const uint32_t b0 = __float_as_uint(__uint_as_float(a0) + 12582912.f);
   const uint32_t b1 = __float_as_uint(__uint_as_float(a1) + 12582912.f);
   const float tl = fmaf(__uint_as_float(a3), 0.001953125f, __uint_as_float(a2));
-  const uint32_t b2 = __float_as_uint(tl + 25165824.f);
+  const uint32_t b2 = __float_as_uint(tl + 25165824.f);                  // 0x4BC00000 + rint(tl / 2)
   const int M = (int)(b0 * 512u + b1 - 0x4B400000u * 513u);              // 512 L0 + L1 (the biases wrap away)
-  const uint32_t Jp = b2 - (0x4BC00000u - 0x800000u);                    // rint(tl / 2) + 2^23
-  const long long W = (long long)M * 256 + (long long)Jp;
+  // one IMAD.WIDE: the addend carries the hi-word magic and the (still biased) low integer
+  const long long W = (long long)M * 256 + (long long)(((unsigned long long)(uint32_t)himag << 32) | b2);
   whi = (uint32_t)(W >> 32); wlo = (uint32_t)W;
+}
+
+// one tcgen05.mma (float16 in, float32 accumulate); MODE: the A operand's collector use - 0 none, 1 fill (keep
+// for the following MMAs), 2 use (same A again), 3 last use.  A slice of X meets up to four slices of Rs in
+// consecutive MMAs, so it is fetched from shared memory once (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).
+template <int MODE>
+__device__ __forceinline__ void etc_mma(const uint32_t dcol, const uint64_t da, const uint64_t db, const uint32_t idesc, const uint32_t acc) {
+  if (MODE == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+  else if (MODE == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+  else if (MODE == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// all MMAs of one chunk: for every k-step of every slice X_i, the products with R_0 .. R_(3-i) into the level
+// accumulators i .. 3 (element offset e along K -> descriptor address offset, in 16-byte units)
+template <int D, int I, int KSI>
+__device__ __forceinline__ void etc_mma_slice(const uint32_t d0, const uint64_t dA, const uint64_t dB, const uint32_t idesc) {
+  constexpr int ea = I * D + KSI * 16;
+  constexpr uint32_t offA = ((ea >> 6) * (ETC_RT * 128) + (ea & 63) * 2) >> 4;
+  constexpr uint32_t acc = (I > 0 || KSI > 0) ? 1u : 0u;
+  constexpr int n = 4 - I;
+#define ETC_OFFB(J) (uint32_t)(((((J) * D + KSI * 16) >> 6) * (ETC_NCOL * 128) + (((J) * D + KSI * 16) & 63) * 2) >> 4)
+  if (n == 1) etc_mma<0>(d0 + I * ETC_NCOL, dA + offA, dB + ETC_OFFB(0), idesc, acc);
+  else {
+    etc_mma<1>(d0 + I * ETC_NCOL, dA + offA, dB + ETC_OFFB(0), idesc, acc);
+    if (n > 2) etc_mma<2>(d0 + (I + 1) * ETC_NCOL, dA + offA, dB + ETC_OFFB(1), idesc, acc);
+    if (n > 3) etc_mma<2>(d0 + (I + 2) * ETC_NCOL, dA + offA, dB + ETC_OFFB(2), idesc, acc);
+    etc_mma<3>(d0 + (I + n - 1) * ETC_NCOL, dA + offA, dB + ETC_OFFB(n - 1), idesc, acc);
+  }
+#undef ETC_OFFB
+}
+
+// D = 32: the factor operand of a chunk is stacked along N - operand row (j & 1) 64 + n, K-half j >> 1 holds
+// row n of R_j - so that one MMA with N = 128 meets a slice of X with TWO slices of Rs and lands in two
+// adjacent level accumulators: 12 MMAs per chunk (8 with N = 128) instead of 20 with N = 64, which ran at
+// 72 cycles each (44 % of the tensor pipe's rate: the A operand is re-read per 64 columns).
+__device__ __forceinline__ void etc_mma_chunk32(const uint32_t d0, const uint64_t dA, const uint64_t dB) {
+  constexpr uint32_t id128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t id64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t acc0 = ks ? 1u : 0u;
+    // A: slice i at elements [32 i, 32 i + 32) of the 128-element row (two SWIZZLE_128B atoms of 64)
+    const uint64_t a0 = dA + ((0 * 64 + ks * 32) >> 4), a1 = dA + ((1 * 64 + ks * 32) >> 4);
+    const uint64_t a2 = dA + ((ETC_RT * 128 + 0 * 64 + ks * 32) >> 4), a3 = dA + ((ETC_RT * 128 + 1 * 64 + ks * 32) >> 4);
+    // B: K-half h at bytes [64 h, 64 h + 64) of the 128-byte row
+    const uint64_t b0 = dB + ((0 * 64 + ks * 32) >> 4), b1 = dB + ((1 * 64 + ks * 32) >> 4);
+    etc_mma<1>(d0 + 0 * ETC_NCOL, a0, b0, id128, acc0);      // X0 [R0; R1] -> levels 0, 1
+    etc_mma<3>(d0 + 2 * ETC_NCOL, a0, b1, id128, acc0);      // X0 [R2; R3] -> levels 2, 3
+    etc_mma<1>(d0 + 1 * ETC_NCOL, a1, b0, id128, 1u);        // X1 [R0; R1] -> levels 1, 2
+    etc_mma<3>(d0 + 3 * ETC_NCOL, a1, b1, id64, 1u);         // X1 R2       -> level 3
+    etc_mma<0>(d0 + 2 * ETC_NCOL, a2, b0, id128, 1u);        // X2 [R0; R1] -> levels 2, 3
+    etc_mma<0>(d0 + 3 * ETC_NCOL, a3, b0, id64, 1u);         // X3 R0       -> level 3
+  }
 }
 
 template <int D>
@@ -254,7 +327,7 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
       for (int j = 0; j < ntl; ++j) {
         etc_wait_sleep(a_full + (j & 1), (j >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t aA = dn_smem(sA + (size_t)(j & 1) * ASZ);
+        const uint64_t dA = dn_desc(dn_smem(sA + (size_t)(j & 1) * ASZ));
         for (int c = 0; c < nch; ++c, ++g) {
           const unsigned slot = g % ETC_RING, stage = g & 1, use = g >> 1;
           etc_wait_sleep(b_full + slot, (g / ETC_RING) & 1);
@@ -262,22 +335,14 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
           if (use > 0) etc_wait_sleep(t_empty + stage, (use - 1) & 1);
           if (a.dbg && blockIdx.x == 0 && j == 1) a.dbg[c * 8 + 2] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t aB = dn_smem(ring + (size_t)slot * SLOT);
-#pragma unroll
-          for (int l = 0; l < 4; ++l) {
-            const uint32_t dcol = tm + stage * 256u + (uint32_t)l * ETC_NCOL;
-#pragma unroll
-            for (int i = 0; i <= l; ++i) {
-#pragma unroll
-              for (int ks = 0; ks < KS; ++ks) {
-                const int ea = i * D + ks * 16, eb = (l - i) * D + ks * 16;          // element offsets along K
-                const uint64_t da = dn_desc(aA + (ea >> 6) * (ETC_RT * 128) + (ea & 63) * 2);
-                const uint64_t db = dn_desc(aB + (eb >> 6) * (ETC_NCOL * 128) + (eb & 63) * 2);
-                const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-              }
-            }
+          const uint64_t dB = dn_desc(dn_smem(ring + (size_t)slot * SLOT));
+          const uint32_t d0 = tm + stage * 256u;
+          if (D == 32) etc_mma_chunk32(d0, dA, dB);
+          else {
+          etc_mma_slice<D, 0, 0>(d0, dA, dB, idesc); if (KS > 1) etc_mma_slice<D, 0, KS - 1>(d0, dA, dB, idesc);
+          etc_mma_slice<D, 1, 0>(d0, dA, dB, idesc); if (KS > 1) etc_mma_slice<D, 1, KS - 1>(d0, dA, dB, idesc);
+          etc_mma_slice<D, 2, 0>(d0, dA, dB, idesc); if (KS > 1) etc_mma_slice<D, 2, KS - 1>(d0, dA, dB, idesc);
+          etc_mma_slice<D, 3, 0>(d0, dA, dB, idesc); if (KS > 1) etc_mma_slice<D, 3, KS - 1>(d0, dA, dB, idesc);
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(dn_smem(t_full + stage)) : "memory");
           if (a.dbg && blockIdx.x == 0 && j == 1) a.dbg[c * 8 + 3] = clock64();
@@ -349,16 +414,14 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
       // per-row constants of etc_combine: sx = 2^e
       const int e = (int)((__float_as_uint(sx_cur) >> 23) & 0xffu) - 127;
       const int himag = 0x43380000 + (dead ? 0 : e) * 0x100000;
-      const double negmag = -(__hiloint2double(himag, 0) + __hiloint2double((1023 + 23 + (dead ? 0 : e)) << 20, 0));
+      const double negmag = -__hiloint2double(himag, 0x4BC00000);
       const size_t grow = (size_t)w * T + t0 + row;
-      double pm = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < nch; ++c) {
         const unsigned g = (unsigned)j * nch + c, slot = g % ETC_RING, stage = g & 1;
         const bool stamp = a.dbg && blockIdx.x == 0 && j == 1 && tid == 0;
         if (stamp) a.dbg[c * 8 + 4] = clock64();
-        stc_wait(t_full + stage, (g >> 1) & 1);
-        stc_wait(b_full + slot, (g / ETC_RING) & 1);
+        etc_wait2(t_full + stage, (g >> 1) & 1, b_full + slot, (g / ETC_RING) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (stamp) a.dbg[c * 8 + 5] = clock64();
         const double2* cst = reinterpret_cast<const double2*>(ring + (size_t)slot * SLOT + IMG) + wg * 32;
@@ -377,38 +440,33 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            etc_combine(v[cg & 1][0][u], v[cg & 1][1][u], v[cg & 1][2][u], v[cg & 1][3][u], whi[cg * 8 + u], wlo[cg * 8 + u]);
+            etc_combine(v[cg & 1][0][u], v[cg & 1][1][u], v[cg & 1][2][u], v[cg & 1][3][u], himag, whi[cg * 8 + u], wlo[cg * 8 + u]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (stamp) a.dbg[c * 8 + 6] = clock64();
-        // phase 2: float64.  hm depends on every integer of phase 1 (a.zero is 0 at run time)
+        // phase 2: float64.  nm depends on every integer of phase 1 (a.zero is 0 at run time)
         uint32_t dep = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) dep ^= wlo[i];
-        const int hm = himag | (int)(dep & (uint32_t)a.zero);
+        const double nm = __hiloint2double(__double2hiint(negmag), __double2loint(negmag) ^ (int)(dep & (uint32_t)a.zero));
         double acc[SPW][2];
 #pragma unroll
         for (int s = 0; s < SPW; ++s) acc[s][0] = acc[s][1] = 0.0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const double vd = __hiloint2double((int)whi[i] + hm, (int)wlo[i]) + negmag;
+          const double vd = __hiloint2double((int)whi[i], (int)wlo[i]) + nm;
           const double2 cu = cst[i];
           const double y = fma(vd, cu.x, -cu.y);
           acc[i / D][i & 1] = fma(y, y, acc[i / D][i & 1]);
         }
-        // Only now is the stage handed back (the accumulators have been in registers since phase 1): the MMAs
-        // of chunk c + 2 must run under phase 1 of chunk c + 1, not under the float64 phase of this chunk.
-        // The constants have been read: the ring slot is free again.
-        __syncwarp();
-        if (lane == 0) { etc_arrive(t_empty + stage); etc_arrive(b_empty + slot); }
-        if (stamp) a.dbg[c * 8 + 7] = clock64();
-        const int kl = c * SPW, k0 = wg * H + kl;                // this thread's states of the chunk: [k0, k0 + SPW)
+        // this thread's states of the chunk: [k0, k0 + SPW).  Every float64 instruction of the chunk comes
+        // BEFORE the stage is handed back (the stores below are ordered before the arrivals)
+        const int kl = c * SPW, k0 = wg * H + kl;
         if (a.bout) {
 #pragma unroll
           for (int s = 0; s < SPW; ++s) {
             const double vv = k0 + s < K ? (dead ? 0.0 : sck[k0 + s] - (acc[s][0] + acc[s][1])) : -INFINITY;
             myll[(size_t)(wg * 32 + kl + s) * ETC_RT] = vv;
-            pm = fmax(pm, vv);
           }
         } else if (row < nrow) {
           double* lp = a.ll + grow * K + k0;
@@ -416,9 +474,17 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
           for (int s = 0; s < SPW; ++s)
             if (k0 + s < K) lp[s] = dead ? 0.0 : sck[k0 + s] - (acc[s][0] + acc[s][1]);
         }
+        // Only now is the stage handed back (the accumulators have been in registers since phase 1): the MMAs
+        // of chunk c + 2 must run under phase 1 of chunk c + 1, not under the float64 phase of this chunk.
+        // The constants have been read: the ring slot is free again.
+        __syncwarp();
+        if (lane == 0) { etc_arrive(t_empty + stage); etc_arrive(b_empty + slot); }
+        if (stamp) a.dbg[c * 8 + 7] = clock64();
       }
       if (a.bout) {
         // row maximum over both warpgroups, then this thread's H contiguous values of b = exp(ll - max)
+        double pm = -INFINITY;
+        for (int k = 0; k < H; ++k) pm = fmax(pm, myll[(size_t)(wg * 32 + k) * ETC_RT]);
         pmax[wg * ETC_RT + row] = pm;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const double m = fmax(pmax[row], pmax[ETC_RT + row]);

@@ -3,7 +3,7 @@ float64 oracle (scaled-domain form, held to the reference-made fixtures in test_
 
   c2  K16 D8 T512, float32 series, B = 256 and B > CTAs in flight   -> k_estep_pipe (vecx branch) /
                                                                         the batched tensor-core path
-  c3  K64 D32 T1024 full covariance, float32 series, B = 64          -> wide64 kernels
+  c3  K64 D32 T1024 full covariance, float32 series, B = 64          -> k_emit_tc + wide64 kernels + k_stats_tc
   c4  K256 D64 T256 B = 256, SVIHMM_BF16_DENSE                        -> tcgen05 recursion + statistics
   c5  K32 x 4 components D16, T = 256 and T = 2048                    -> mixture path
 
@@ -241,4 +241,53 @@ def test_long_chain_block_parallel_scan(K, D, T, B, kind, keep):
             assert np.isfinite(la).all() and np.isfinite(lb).all()
             np.testing.assert_allclose(la, r["lalpha"][b], rtol=1e-6, atol=2e-5)
             np.testing.assert_allclose(lb, r["lbeta"][b], rtol=1e-6, atol=2e-5)
+    eng.close()
+
+
+@pytest.mark.parametrize("K,T,B,flags_extra", [(64, 300, 5, 0), (40, 129, 3, 0), (24, 515, 4, 4)])
+def test_tensor_core_emissions_edge_cases(K, T, B, flags_extra):
+    """k_emit_tc (exact sliced product on tcgen05, D = 32, float32 series): ragged tiles (T not a multiple of
+    128), a state count that does not fill the chunks (K = 40: 20 states per warpgroup), NaN rows, masked rows
+    with SVIHMM_MASK_LL (flag 4), rows 1e3 times larger / 1e6 times smaller than the rest (per-row scales), an all-zero
+    row, a window ending at the last row of the series.  Marginals against the float64 oracle at 1e-5 and
+    against the engine's float64 emission kernel (which SVIHMM_KEEP_LOCALS keeps) at the float32 noise floor
+    of the recursions."""
+    from oracle import svihmm_oracle as O
+    from pysvihmm_b200 import _lib as L
+    from pysvihmm_b200.engine import EStepEngine
+    D, kind = 32, "niw_full"
+    p = make_random_problem(seed=K * 1000 + T, K=K, D=D, T_full=4000, kind=kind, miss=0.05, sep=0.4)
+    obs = p["obs"].copy()
+    starts = np.random.RandomState(5).randint(0, obs.shape[0] - T + 1, B)
+    starts[0], starts[-1] = 0, obs.shape[0] - T
+    obs[starts[0] + 3] = np.nan
+    obs[starts[0] + 17, 5] = np.nan
+    obs[starts[1] + 40] *= 1e3           # (beyond ~1e4 the REFERENCE's log-domain tables run out of float64 digits)
+    obs[starts[1] + 41] *= 1e-6
+    obs[starts[1] + 42] = 0.0
+    obs[starts[-1] + T - 1, 0] = np.nan
+    obs = obs.astype(np.float32).astype(np.float64)
+    mask = p["mask"] | np.isnan(obs).any(1)              # see _run_case: keeps the oracle's sums finite
+    eng = EStepEngine(K, D, kind)
+    eng.set_series(obs, mask, dtype="f32")
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    fl = L.WRAP | L.ADD_PRIOR | flags_extra
+    n0 = eng.launch_count()
+    vx, stats = eng.estep(starts, T, flags=fl)
+    q = vx.cpu().numpy().copy()
+    s = eng.unpack_stats(stats)
+    vx64, stats64 = eng.estep(starts, T, flags=fl | L.KEEP_LOCALS)
+    q64 = vx64.cpu().numpy()
+    assert np.isfinite(q).all()
+    assert float(np.max(np.abs(q - q64))) < 2e-6
+    if flags_extra == 0:
+        r = O.svi_minibatch_step(obs, mask, starts, T, p["var_tran"], p["emit"], p["prior_tran"],
+                                 p["prior_emit"], 0.37, max(T // 2, 1), wrap=True, scaled=True)
+        assert frac_soft(r["var_x"]) > 0.2, "vacuous parity: posteriors are one-hot"
+        assert_q(q, r["var_x"])
+        np.testing.assert_allclose(s["logZ"], r["logZ"].sum(), rtol=3e-6)
+    s64 = eng.unpack_stats(stats64)
+    for key in ("A", "n", "sx", "sxx"):
+        assert_block(s[key], s64[key], 1e-5, key)
     eng.close()
