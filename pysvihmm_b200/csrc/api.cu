@@ -1114,6 +1114,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
     LAUNCHED(c);
   } else {
+  bool diag_fused_b = false;
   if (c->kind == SVIHMM_EMIT_NIW_FULL) {
     const size_t smem = ((size_t)EMIT_ROWS * D + (size_t)D * (D + 1) / 2 + D) * sizeof(double);
     if (smem > 200 * 1024) return fail(SVIHMM_EUNSUPPORTED, "D = %d too large for the emission kernel", D);
@@ -1122,7 +1123,18 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
         B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out);
   } else {
     size_t smem = 2 * (size_t)Ke * D * sizeof(double);
-    if (smem <= 200 * 1024) {
+    if (Ke >= 32 && (D == 64 || D == 32 || D == 16)) {
+      // register-blocked float64 kernel (row in registers), row maximum and b = exp(ll - max) fused in
+      const unsigned grid = (unsigned)((R + EDR_NT - 1) / EDR_NT);
+#define EDR_LAUNCH(DV) do { \
+      const size_t sm2 = (size_t)2 * EDR_KC * DV * sizeof(double2); \
+      if (sm2 > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag_rb<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); \
+      k_emit_diag_rb<DV><<<grid, EDR_NT, sm2, st>>>(R, T, Ke, obs, dtype, mask, starts, mask_ll, c->par2, c->ckp, \
+                                                     ll_out, b_out, c->mx_ws); } while (0)
+      if (D == 64) EDR_LAUNCH(64); else if (D == 32) EDR_LAUNCH(32); else EDR_LAUNCH(16);
+#undef EDR_LAUNCH
+      diag_fused_b = !mix;
+    } else if (smem <= 200 * 1024) {
       if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_emit_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_emit_diag<<<(unsigned)((R * Ke + 255) / 256), 256, smem, st>>>(
           B, T, Ke, D, obs, dtype, mask, starts, mask_ll, c->Rs, c->gk, c->ck, ll_out, 1);
@@ -1137,7 +1149,7 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     }
   }
   LAUNCHED(c);
-  if (!mix) {
+  if (!mix && !diag_fused_b) {
     k_ll_to_b<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(R, K, c->ll_ws, c->b_ws, c->mx_ws);
     LAUNCHED(c);
   }

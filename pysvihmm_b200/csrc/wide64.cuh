@@ -170,6 +170,103 @@ k_emit_full_rb(int64_t R, int T, int K, const void* __restrict__ obs, int dtype,
   }
 }
 
+// Diagonal emissions for many states (BASELINE config 4: K = 256, D = 64), the counterpart of
+// k_emit_full_rb: thread = observation row with the row in REGISTERS (float64, converted once - the float ->
+// double conversion runs at 16 lanes per clock, and k_emit_diag_tiled paid it per (row, state, d)), the
+// parameters of EDR_KC states at a time in shared memory as (c2, c1) pairs, double buffered with 16-byte
+// cp.async; ll = ck' + sum_d x_d (c2 x_d + c1) in the expanded form of the fused kernels (global.cuh: par2 /
+// ckp), two DFMA per 128-bit broadcast load; the row maximum and b = exp(ll - max) are fused in.
+#define EDR_NT 128
+#define EDR_KC 16
+template <int D>
+__global__ void __launch_bounds__(EDR_NT)
+k_emit_diag_rb(int64_t R, int T, int K, const void* __restrict__ obs, int dtype,
+               const uint8_t* __restrict__ mask, const int64_t* __restrict__ starts, int mask_ll,
+               const double* __restrict__ par2, const double* __restrict__ ckp,
+               double* __restrict__ ll, float* __restrict__ bout, double* __restrict__ mx) {
+  extern __shared__ __align__(16) double esm[];          // [2][EDR_KC][D] double2
+  double2* tiles = reinterpret_cast<double2*>(esm);
+  const int tid = threadIdx.x;
+  const int64_t r = (int64_t)blockIdx.x * EDR_NT + tid;
+  double x[D];
+  bool dead = r >= R;
+  if (!dead) {
+    const int b = (int)(r / T); const int t = (int)(r - (int64_t)b * T);
+    const int64_t gi = starts[b] + t;
+    if (mask_ll && mask && mask[gi]) dead = true;
+    if (dtype == SVIHMM_F32 && (D % 4) == 0 && ((((uintptr_t)obs) & 15) == 0)) {
+      const float4* p = reinterpret_cast<const float4*>((const float*)obs + gi * D);
+#pragma unroll
+      for (int d = 0; d < D; d += 4) { const float4 q = __ldg(p + d / 4); x[d] = q.x; x[d + 1] = q.y; x[d + 2] = q.z; x[d + 3] = q.w; }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) x[d] = ld_obs(obs, dtype, gi * D + d);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) if (isnan(x[d])) dead = true;
+  }
+  if (dead) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = 0.0;
+  }
+  // par2 is [d][K] pairs: the tile of states [kc, kc + EDR_KC) lands as [state][d]
+  auto stage = [&](const int kc, double2* buf) {
+    for (int idx = tid; idx < EDR_KC * D; idx += EDR_NT) {
+      const int d = idx / EDR_KC, s = idx - d * EDR_KC;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + s * D + d);
+      if (kc + s < K)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(par2 + 2 * ((size_t)d * K + kc + s)) : "memory");
+      else buf[s * D + d] = make_double2(0.0, 0.0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0, tiles);
+  double m = -INFINITY;
+  int cur = 0;
+  for (int kc = 0; kc < K; kc += EDR_KC, cur ^= 1) {
+    const double2* tile = tiles + (size_t)cur * EDR_KC * D;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                 // tile kc has landed; everyone is done with the other buffer
+    if (kc + EDR_KC < K) stage(kc + EDR_KC, tiles + (size_t)(cur ^ 1) * EDR_KC * D);
+#pragma unroll 1
+    for (int s = 0; s < EDR_KC; s += 2) {
+      const double2* pa = tile + s * D; const double2* pb = pa + D;
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;           // two states x two partial sums
+#pragma unroll
+      for (int d = 0; d < D; d += 2) {
+        const double2 u0 = pa[d], u1 = pa[d + 1], v0 = pb[d], v1 = pb[d + 1];
+        a0 = fma(x[d], fma(u0.x, x[d], u0.y), a0); a1 = fma(x[d + 1], fma(u1.x, x[d + 1], u1.y), a1);
+        b0 = fma(x[d], fma(v0.x, x[d], v0.y), b0); b1 = fma(x[d + 1], fma(v1.x, x[d + 1], v1.y), b1);
+      }
+      const int k = kc + s;
+      if (k < K) {
+        const double la = dead ? 0.0 : ckp[k] + (a0 + a1);
+        m = fmax(m, la);
+        if (r < R) ll[r * K + k] = la;
+      }
+      if (k + 1 < K) {
+        const double lb = dead ? 0.0 : ckp[k + 1] + (b0 + b1);
+        m = fmax(m, lb);
+        if (r < R) ll[r * K + k + 1] = lb;
+      }
+    }
+  }
+  if (!bout || r >= R) return;                  // mixtures: only the component log-likelihoods are wanted
+  // b = exp(ll - max): this thread re-reads the row it has just written (L1/L2 hits)
+  const double* lp = ll + r * K;
+  float* bp = bout + r * K;
+  if (!(K & 3) && ((((uintptr_t)bout) & 15) == 0)) {
+    for (int k = 0; k < K; k += 4) {
+      const double2 u = *reinterpret_cast<const double2*>(lp + k), v = *reinterpret_cast<const double2*>(lp + k + 2);
+      *reinterpret_cast<float4*>(bp + k) = make_float4(__expf((float)(u.x - m)), __expf((float)(u.y - m)),
+                                                       __expf((float)(v.x - m)), __expf((float)(v.y - m)));
+    }
+  } else {
+    for (int k = 0; k < K; ++k) bp[k] = __expf((float)(lp[k] - m));
+  }
+  mx[r] = m;
+}
+
 // ------------------------------------------------------------------------------------------------
 // recursions: one warp per (window, direction)
 // ------------------------------------------------------------------------------------------------
