@@ -263,7 +263,7 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
   unsigned long long* x_full = bars;                         // observation tile landed (TMA)
   unsigned long long* a_full = bars + 1;                     // [2] A operand written (256 arrivals)
   unsigned long long* b_full = bars + 3;                     // [RING] factor chunk landed
-  unsigned long long* b_empty = bars + 3 + ETC_RING;         // [RING] chunk consumed by the epilogue warps (8 arrivals)
+  unsigned long long* b_empty = bars + 3 + ETC_RING;         // [RING] chunk consumed by the epilogue threads (256 arrivals: every reader of the constants releases its own reads)
   unsigned long long* t_full = bars + 3 + 2 * ETC_RING;      // [2] MMAs of the stage complete (tcgen05.commit)
   unsigned long long* t_empty = t_full + 2;                  // [2] stage read back (8 arrivals)
   __shared__ uint32_t tmem_base;
@@ -278,7 +278,7 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
     }
     for (int i = 0; i < ETC_RING; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dn_smem(b_full + i)) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(dn_smem(b_empty + i)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" ::"r"(dn_smem(b_empty + i)) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
@@ -477,8 +477,9 @@ k_emit_tc(const __grid_constant__ CUtensorMap tm_x, const EtcArgs a) {
         // Only now is the stage handed back (the accumulators have been in registers since phase 1): the MMAs
         // of chunk c + 2 must run under phase 1 of chunk c + 1, not under the float64 phase of this chunk.
         // The constants have been read: the ring slot is free again.
+        etc_arrive(b_empty + slot);
         __syncwarp();
-        if (lane == 0) { etc_arrive(t_empty + stage); etc_arrive(b_empty + slot); }
+        if (lane == 0) etc_arrive(t_empty + stage);
         if (stamp) a.dbg[c * 8 + 7] = clock64();
       }
       if (a.bout) {
