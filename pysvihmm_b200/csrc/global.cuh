@@ -40,6 +40,7 @@ struct GlobalArgs {
   double *par2, *ckp;                       // diagonal, fused-kernel form: [d][k] (-Rs, 2 Rs mu) and ck - sum Rs mu^2
   int* status;                              // bit 0: a scale matrix lost positive definiteness (see svihmm_check)
   double* zero_buf;                         // non-NULL: slen doubles zeroed by block 0 (the NEXT E-step's accumulator, svihmm_svi_run)
+  int gth_ext;                              // the stationary vector is left to k_gth_cluster (gth_cluster.cuh), which follows
 };
 
 // The global-step kernel runs each code path once per launch, so its time is dominated by cold
@@ -360,7 +361,7 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   }
   GSYNC();
   GSTAMP(2);
-  if (!a.user_init && !inwarp) {
+  if (!a.user_init && !inwarp && !a.gth_ext) {
     // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
     gth_block<4>(K, G);
     // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]: column j accumulates as the pi[i] become final
@@ -377,7 +378,8 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
       }
     }
   }
-  if (wp == 0) pi0_section(a.user_init, K, pi, a.vinit, a.pi0, lane, a.dbg && tid == 0 ? a.dbg : nullptr);
+  if (wp == 0 && (a.user_init || inwarp || !a.gth_ext))
+    pi0_section(a.user_init, K, pi, a.vinit, a.pi0, lane, a.dbg && tid == 0 ? a.dbg : nullptr);
   GSTAMP(3);
 }
 
