@@ -20,6 +20,7 @@
 #include "stats_tc.cuh"
 #include "emit_tc.cuh"
 #include "gth_cluster.cuh"
+#include "emit_dense.cuh"
 #include "scan16.cuh"
 #include "bound.cuh"
 #include <cudaTypedefs.h>
@@ -892,6 +893,35 @@ static int emit_tc_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, co
   return SVIHMM_OK;
 }
 
+// ---- tensor-core diagonal emissions of the bf16 dense path (emit_dense.cuh) ---------------------------
+static bool emit_dense_eligible(const svihmm_ctx* c, int T, int dtype, const void* obs, int64_t series_rows, unsigned flags) {
+  static const bool off = getenv("SVIHMM_NO_EMIT_DENSE_TC") != nullptr;   // A/B switch, read once
+  const int K = c->K, D = c->D;
+  if (off || !(flags & SVIHMM_BF16_DENSE) || (flags & (SVIHMM_EXACT_XI | SVIHMM_KEEP_LOCALS)) || c->C > 1) return false;
+  if (c->kind != SVIHMM_EMIT_NIW_DIAG || K <= 64 || K > 256 || (K & 3) || D < 16 || D > 64 || (D & 15)) return false;
+  if (dtype != SVIHMM_F32 || ((uintptr_t)obs & 15) || series_rows >= (int64_t)0x7fffffff || T < 32 || !tmap_encoder()) return false;
+  const int N = (K + 15) / 16 * 16;
+  return edt_layout(D, N).total <= (size_t)c->max_smem_optin;
+}
+static int emit_dense_phase(svihmm_ctx* c, const void* obs, int64_t series_rows, const uint8_t* mask, const int64_t* starts,
+                            int B, int T, int mask_ll, cudaStream_t st) {
+  EdtArgs a;
+  a.B = B; a.T = T; a.K = c->K; a.D = c->D; a.N = (c->K + 15) / 16 * 16; a.mask_ll = mask_ll;
+  a.ntpw = (T + EDT_RT - 1) / EDT_RT;
+  const int64_t nt = (int64_t)B * a.ntpw;
+  if (nt >= (int64_t)0x7fffffff || (int64_t)B * T >= (int64_t)0x7fffffff) return fail(SVIHMM_EUNSUPPORTED, "minibatch too large for the tensor-core emissions");
+  a.ntiles = (int)nt;
+  a.starts = starts; a.mask = mask; a.par2 = c->par2; a.ckp = c->ckp; a.bout = c->b_ws; a.mx = c->mx_ws;
+  CUtensorMap tm_x;
+  if (!tmap_2d_f32(&tm_x, obs, (uint64_t)series_rows, (uint64_t)c->D, EDT_RT)) return fail(SVIHMM_ECUDA, "cuTensorMapEncodeTiled failed");
+  const EdtSmem L = edt_layout(c->D, a.N);
+  static bool attr_set = false;
+  if (!attr_set) { CU(cudaFuncSetAttribute(k_emit_diag_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem_optin)); attr_set = true; }
+  k_emit_diag_tc<<<(int)std::min<int64_t>(148, nt), EDT_NT, L.total, st>>>(tm_x, a);
+  LAUNCHED(c);
+  return SVIHMM_OK;
+}
+
 // generic statistics contraction (stats.cuh) of a dense (B, T, K) table of marginals
 static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* mask,
                                const int64_t* starts, int B, int T, const float* q, double* stats_out,
@@ -1101,7 +1131,10 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
   const int Ke = c->KE;                                   // emission components (= K without mixtures)
   double* ll_out = mix ? c->ell_ws : c->ll_ws;
   float* b_out = mix ? nullptr : c->b_ws;
-  if (emit_tc_eligible(c, T, dtype, obs, series_rows, flags)) {
+  if (emit_dense_eligible(c, T, dtype, obs, series_rows, flags)) {
+    // bf16 dense path: diagonal emissions as one bf16 hi + lo contraction on tcgen05 (emit_dense.cuh)
+    if ((rc = emit_dense_phase(c, obs, series_rows, mask, starts, B, T, mask_ll, st))) return rc;
+  } else if (emit_tc_eligible(c, T, dtype, obs, series_rows, flags)) {
     // exact sliced product on tcgen05, float64 square-and-sum epilogue (emit_tc.cuh)
     if ((rc = emit_tc_phase(c, obs, series_rows, mask, starts, B, T, mask_ll, st))) return rc;
   } else if (c->kind == SVIHMM_EMIT_NIW_FULL && (D == 8 || D == 16 || D == 32)) {

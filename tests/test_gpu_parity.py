@@ -145,6 +145,24 @@ def test_stationary_init_matches_reference():
     eng.close()
 
 
+@pytest.mark.parametrize("K", [40, 64, 100, 256, 300])
+def test_stationary_init_large_K_matches_oracle(K):
+    """The same vector for K > 32: one-CTA GTH elimination (K <= 64) and the cluster kernel with the matrix in
+    distributed shared memory (64 < K <= 384, gth_cluster.cuh) against the oracle's eig-based restatement of
+    hmmsgd_metaobs.py:413-418, for a sticky and for a nearly uniform transition matrix."""
+    from oracle import svihmm_oracle as O
+    rs = np.random.RandomState(K)
+    D = 2
+    emit = emit_list(rs.randn(K, D), np.tile(np.eye(D)[None], (K, 1, 1)), np.ones(K), (D + 3.) * np.ones(K))
+    for var_tran in (1. + 5. * rs.rand(K, K), 0.05 + rs.rand(K, K) + 40. * np.eye(K)):
+        eng = _engine(K, D)
+        eng.set_globals(var_tran, pack_emit_np(emit))
+        _, vi, _ = eng.get_globals()
+        np.testing.assert_allclose(vi, O.stationary_init(var_tran), rtol=1e-9)
+        assert abs(np.linalg.norm(vi) - 1.0) < 1e-12
+        eng.close()
+
+
 def test_batch_cavi_matches_reference_golden():
     """hmmbatchcd.VBHMM.infer iterations (hmmbatchcd.py:135-141,172-189) on device."""
     g = load_golden("cavi_k2_d2_t200")
