@@ -16,6 +16,7 @@
 #include "wide64.cuh"
 #include "ffbs.cuh"
 #include "dense.cuh"
+#include "dense_cluster.cuh"
 #include "batch16.cuh"
 #include "stats_tc.cuh"
 #include "emit_tc.cuh"
@@ -1276,8 +1277,18 @@ static int estep_impl(svihmm_ctx* c, const void* obs, int dtype, const uint8_t* 
     { PhaseTimer pt(c, PH_FORWARD, st);
       k_dense_tile_b<<<dim3(T, tiles), 256, 0, st>>>(B, T, K, c->b_ws, c->dn_b);
       LAUNCHED(c);
-      k_chain_dense<<<dim3(tiles, 2), DN_M * DN_NS, smem, st>>>(B, T, K, KPd, c->PtT, c->Pt, c->pi0, c->dn_b,
-                                                       c->dn_a, c->dn_r, c->dn_e);
+      static const bool no_cl = getenv("SVIHMM_NO_DENSE_CLUSTER") != nullptr;    // A/B switch, read once
+      if (KPd == DNC_KP && !no_cl) {
+        // N split over a cluster of 4 CTAs, carried vector exchanged through distributed shared memory
+        const size_t smc = 2 * (size_t)DN_M * DNC_KP * 2 + (size_t)DNC_NS * DNC_KP * 2 + 2 * 16 * DN_M * sizeof(float) + 1024;
+        static bool cl_attr = false;
+        if (!cl_attr) { CU(cudaFuncSetAttribute(k_chain_dense_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc)); cl_attr = true; }
+        k_chain_dense_cl<<<dim3(tiles * DNC_R, 2), DN_M * 4, smc, st>>>(B, T, K, c->PtT, c->Pt, c->pi0, c->dn_b,
+                                                                   c->dn_a, c->dn_r, c->dn_e);
+      } else {
+        k_chain_dense<<<dim3(tiles, 2), DN_M * DN_NS, smem, st>>>(B, T, K, KPd, c->PtT, c->Pt, c->pi0, c->dn_b,
+                                                         c->dn_a, c->dn_r, c->dn_e);
+      }
       LAUNCHED(c); }
     { PhaseTimer pt(c, PH_BACKWARD, st);
       k_marginals_tiled<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, K, c->dn_a, c->dn_r, c->dn_e, q, c->lt_ws,
