@@ -970,6 +970,22 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
     const int NB = c->nfeat - K;
     static const bool ffma_emit_stats = getenv("SVIHMM_DENSE_FFMA_EMIT_STATS") != nullptr;   // A/B switch, read once
     const bool tc_emit = !a.cat && NB <= ESD_NB && !ffma_emit_stats;
+    const int NP = (flags & SVIHMM_WRAP) ? T : T - 1;
+    const int TS = std::max(1, std::min(NP, 148 / tiles));
+    const int TSe = std::max(1, std::min(T, 148 / tiles));
+    // every CTA of the tensor-core kernels owns one split of the partials (no float atomics: the sums are
+    // run-to-run deterministic); unused (split, column block) combinations stay zero
+    const int nsd = std::max(tiles * TS, tc_emit ? tiles * TSe : (int)nsplit);
+    const size_t need_d = (size_t)nsd * K * c->nfeat;
+    if (need_d > c->cap_part) {
+      if (c->part_ws) CU(cudaFree(c->part_ws));
+      c->part_ws = nullptr; c->cap_part = 0;
+      CU(dalloc(&c->part_ws, need_d));
+      c->cap_part = need_d;
+      a.part = c->part_ws;
+    }
+    CU(cudaMemsetAsync(c->part_ws, 0, need_d * sizeof(float), st));
+    nsplit_fin = nsd;
     if (tc_emit) {
       const size_t needf = (size_t)tiles * T * NB * DN_M;
       if (needf > c->cap_dnf) {
@@ -979,13 +995,10 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
         CU(dalloc(&c->dn_fhi, needf)); CU(dalloc(&c->dn_flo, needf));
         c->cap_dnf = needf;
       }
-      nsplit_fin = 1;
-      CU(cudaMemsetAsync(c->part_ws, 0, (size_t)K * c->nfeat * sizeof(float), st));
       k_dense_tile_feat<<<dim3(T, tiles), DN_M, 0, st>>>(B, T, D, NB, a.diag, obs, dtype, mask, starts,
                                                         reinterpret_cast<__nv_bfloat16*>(c->dn_fhi),
                                                         reinterpret_cast<__nv_bfloat16*>(c->dn_flo));
       LAUNCHED(c);
-      const int TSe = std::max(1, std::min(T, 148 / tiles));
       const size_t smem_e = (size_t)TSD_SLOT + 2 * (size_t)ESD_NB * 256 + 1024;
       CU(cudaFuncSetAttribute(k_emit_stats_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
       k_emit_stats_dense<<<dim3(tiles, TSe), 256, smem_e, st>>>(T, K, KPd, NB, TSe, reinterpret_cast<const __nv_bfloat16*>(q16),
@@ -995,10 +1008,7 @@ static int stats_generic_phase(svihmm_ctx* c, const void* obs, int dtype, const 
       LAUNCHED(c);
     } else {
       launch_stats(q, q, K, c->nfeat, 0);
-      CU(cudaMemset2DAsync(c->part_ws, (size_t)c->nfeat * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)nsplit * K, st));
     }
-    const int NP = (flags & SVIHMM_WRAP) ? T : T - 1;
-    const int TS = std::max(1, std::min(NP, 148 / tiles));
     const size_t smem = 3 * (size_t)TSD_SLOT + 1024;
     CU(cudaFuncSetAttribute(k_tran_stats_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (NP > 0) {

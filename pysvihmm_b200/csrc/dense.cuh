@@ -273,8 +273,8 @@ k_marginals_tiled(int B, int T, int K, const float* __restrict__ alphaT, const f
 // K-major tcgen05 operand: one pair is Q_t (M = K rows, two halves of 128) times Q_{t+1} (N = K rows) over
 // 128 windows = 16 tcgen05.mma of 128 x KP x 16, accumulated in TENSOR MEMORY across all pairs of the CTA
 // (2 x KP float32 columns).  grid (tiles, TS): a CTA owns pairs [p0, p1) of one tile; three 64 KB
-// operand slots (Q_t, Q_{t+1}, Q_{t+2} in flight by cp.async).  The epilogue adds the accumulators
-// to split 0 of the k_stats partials (float atomics), summed in float64 by k_stats_finalize.
+// operand slots (Q_t, Q_{t+1}, Q_{t+2} in flight by cp.async).  The epilogue stores the accumulators
+// into the CTA's own split of the k_stats partials, summed in float64 and fixed order by k_stats_finalize.
 #define TSD_SLOT 65536
 __global__ void __launch_bounds__(256)
 k_tran_stats_dense(int T, int K, int KP, int NP, int TS, const __nv_bfloat16* __restrict__ q16,
@@ -352,6 +352,9 @@ k_tran_stats_dense(int T, int K, int KP, int NP, int TS, const __nv_bfloat16* __
                    : "=r"(ok) : "r"(dn_smem(&bar)), "r"(phase) : "memory");
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // every CTA owns one split of the partials (plain stores; k_stats_finalize sums the splits in a fixed order in
+  // float64: run-to-run deterministic, no float atomics)
+  float* pout = part + (size_t)(blockIdx.x * gridDim.y + blockIdx.y) * K * N;
   // epilogue: warp (wp & 3) owns TMEM lanes 32 (wp & 3) .. +31; the two warp groups alternate 32-column chunks
   const int wq = wp & 3, wh = wp >> 2;
   for (int h = 0; h < MH; ++h) {
@@ -369,7 +372,7 @@ k_tran_stats_dense(int T, int K, int KP, int NP, int TS, const __nv_bfloat16* __
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = c32 * 32 + j;
-          if (col < K) atomicAdd(part + (size_t)row * N + col, __uint_as_float(a[j]));
+          if (col < K) pout[(size_t)row * N + col] = __uint_as_float(a[j]);
         }
     }
   }
@@ -490,6 +493,7 @@ k_emit_stats_dense(int T, int K, int KP, int NB, int TS, const __nv_bfloat16* __
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  float* pout = part + (size_t)(blockIdx.x * gridDim.y + blockIdx.y) * K * N;     // this CTA's split (see k_tran_stats_dense)
   const int wq = wp & 3, wh = wp >> 2;
   for (int h = 0; h < MH; ++h) {
     const int row = h * 128 + wq * 32 + lane;
@@ -506,7 +510,7 @@ k_emit_stats_dense(int T, int K, int KP, int NB, int TS, const __nv_bfloat16* __
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = c32 * 32 + j;
-          if (col < NB) atomicAdd(part + (size_t)row * N + col0 + col, __uint_as_float(a[j]));
+          if (col < NB) pout[(size_t)row * N + col0 + col] = __uint_as_float(a[j]);
         }
     }
   }
