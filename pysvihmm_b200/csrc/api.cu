@@ -329,7 +329,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
       const size_t gsm = gth_cluster_smem(K);
       static bool gc_attr = false;
       if (!gc_attr) { CU(cudaFuncSetAttribute(k_gth_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gth_cluster_smem(GC_KMAX))); gc_attr = true; }
-      k_gth_cluster<<<GC_CTAS, GC_NT, gsm, st>>>(K, c->lu, c->vinit, c->pi0);
+      k_gth_cluster<<<GC_CTAS, GC_NT, gsm, st>>>(K, c->lu, c->W, c->rowsum, c->Pt, c->PtT, c->vinit, c->pi0);
       LAUNCHED(c);
     }
   }

@@ -353,10 +353,11 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
     for (int idx = tid; idx < KK; idx += nt) {
       const int i = idx / K, j = idx - i * K;
       const double w = a.W[idx];
+      if (!inwarp) G[idx] = w / a.rowsum[i];
+      if (a.gth_ext) continue;                               // k_gth_cluster does the transforms on 8 CTAs
       const float v = (float)dexp_ni(digamma_fast(w + SVIHMM_EPS) - digamma_fast(a.rowsum[i] + SVIHMM_EPS));
       a.Pt[idx] = v;
       a.PtT[j * K + i] = v;
-      if (!inwarp) G[idx] = w / a.rowsum[i];
     }
   }
   GSYNC();

@@ -13,7 +13,8 @@
 //   so the result is componentwise accurate as before.
 //   back-substitution: pi[0] = 1, pi[j] += pi[i] G[i][j] row by row on warp 0 of CTA 0, the rows read through
 //   DSMEM four ahead; then the L2 normalisation, |.| and the digamma transform (pi0_section), as in block 0 of
-//   k_global_step, which skips all of this when a.gth_ext is set.
+//   k_global_step, which skips all of this when a.gth_ext is set - and leaves the digamma transforms of the
+//   transition matrix (Pt, PtT) to the 4096 threads of this kernel.
 #pragma once
 #include <cooperative_groups.h>
 #include "global.cuh"
@@ -28,7 +29,8 @@ __host__ __device__ inline size_t gth_cluster_smem(int K) {
 }
 
 __global__ void __cluster_dims__(GC_CTAS, 1, 1) __launch_bounds__(GC_NT, 1)
-k_gth_cluster(const int K, const double* __restrict__ G, double* __restrict__ vinit, float* __restrict__ pi0) {
+k_gth_cluster(const int K, const double* __restrict__ G, const double* __restrict__ W, const double* __restrict__ rowsum,
+              float* __restrict__ Pt, float* __restrict__ PtT, double* __restrict__ vinit, float* __restrict__ pi0) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) double gcs[];
@@ -41,6 +43,18 @@ k_gth_cluster(const int K, const double* __restrict__ G, double* __restrict__ vi
   for (int l = wp; l < nr; l += nw) {
     const int i = l * GC_CTAS + rank;
     for (int j = lane; j < K; j += 32) rows[(size_t)l * K + j] = i < K ? G[(size_t)i * K + j] : 0.0;
+  }
+  // P = exp(psi(W) - psi(rowsum)) (hmmsgd_metaobs.py:503-504) and its transpose: K^2 digamma pairs over the 4096
+  // threads of the cluster instead of the 512 of block 0 of k_global_step (0.24 ms there at K = 256)
+  {
+    const int KK = K * K;
+#pragma unroll 1
+    for (int idx = rank * GC_NT + tid; idx < KK; idx += GC_CTAS * GC_NT) {
+      const int i = idx / K, j = idx - i * K;
+      const float v = (float)dexp_ni(digamma_fast(W[idx] + SVIHMM_EPS) - digamma_fast(rowsum[i] + SVIHMM_EPS));
+      Pt[idx] = v;
+      PtT[j * K + i] = v;
+    }
   }
   cluster.sync();
 #pragma unroll 1
