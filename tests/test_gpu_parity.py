@@ -522,6 +522,30 @@ def test_host_call_equals_device_call():
         eng.close()
 
 
+@pytest.mark.parametrize("D,T,dt", [(8, 300, np.float32), (3, 50, np.float32), (6, 171, np.float64), (32, 129, np.float32)])
+def test_window_gather_paths(D, T, dt):
+    """The host -> device window gather of svihmm_estep_host: the bulk-copy engine (rows that are 16-byte multiples;
+    windows of several 4 KB pieces with a ragged last piece, (8, 300) = 9600 bytes, (32, 129) = 16512 bytes, and a
+    float64 series) and the load/store fallback (12-byte rows), with mask bytes: identical marginals, statistics to
+    round-off against the HBM-resident series."""
+    from pysvihmm_b200 import _lib as L
+    K, B = 6, 19
+    p = make_random_problem(seed=D * 100 + T, K=K, D=D, T_full=3000, kind="niw_diag", miss=0.1)
+    obs = p["obs"].astype(dt)
+    starts = np.random.RandomState(2).randint(0, 3000 - T + 1, B)
+    starts[0], starts[-1] = 0, 3000 - T
+    eng = _engine(K, D, "niw_diag")
+    eng.set_series(obs, p["mask"])
+    eng.set_series_streamed(obs, p["mask"])
+    eng.set_prior(p["prior_tran"], pack_emit_np(p["prior_emit"]))
+    eng.set_globals(p["var_tran"], pack_emit_np(p["emit"]))
+    vx, stats = eng.estep(starts, T, flags=L.WRAP | L.ADD_PRIOR | L.MASK_LL)
+    vxh, sh = eng.estep_host(starts, T, flags=L.WRAP | L.ADD_PRIOR | L.MASK_LL, want_var_x=True)
+    assert np.array_equal(vx.cpu().numpy(), vxh)
+    np.testing.assert_allclose(stats.cpu().numpy(), sh, rtol=1e-12, atol=1e-12)
+    eng.close()
+
+
 def test_streamed_step_equals_device_step():
     """svihmm_estep_streamed / svihmm_svi_step_host (host series, double-buffered window gather with
     the next minibatch announced one step ahead) follow the same trajectory as svihmm_estep +
