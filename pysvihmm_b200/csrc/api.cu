@@ -1523,12 +1523,15 @@ k_gather_windows(int B, int T, int rowbytes, const uint8_t* __restrict__ src, co
 }
 // The same gather on the bulk-copy engine: ONE thread per CTA moves 4 KB pieces host -> shared memory
 // (cp.async.bulk over PCIe, completion on an mbarrier) -> staging buffer (cp.async.bulk shared -> global),
-// two 4 KB slots per CTA (8 KB of shared memory: the CTAs fit beside two E-step CTAs on an SM), 32 CTAs.  46 GB/s with 8 threads in all against 36-44 GB/s for the
-// load/store kernel with 2048 threads (scripts/probes/tma_gather_probe.cu), and no thread slots or issue
-// bandwidth are taken from the E-step kernel running beside it.  Lanes 1..31 gather the mask bytes.
+// a ring of 4 slots per CTA, 8 CTAs: 128 KB in flight, 46 GB/s stand-alone with 8 threads in all against 36-44 GB/s
+// for the load/store kernel with 2048 threads (scripts/probes/tma_gather_probe.cu).  Beside the E-step kernel the
+// gather settles at ~39 GB/s whatever the geometry (4.2 MB in 105-108 us); what the geometry decides is how much the
+// gather CTAs disturb the placement of the E-step CTAs (two of those fill an SM's shared memory): measured
+// end to end at c2, CTAs x slots: 32 x 2 -> 2.22 M E-steps/s (E-step kernel 80 us), 64 x 2 -> 1.63 M (107 us),
+// 16 x 2 -> 2.37 M, 8 x 4 -> 2.43 M (66 us).  Lanes 1..31 gather the mask bytes.
 #define GB_PIECE 4096
-#define GB_SLOTS 2
-#define GB_CTAS 32
+#define GB_SLOTS 4
+#define GB_CTAS 8
 __global__ void __launch_bounds__(32)
 k_gather_bulk(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const uint8_t* __restrict__ msrc,
               const int64_t* __restrict__ starts, uint8_t* __restrict__ dst, uint8_t* __restrict__ mdst,
@@ -1584,9 +1587,10 @@ k_gather_bulk(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const
 static void launch_gather(int B, int T, int rowbytes, const uint8_t* src, const uint8_t* msrc, const int64_t* starts,
                           uint8_t* dst, uint8_t* mdst, int64_t* dense_starts, cudaStream_t st) {
   static const bool zc = getenv("SVIHMM_GATHER_ZEROCOPY") != nullptr;    // A/B switch, read once
+  static const int gb_ctas = getenv("SVIHMM_GATHER_CTAS") ? std::max(1, atoi(getenv("SVIHMM_GATHER_CTAS"))) : GB_CTAS;
   const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
   if (vec16 && !zc && ((uintptr_t)dst % 16) == 0)
-    k_gather_bulk<<<GB_CTAS, 32, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts);
+    k_gather_bulk<<<gb_ctas, 32, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts);
   else
     k_gather_windows<<<gather_ctas(), 256, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts, vec16);
 }
