@@ -1535,41 +1535,46 @@ k_gather_windows(int B, int T, int rowbytes, const uint8_t* __restrict__ src, co
 __global__ void __launch_bounds__(32)
 k_gather_bulk(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const uint8_t* __restrict__ msrc,
               const int64_t* __restrict__ starts, uint8_t* __restrict__ dst, uint8_t* __restrict__ mdst,
-              int64_t* __restrict__ dense_starts) {
-  __shared__ __align__(128) uint8_t ring[GB_SLOTS * GB_PIECE];
+              int64_t* __restrict__ dense_starts, const int nslots, const int piece) {
+  extern __shared__ __align__(128) uint8_t ring[];          // [nslots][piece]
   __shared__ __align__(8) unsigned long long full[GB_SLOTS];
   const size_t wbytes = (size_t)T * rowbytes;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GB_SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(full + s)) : "memory");
+    for (int s = 0; s < nslots; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(full + s)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int ppw = (int)((wbytes + GB_PIECE - 1) / GB_PIECE);
+    const int ppw = (int)((wbytes + piece - 1) / piece);
     const long long np = (long long)B * ppw;
     const int mine = np > (long long)blockIdx.x ? (int)((np - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
     int issued = 0, done = 0;
     while (done < mine) {
-      while (issued < mine && issued < done + GB_SLOTS) {
+      while (issued < mine && issued < done + nslots) {
         // slot reuse: every store issued so far has finished READING its slot
-        if (issued >= GB_SLOTS) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (issued >= nslots) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         const long long p = blockIdx.x + (long long)issued * gridDim.x;
-        const int b = (int)(p / ppw), k = (int)(p - (long long)b * ppw), s = issued % GB_SLOTS;
-        const unsigned nb = (unsigned)min((size_t)GB_PIECE, wbytes - (size_t)k * GB_PIECE);
+        const int b = (int)(p / ppw), k = (int)(p - (long long)b * ppw), s = issued % nslots;
+        const unsigned nb = (unsigned)min((size_t)piece, wbytes - (size_t)k * piece);
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(full + s);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"((uint32_t)__cvta_generic_to_shared(ring + s * GB_PIECE)),
-                       "l"(src + (size_t)starts[b] * rowbytes + (size_t)k * GB_PIECE), "r"(nb), "r"(bar) : "memory");
+                     ::"r"((uint32_t)__cvta_generic_to_shared(ring + s * piece)),
+                       "l"(src + (size_t)starts[b] * rowbytes + (size_t)k * piece), "r"(nb), "r"(bar) : "memory");
         ++issued;
       }
-      const int s = done % GB_SLOTS; const unsigned par = (done / GB_SLOTS) & 1;
-      unsigned ok = 0;
-      while (!ok)
+      const int s = done % nslots; const unsigned par = (done / nslots) & 1;
+      // the piece is microseconds away: sleep between polls (a spinning thread takes issue slots from the E-step CTA
+      // that shares the SM, and a persistent kernel is as slow as its slowest CTA)
+      for (;;) {
+        unsigned ok = 0;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(full + s)), "r"(par) : "memory");
+        if (ok) break;
+        __nanosleep(250);
+      }
       const long long p = blockIdx.x + (long long)done * gridDim.x;
       const int b = (int)(p / ppw), k = (int)(p - (long long)b * ppw);
-      const unsigned nb = (unsigned)min((size_t)GB_PIECE, wbytes - (size_t)k * GB_PIECE);
+      const unsigned nb = (unsigned)min((size_t)piece, wbytes - (size_t)k * piece);
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                   ::"l"(dst + (size_t)b * wbytes + (size_t)k * GB_PIECE), "r"((uint32_t)__cvta_generic_to_shared(ring + s * GB_PIECE)), "r"(nb) : "memory");
+                   ::"l"(dst + (size_t)b * wbytes + (size_t)k * piece), "r"((uint32_t)__cvta_generic_to_shared(ring + s * piece)), "r"(nb) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       ++done;
     }
@@ -1585,12 +1590,16 @@ k_gather_bulk(int B, int T, int rowbytes, const uint8_t* __restrict__ src, const
 }
 // windows out of the mapped host series: the bulk-copy engine when rows are 16-byte multiples, else loads/stores
 static void launch_gather(int B, int T, int rowbytes, const uint8_t* src, const uint8_t* msrc, const int64_t* starts,
-                          uint8_t* dst, uint8_t* mdst, int64_t* dense_starts, cudaStream_t st) {
+                          uint8_t* dst, uint8_t* mdst, int64_t* dense_starts, cudaStream_t st, bool small_smem) {
   static const bool zc = getenv("SVIHMM_GATHER_ZEROCOPY") != nullptr;    // A/B switch, read once
-  static const int gb_ctas = getenv("SVIHMM_GATHER_CTAS") ? std::max(1, atoi(getenv("SVIHMM_GATHER_CTAS"))) : GB_CTAS;
+  static const int env_ctas = getenv("SVIHMM_GATHER_CTAS") ? std::max(1, atoi(getenv("SVIHMM_GATHER_CTAS"))) : 0;
+  // beside kernels that fill an SM's shared memory on their own (the persistent tcgen05 kernels: 212-226 KB) only a
+  // small CTA can be placed: 2 slots of 2 KB on four times the CTAs; else 4 slots of 4 KB on GB_CTAS CTAs (see above)
+  const int nslots = small_smem ? 2 : GB_SLOTS, piece = small_smem ? GB_PIECE / 2 : GB_PIECE;
+  const int gb_ctas = env_ctas ? env_ctas : (small_smem ? 4 * GB_CTAS : GB_CTAS);
   const int vec16 = (rowbytes % 16 == 0) && (((uintptr_t)src) % 16 == 0);
   if (vec16 && !zc && ((uintptr_t)dst % 16) == 0)
-    k_gather_bulk<<<gb_ctas, 32, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts);
+    k_gather_bulk<<<gb_ctas, 32, (size_t)nslots * piece, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts, nslots, piece);
   else
     k_gather_windows<<<gather_ctas(), 256, 0, st>>>(B, T, rowbytes, src, msrc, starts, dst, mdst, dense_starts, vec16);
 }
@@ -1628,7 +1637,7 @@ extern "C" int svihmm_estep_host(svihmm_ctx* c, const int64_t* starts_host, int 
     CU(cudaMemcpyAsync(c->stage_src, starts_host, sizeof(int64_t) * B, cudaMemcpyHostToDevice, st));
     PhaseTimer pt(c, PH_GATHER, st);
     launch_gather(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev, has_mask ? c->hmask_dev : nullptr, c->stage_src,
-                  (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, st);
+                  (uint8_t*)c->stage_obs, c->stage_mask, c->stage_starts, st, c->K > 32);
     LAUNCHED(c);
   } else {
     // CPU gather into pinned staging, one H2D copy
@@ -1760,7 +1769,7 @@ static int sg_gather(svihmm_ctx* c, int s, const int64_t* starts_host, int B, in
   // the GPU gathers the windows itself out of the mapped host series (one small persistent kernel)
   CU(cudaMemcpyAsync(c->sg_src[s], c->sg_pin_starts[s], sizeof(int64_t) * B, cudaMemcpyHostToDevice, q));
   launch_gather(B, T, (int)rowbytes, (const uint8_t*)c->hobs_dev, has_mask ? c->hmask_dev : nullptr, c->sg_src[s],
-                (uint8_t*)c->sg_obs[s], c->sg_mask[s], c->sg_dense[s], q);
+                (uint8_t*)c->sg_obs[s], c->sg_mask[s], c->sg_dense[s], q, c->K > 32);
   LAUNCHED(c);
   c->sg_valid[s] = 1; c->sg_T[s] = T; c->sg_nB[s] = B;
   return SVIHMM_OK;
