@@ -142,6 +142,13 @@ k_chain_dense_cl(int B, int T, int K, const float* __restrict__ Pfwd, const floa
   // release of barrier.cluster waits for every earlier store of the thread to be performed, and with the 16 global
   // stores right in front of it every step paid their L2 round trip (measured: 11 k cycles per step).
   float pend[16]; float* pend_ot = nullptr; int pend_E = 0; int* pend_Ep = nullptr;
+  // b of the NEXT step is loaded one whole step ahead (ncu: the kernel sat on long-scoreboard stalls, 7.4 warps per
+  // issue, at the first use of b when it was loaded under the MMAs of the same step)
+  float bq[16];
+  if (T > 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) bq[j] = (k0 + j < K) ? bw[((size_t)(t + dt) * K + k0 + j) * DN_M] : 0.f;
+  }
   for (int s = 1; s < T; ++s) {
     t += dt;
     wait_recv((s - 1) & 1, ((s - 1) >> 1) & 1);        // the carried vectors of step s - 1 are complete in this CTA
@@ -178,9 +185,6 @@ k_chain_dense_cl(int B, int T, int K, const float* __restrict__ Pfwd, const floa
       for (int j = 0; j < 16; ++j) if (k0 + j < K) pend_ot[(size_t)(k0 + j) * DN_M] = pend[j];
       if (pend_Ep) *pend_Ep = pend_E;
     }
-    float bq[16];                                      // in flight under the MMAs
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bq[j] = (k0 + j < K) ? bt[(size_t)(k0 + j) * DN_M] : 0.f;
     uint32_t ok = 0;
     while (!ok)
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -196,6 +200,10 @@ k_chain_dense_cl(int B, int T, int K, const float* __restrict__ Pfwd, const floa
       v[j] = m * bq[j];
       pend[j] = fwd ? v[j] : m;
       if (j & 1) s1 += v[j]; else s0 += v[j];
+    }
+    if (s + 1 < T) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bq[j] = (k0 + j < K) ? bw[((size_t)(t + dt) * K + k0 + j) * DN_M] : 0.f;
     }
     pend_ot = ot; pend_E = E; pend_Ep = (fwd && rank == 0 && part == 0) ? Ep + (size_t)t * DN_M : nullptr;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
