@@ -187,13 +187,16 @@ k_mix_combine(int B, int T, int K, int C, int D, const void* __restrict__ obs, i
     for (int c = 0; c < C; ++c) rp[c] = 0.f;
     return;
   }
+  // The differences to the maximum are formed in float64; their exponentials and the logarithm of the sum
+  // (in [1, C]) in float32: |error of ll| < 3e-7, far below what moves a marginal by 1e-5, and the float64
+  // exp / log (150 / 290 cycles each, 2 C + 1 per thread) were most of this kernel.
   double m = -INFINITY;
   for (int c = 0; c < C; ++c) m = fmax(m, lp[c] + ep[c]);
-  double s = 0.0;
-  for (int c = 0; c < C; ++c) s += exp(lp[c] + ep[c] - m);
-  const double l = m + log(s);
-  ll[e] = l;
-  for (int c = 0; c < C; ++c) rp[c] = (float)exp(lp[c] + ep[c] - l);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += __expf((float)(lp[c] + ep[c] - m));
+  const float ls = __logf(s), inv = 1.f / s;
+  ll[e] = m + (double)ls;
+  for (int c = 0; c < C; ++c) rp[c] = __expf((float)(lp[c] + ep[c] - m)) * inv;
 }
 
 // statistics weights of the components: wq[r][kc] = q[r][k] * resp[r][kc]
