@@ -9,7 +9,7 @@
 //             side of the last pair) and the 128 x D block of observations of the tile into shared
 //             memory (tensor maps over the (B*T, K) marginals and over the (T_full, D) series; the
 //             window start is a runtime coordinate), completion on mbarriers
-//   operands  all 256 threads turn them into bf16 hi + lo pairs (v = hi + lo to 2^-17) in the K-major
+//   operands  all 512 threads turn them into bf16 hi + lo pairs (v = hi + lo to 2^-17) in the K-major
 //             SWIZZLE_128B layout of tcgen05: B operand = q^T (64 states x 128 rows), A operand = one
 //             M-tile of 128 feature rows x 128 rows; two A buffers, so the generation of the next M-tile
 //             overlaps the MMAs of the current one
@@ -27,7 +27,7 @@
 #include <cuda.h>
 #include "dense.cuh"
 
-#define STC_NT 256
+#define STC_NT 512            // 16 warps: the operand generation is issue-latency bound (ncu: 46 % of the issue slots with 8 warps)
 
 struct StcArgs {
   int B, T, K, D, NF, diag, wrap, ntpw, nmt, ntiles;
@@ -173,7 +173,7 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     stc_wait(full_x, it & 1);
     {
       const int64_t g0 = a.starts[w] + t0;
-      for (int r = wp * (RT / 8); r < (wp + 1) * (RT / 8); ++r) {
+      for (int r = wp * (RT / (STC_NT / 32)); r < (wp + 1) * (RT / (STC_NT / 32)); ++r) {
         const bool isn = lane < D ? isnan(xs[r * D + lane]) : false;
         const unsigned any = __ballot_sync(0xffffffffu, isn);
         if (lane == 0) wrow[r] = (r < nrow && !any && !(a.mask && a.mask[g0 + r])) ? 1.f : 0.f;
@@ -184,13 +184,14 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const unsigned ab = gen & 1, use = gen >> 1;
       if (use > 0) { stc_wait(mma_done + ab, (use - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
       uint8_t* Ah = sA + (size_t)ab * 2 * L.Asz; uint8_t* Al = Ah + L.Asz;
-      // ---- A operand of M-tile m: thread = (feature row fl, half of the chunks of 8 rows)
+      // ---- A operand of M-tile m: thread = (feature row fl, one part of the chunks of 8 rows)
       {
-        const int fl = tid & 127, half = tid >> 7, f = 128 * m + fl;
+        constexpr int NPART = STC_NT / 128;
+        const int fl = tid & 127, part = tid >> 7, f = 128 * m + fl;
         const int ka = fa[f], kb = fb[f];
 #pragma unroll 2
-        for (int c8 = 0; c8 < nchunk / 2; ++c8) {
-          const int c = half * (nchunk / 2) + c8;
+        for (int c8 = 0; c8 < nchunk / NPART; ++c8) {
+          const int c = part * (nchunk / NPART) + c8;
           float v[8];
           if (ka == 255) {
 #pragma unroll
@@ -258,7 +259,7 @@ k_stats_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     float* part = a.part + (size_t)blockIdx.x * Kout * NF;
     const int quarter = wp & 3;
     for (int m = 0; m < a.nmt; ++m) {
-      for (int cc = wp >> 2; cc < (N + 31) / 32; cc += 2) {       // 32-column chunks, two warps per lane quarter
+      for (int cc = wp >> 2; cc < (N + 31) / 32; cc += STC_NT / 128) {       // 32-column chunks, STC_NT / 128 warps per lane quarter
         uint32_t v[32];
         const uint32_t ta = tm + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * N + cc * 32);
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
