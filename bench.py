@@ -120,12 +120,30 @@ class ClockSampler(object):
                 "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(rows)}
 
 
+def nvlink_kib(gpu_index):
+    """Cumulative NVLink payload counters of this GPU summed over its links (NVML field values, KiB), or None:
+    read before and after the timed region at N > 1, the difference is what the fused peer exchange moved."""
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        v = N.nvmlDeviceGetFieldValues(h, [(N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                           (N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        if any(x.nvmlReturn != 0 for x in v):
+            return None
+        return [int(x.value.ullVal) for x in v]
+    except Exception:       # noqa: BLE001
+        return None
+
+
 def ncu_traffic(kernel):
     """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_c2_pipe_ncu_summary.txt), or None when there is no capture for this kernel/config."""
+    (profiles/r2_c2_pipe_ncu_summary.txt), or None when there is no capture for this kernel/config."""
     if kernel != "fused":
         return None
-    p = os.path.join(ROOT, "profiles", "r1_c2_pipe_ncu_summary.txt")
+    p = os.path.join(ROOT, "profiles", "r2_c2_pipe_ncu_summary.txt")
     try:
         tot, unit = 0.0, {"byte": 1., "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(p):
@@ -490,9 +508,11 @@ def run_ours(args, cfg):
             if go.item() < 0.5:
                 return out
 
+    nvl0 = nvlink_kib(local) if (world > 1 and rank == 0) else None
     tw0 = time.perf_counter()
     blocks = timed_blocks(step, args.min_seconds)
     tw1 = time.perf_counter()
+    nvl1 = nvlink_kib(local) if (world > 1 and rank == 0) else None
     launches = (eng.launch_count() - l0) // len(blocks)
     clk = clocks.stop(tw0, tw1) if rank == 0 else None
     eng.set_profiling(True)
@@ -670,6 +690,13 @@ def run_ours(args, cfg):
             line["b_sweep"] = b_sweep
         if xr is not None:
             line.update(xr)
+        if nvl0 is not None and nvl1 is not None:
+            # rank 0's NVLink payload counters over the timed region (NVML, all links): what the peer exchange moved
+            nsteps = len(blocks) * args.steps
+            line["nvlink"] = {"source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU, difference over the timed region",
+                              "tx_bytes_per_step": (nvl1[0] - nvl0[0]) * 1024.0 / nsteps,
+                              "rx_bytes_per_step": (nvl1[1] - nvl0[1]) * 1024.0 / nsteps,
+                              "statistics_bytes_per_rank": slen * 8, "steps_counted": nsteps}
         if extras:
             line["extra_configs"] = extras
         if cfg.get("bf16_dense"):
