@@ -121,21 +121,33 @@ class ClockSampler(object):
 
 
 def nvlink_kib(gpu_index):
-    """Cumulative NVLink payload counters of this GPU summed over its links (NVML field values, KiB), or None:
-    read before and after the timed region at N > 1, the difference is what the fused peer exchange moved."""
+    """Cumulative NVLink payload counters of this GPU summed over its links (NVML field values, KiB) as
+    [tx, rx], or a string saying why they could not be read: taken before and after the timed region at
+    N > 1, the difference is what the fused peer exchange moved."""
     try:
         import pynvml as N
         N.nvmlInit()
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         idx = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
         h = N.nvmlDeviceGetHandleByIndex(idx)
-        v = N.nvmlDeviceGetFieldValues(h, [(N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
-                                           (N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
-        if any(x.nvmlReturn != 0 for x in v):
-            return None
-        return [int(x.value.ullVal) for x in v]
-    except Exception:       # noqa: BLE001
-        return None
+        ids = (N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, N.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX)
+
+        def val(x):
+            t = int(x.valueType)        # NVML_VALUE_TYPE_*: 0 double, 1 uint, 2 ulong, 3 ulonglong, 4 slonglong
+            return int({0: x.value.dVal, 1: x.value.uiVal, 2: x.value.ulVal, 3: x.value.ullVal,
+                        4: x.value.sllVal}.get(t, x.value.ullVal))
+        v = N.nvmlDeviceGetFieldValues(h, [(i, 0xFFFFFFFF) for i in ids])
+        if all(int(x.nvmlReturn) == 0 for x in v):
+            return [val(x) for x in v]
+        rc_all = [int(x.nvmlReturn) for x in v]
+        tot, seen = [0, 0], 0
+        for link in range(18):          # per-link scope, summed
+            v = N.nvmlDeviceGetFieldValues(h, [(i, link) for i in ids])
+            if all(int(x.nvmlReturn) == 0 for x in v):
+                tot[0] += val(v[0]); tot[1] += val(v[1]); seen += 1
+        return tot if seen else "nvmlDeviceGetFieldValues: all-links rc %s, no per-link counter readable" % rc_all
+    except Exception as e:       # noqa: BLE001
+        return "nvml: %r" % (e,)
 
 
 def ncu_traffic(kernel):
@@ -690,7 +702,9 @@ def run_ours(args, cfg):
             line["b_sweep"] = b_sweep
         if xr is not None:
             line.update(xr)
-        if nvl0 is not None and nvl1 is not None:
+        if isinstance(nvl0, str) or isinstance(nvl1, str):
+            line["nvlink"] = {"unavailable": nvl0 if isinstance(nvl0, str) else nvl1}
+        elif nvl0 is not None and nvl1 is not None:
             # rank 0's NVLink payload counters over the timed region (NVML, all links): what the peer exchange moved
             nsteps = len(blocks) * args.steps
             line["nvlink"] = {"source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX of rank 0's GPU, difference over the timed region",
