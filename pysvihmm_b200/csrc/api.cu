@@ -297,6 +297,7 @@ static int run_global(svihmm_ctx* c, int mode, const double* stats, double lrate
   const int nblk = ga.diag ? std::max(1, std::min(KE, (KE * D + 255) / 256)) : KE;   // full / categorical: one block per component
   size_t smem = (2 * (size_t)K + 2) * sizeof(double);
   if (!ga.diag && !ga.cat) smem = std::max(smem, (2 * (size_t)D * D + 3 * (size_t)D) * sizeof(double));
+  if (K > 32 && K <= GTH_SMEM_KMAX) smem = std::max(smem, (2 * (size_t)K + 2 + (size_t)K * K) * sizeof(double));   // elimination matrix of block 0
   if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_global_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (peers) {
     ga.world = c->comm_world; ga.rank = c->comm_rank; ga.seq = ++c->comm_seq; ga.red_out = c->stage_stats;

@@ -101,6 +101,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 __device__ __forceinline__ void st_peer(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+#define GTH_SMEM_KMAX 64
 struct CommRange { size_t lo, hi; };
 __device__ void comm_exchange(const GlobalArgs& a, const CommRange* rg, const int nrg) {
   const int tid = threadIdx.x, nth = blockDim.x, W = a.world, me = a.rank;
@@ -142,40 +143,42 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
 // Step n: every warp forms s = sum_{j<n} G[n][j] (same order in all warps), then for its rows
 // i = wp, wp + nw, ...: f = G[i][n] / s (kept for the back-substitution), G[i][j] += f G[n][j], j < n.
 // The step is bound by the L2 round trip of the rows, so R rows of a warp are in flight together.
-template <int R>
+// U: 32-column groups held per lane (K <= 32 U on the register path; U = 2 for K <= 64 keeps the step at ~70
+// instead of ~250 warp instructions: the predicated-off groups of the U = 8 form still take issue slots)
+template <int R, int U>
 __device__ __noinline__ void gth_block(const int K, double* __restrict__ G) {
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, nw = blockDim.x >> 5;
 #pragma unroll 1
   for (int n = K - 1; n >= 1; --n) {
     const double* rown = G + (size_t)n * K;
     double s = 0.0;
-    if (K <= 256) {
-      double rn[8];
+    if (K <= 32 * U) {
+      double rn[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; rn[u] = j < n ? rown[j] : 0.0; }
+      for (int u = 0; u < U; ++u) { const int j = lane + 32 * u; rn[u] = j < n ? rown[j] : 0.0; }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) if (lane + 32 * u < n) s += rn[u];
+      for (int u = 0; u < U; ++u) if (lane + 32 * u < n) s += rn[u];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const double rinv = 1.0 / s;
 #pragma unroll 1
       for (int i0 = wp; i0 < n; i0 += R * nw) {
         double* rp[R];
-        double g[R], v[R][8];
+        double g[R], v[R][U];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int i = i0 + r * nw;
           rp[r] = G + (size_t)(i < n ? i : i0) * K;      // rows beyond n: re-read row i0, never stored
           g[r] = rp[r][n];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; v[r][u] = j < n ? rp[r][j] : 0.0; }
+          for (int u = 0; u < U; ++u) { const int j = lane + 32 * u; v[r][u] = j < n ? rp[r][j] : 0.0; }
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           g[r] *= rinv;
           if (i0 + r * nw < n) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { const int j = lane + 32 * u; if (j < n) rp[r][j] = fma(g[r], rn[u], v[r][u]); }
+            for (int u = 0; u < U; ++u) { const int j = lane + 32 * u; if (j < n) rp[r][j] = fma(g[r], rn[u], v[r][u]); }
           }
         }
         __syncwarp();
@@ -336,7 +339,9 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   GSYNC();
   GSTAMP(1);
   double* pi = sm;                                        // K + 1 doubles
-  double* G = a.gth;                                      // K*K doubles of scratch (K > 32 only)
+  // K*K doubles of scratch (K > 32 only): in shared memory up to K = 64 (32 KB; a censoring step is then a
+  // shared-memory round trip instead of an L2 round trip per row pass), in global memory (L2) beyond
+  double* G = (K > 32 && K <= GTH_SMEM_KMAX) ? sm + 2 * K + 2 : a.gth;
   const bool inwarp = !a.user_init && K <= 32;
   // the LAST warp of the block computes the stationary vector while the others do the digamma
   // transforms of the transition matrix
@@ -364,7 +369,8 @@ __device__ void global_tran_block(const GlobalArgs& a, double* sm) {
   GSTAMP(2);
   if (!a.user_init && !inwarp && !a.gth_ext) {
     // Grassmann-Taksar-Heyman: censor states K-1, K-2, ..., 1 (no subtractions)
-    gth_block<4>(K, G);
+    if (K <= 64) gth_block<4, 2>(K, G);
+    else gth_block<4, 8>(K, G);
     // pi[0] = 1; pi[j] = sum_{i<j} pi[i] G[i][j]: column j accumulates as the pi[i] become final
     if (wp == 0) {
 #pragma unroll 1
