@@ -157,3 +157,12 @@ def test_util_diagnostics_match_reference_fixture():
     assert np.isclose(kappa, float(g["n2m_kappa"])) and np.isclose(nu, float(g["n2m_nu"]))
     np.random.seed(73)
     assert np.allclose(util.mvnrand(g["kl_mu1"], g["kl_sig1"], size=5), g["mvn"], rtol=1e-13, atol=1e-15)
+
+
+def test_bench_nvlink_counters_degrade_to_a_reason():
+    """bench.py reads rank 0's NVLink payload counters around the timed region at N > 1; where NVML (or the
+    counters) are missing it must hand back a reason string, never raise (the pool's B200s answer
+    NOT_SUPPORTED, profiles/r2_nvlink_counters_unavailable.txt)."""
+    import bench
+    r = bench.nvlink_kib(0)
+    assert isinstance(r, str) or (isinstance(r, list) and len(r) == 2 and all(isinstance(x, int) for x in r))
